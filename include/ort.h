@@ -1,0 +1,250 @@
+/*
+ * ort.h -- C-ABI of the B200-native per-ray trace loop of OpticalRayTrace.
+ *
+ * This is the seam the reference's two OpenMP ray loops are replaced by
+ * (reference src/main.f90:90-109 "ring" loop, src/main.f90:127-162 "point" loop).
+ * Everything is `extern "C"`, every struct is plain-old-data made of double /
+ * int32_t / int64_t / uint64_t so it can be mirrored 1:1 by a Fortran
+ * `type, bind(C)` (fortran/ort_interface.f90), by ctypes, or by cgo.
+ *
+ * Conventions
+ *   - every entry point returns 0 on success and a negative ORT_E* code otherwise;
+ *     nothing in the library calls exit()/abort().  ort_last_error() gives the text.
+ *   - the caller owns all host buffers; the library owns device memory between
+ *     ort_init*() and ort_finalize().
+ *   - one host thread drives the library (the OpenMP region of the reference is gone).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry fails
+ *     with ORT_ENODEVICE.
+ *   - all lengths are metres, all reals fp64 (the reference is built with
+ *     -freal-4-real-8, reference src/Makefile:2).
+ */
+#ifndef ORT_H
+#define ORT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORT_VERSION 100
+
+/* detector: image(-200:200,-200:200,layer), reference src/imageMod.f90:23 */
+#define ORT_IMG_N 401
+#define ORT_IMG_HALF 200
+#define ORT_IMG_BINS (ORT_IMG_N * ORT_IMG_N)
+
+/* error codes */
+#define ORT_OK 0
+#define ORT_EINVAL (-1)    /* bad argument */
+#define ORT_ENODEVICE (-2) /* no CUDA device / library not initialised */
+#define ORT_ECUDA (-3)     /* CUDA runtime error (text in ort_last_error) */
+#define ORT_ENCCL (-4)     /* NCCL error or NCCL not loadable */
+#define ORT_EIO (-5)       /* file could not be read / written */
+#define ORT_EPARSE (-6)    /* malformed params file */
+#define ORT_ETRACE (-7)    /* the kernels hit one of the reference's `error stop` invariants;
+                              results are still returned, see status codes 18 and 24 */
+
+/* phases */
+#define ORT_PHASE_RING 1  /* reference src/main.f90:90-109 */
+#define ORT_PHASE_POINT 2 /* reference src/main.f90:127-162 */
+
+/* ort_job.flags */
+#define ORT_FLAG_FIX_OUTER_ELLIPSE 1 /* opt-in: outer ellipse wall uses (Ra,Rb), not the
+                                        reference's (Ra/2,Rb/2) (src/lens.f90:301) */
+#define ORT_FLAG_NO_REDUCE 2         /* rank mode: leave per-rank images un-reduced */
+#define ORT_FLAG_NO_COMPACTION 4     /* diagnostic: one-thread-per-ray kernel without the
+                                        warp-level live-ray compaction */
+
+/* ort_job.stop_after (explicit-ray entry point only): where pos_out/dir_out are sampled */
+#define ORT_STOP_NONE 0   /* full path, sampled at the image plane */
+#define ORT_STOP_SOURCE 1 /* after ring()/point() */
+#define ORT_STOP_BOTTLE 2 /* after glass_bottle%forward (point phase) */
+#define ORT_STOP_L2 3     /* after plano_convex%forward */
+#define ORT_STOP_L3 4     /* after achromatic_doublet%forward */
+
+/* Final state of a ray ("which stage killed it").  0 = counted in the image. */
+enum ort_status {
+    ORT_ST_BINNED = 0,
+    ORT_ST_BOTTLE_INNER_MISS = 1,    /* src/lens.f90:257-260 */
+    ORT_ST_CONTENTS_ABSORBED = 2,    /* src/lens.f90:270-274 */
+    ORT_ST_CONTENTS_BACKWARD = 3,    /* src/lens.f90:278-281 */
+    ORT_ST_BOTTLE_INNER_REFLECT = 4, /* src/lens.f90:293-297 */
+    ORT_ST_BOTTLE_OUTER_MISS = 5,    /* src/lens.f90:305-308 */
+    ORT_ST_WALL_ABSORBED = 6,        /* src/lens.f90:321-325 */
+    ORT_ST_WALL_BACKWARD = 7,        /* src/lens.f90:329-332 */
+    ORT_ST_BOTTLE_OUTER_REFLECT = 8, /* src/lens.f90:344-348 */
+    ORT_ST_L2_APERTURE = 9,          /* src/lens.f90:450-454 */
+    ORT_ST_L2_SPHERE_MISS = 10,      /* src/lens.f90:462-467 */
+    ORT_ST_L2_CURVED_REFLECT = 11,   /* src/lens.f90:475-479 */
+    ORT_ST_L3_IRIS_BEFORE = 12,      /* src/lens.f90:551-565 */
+    ORT_ST_L3_S1_MISS = 13,          /* src/lens.f90:568-572 */
+    ORT_ST_L3_APERTURE = 14,         /* src/lens.f90:576-580 */
+    ORT_ST_L3_S1_REFLECT = 15,       /* src/lens.f90:586-590 */
+    ORT_ST_L3_S2_MISS = 16,          /* src/lens.f90:595-599 */
+    ORT_ST_L3_S2_REFLECT = 17,       /* src/lens.f90:606-610 */
+    ORT_ST_L3_S3_MISS = 18,          /* src/lens.f90:617  `error stop "Help3"` */
+    ORT_ST_L3_S3_REFLECT = 19,       /* src/lens.f90:624-628 */
+    ORT_ST_L3_IRIS_AFTER = 20,       /* src/lens.f90:632-644 */
+    ORT_ST_NA_REJECT = 21,           /* src/imageMod.f90:42-44 */
+    ORT_ST_FAR = 22,                 /* src/imageMod.f90:48, plus non-finite positions */
+    ORT_ST_OFF_DETECTOR = 23,        /* src/imageMod.f90:52-54 */
+    ORT_ST_TAUINT_MISS = 24,         /* src/surfaces.f90:33-39 `error stop "no intersection"` */
+    ORT_ST_STOPPED = 25              /* explicit-ray mode: reached ort_job.stop_after alive */
+};
+#define ORT_NSTATUS 32
+/* statuses 1..20 and 24 are what the reference adds to rcount / pcount
+ * (src/optics_system.f90:32,42 and src/main.f90:150-151) */
+#define ORT_STATUS_IS_LOST(s) (((s) >= 1 && (s) <= 20) || (s) == 24)
+
+/* reference src/lens.f90:8-20 (type lens + plano_convex) */
+typedef struct {
+    double thickness, diameter, radius, fb, f, n1, n2, curve_radius;
+    double centre[3];
+    double flat_normal[3];
+} ort_plano;
+
+/* reference src/lens.f90:8-12,27-33 (type lens + achromatic_doublet) */
+typedef struct {
+    double thickness, diameter, radius, fb, f, n1, n2, n3;
+    double thickness1, thickness2, R1, R2, R3;
+    double centre1[3], centre2[3], centre3[3];
+} ort_doublet;
+
+/* reference src/lens.f90:40-48 (type glass_bottle) */
+typedef struct {
+    double nbottle, ncontents, thickness, radiusa, radiusb;
+    double mua_b, mus_b, mua_c, mus_c;
+    double centre[3];
+    int32_t ellipse, scatter_b, scatter_c, _pad;
+} ort_bottle;
+
+/* One optical configuration: what reference src/main.f90 holds in (bottle, L2, L3) plus the
+ * scalars its prologue derives from them (src/main.f90:51-70,81).  A batched launch traces
+ * many scenes at once (the runner.py sweeps become one call). */
+typedef struct {
+    ort_bottle bottle;
+    ort_plano L2;
+    ort_doublet L3;
+    double cos_theta_max; /* src/main.f90:51-52 */
+    double r1, r2;        /* squared annulus radii, src/main.f90:66-70 */
+    double img_plane;     /* src/main.f90:81 */
+    double point_offset;  /* z of the point source (0; bottle centre z for isors, main.f90:140) */
+} ort_scene;
+
+/* One launch of a ray loop. */
+typedef struct {
+    int32_t phase;       /* ORT_PHASE_RING | ORT_PHASE_POINT */
+    int32_t use_bottle;  /* src/setupMod.f90:63 (point phase only, src/main.f90:145) */
+    int32_t iris_before; /* iris(1), src/setupMod.f90:103-108 */
+    int32_t iris_after;  /* iris(2) */
+    int32_t precision;   /* 64 (fp64, the reference's arithmetic) */
+    int32_t flags;       /* ORT_FLAG_* */
+    int32_t stop_after;  /* ORT_STOP_* (ort_trace_rays only) */
+    int32_t _pad;
+    double iris_radius;      /* fraction of the lens radius, src/setupMod.f90:101 */
+    double fibre_offset;     /* src/setupMod.f90:84 */
+    double image_diameter;   /* src/setupMod.f90:83 */
+    double uniform_override; /* < 0: draws come from the counter-based generator;
+                                in [0,1): every draw returns this value (known-answer tests) */
+    uint64_t seed;     /* key of the counter-based generator (reference seeds 123456789,
+                          src/main.f90:79) */
+    int64_t first_ray; /* index of the first ray; uniforms are a pure function of
+                          (seed, phase, ray index, draw slot) */
+    int64_t nrays;     /* rays per scene */
+} ort_job;
+
+typedef struct {
+    double trace_seconds;  /* CUDA-event time: image clear + trace kernels, max over devices */
+    double reduce_seconds; /* CUDA-event time of the NCCL image reduce (0 on one GPU) */
+    double wall_seconds;   /* host wall clock of the whole call incl. H2D/D2H */
+    int64_t kernel_launches;
+    int64_t h2d_bytes, d2h_bytes;
+} ort_timing;
+
+/* parsed settings.params, reference src/setupMod.f90:57-133 */
+typedef struct {
+    double ring_width, wavelength, alpha_deg, n_axicon, image_diameter, fibre_offset;
+    double iris_radius, isors_offset, spot_size;
+    int64_t nphotons;
+    int32_t use_bottle, use_tracker, make_images, iris_before, iris_after, _pad;
+    char source_type[64];
+    char iris_name[64];
+    char bottle_file[256], l2_file[256], l3_file[256], image_file[256], folder[256];
+} ort_settings;
+
+/* ---- lifetime ------------------------------------------------------------------------ */
+/* Single-process mode: drive devices 0..ngpus-1 from this process (ngpus<=0: all visible).
+ * `./install.sh -n N` maps to this.  Returns the number of devices in use (>0) or ORT_E*. */
+int ort_init(int ngpus);
+/* One-process-per-GPU mode (torchrun / MPI style): this process owns `device`; when
+ * nranks > 1, `nccl_id` is the 128-byte ncclUniqueId rank 0 got from ort_nccl_unique_id()
+ * and distributed by any side channel. */
+int ort_init_rank(int device, int rank, int nranks, const void* nccl_id);
+int ort_nccl_unique_id(void* out128);
+int ort_finalize(void);
+const char* ort_last_error(void);
+int ort_device_count(void);
+
+/* ---- the hot path -------------------------------------------------------------------- */
+/* Replaces one ray loop of reference src/main.f90 for `nscenes` optical configurations.
+ *   image        [nscenes][ORT_IMG_BINS] uint64, host, OVERWRITTEN with the counts of this
+ *                phase; element ((yp+200)*401 + (xp+200)) as in src/imageMod.f90:102-112.
+ *                May be NULL (timing runs).
+ *   lost         [nscenes] rays lost in bottle/lenses = rcount | pcount of src/main.f90:28
+ *   status_hist  [nscenes][ORT_NSTATUS] histogram of enum ort_status (may be NULL)
+ * In single-process multi-GPU mode the ray range is split over the devices and the
+ * per-device images are summed with one ncclReduce before the call returns; in rank mode
+ * each rank traces the [first_ray, first_ray+nrays) it is given and rank 0 receives the sum
+ * (the other ranks' outputs are their private partial results). */
+int ort_trace(const ort_job* job, const ort_scene* scenes, int nscenes, uint64_t* image,
+              int64_t* lost, int64_t* status_hist, ort_timing* timing);
+
+/* Parity entry point: trace an explicit list of n rays through ONE scene.
+ *   pos_in/dir_in   structure-of-arrays [3][n] (x block, y block, z block); NULL => rays are
+ *                   emitted by the device-side source of job->phase (ray index first_ray+i)
+ *   pos_out/dir_out [3][n] state where the ray stopped (see ort_job.stop_after)
+ *   status          [n] enum ort_status
+ *   bin_xy          [2][n] (xp, yp) in -200..200, or INT32_MIN when not binned
+ * Draws use ray index job->first_ray + i, so the same rays give the same decisions as
+ * ort_trace. */
+int ort_trace_rays(const ort_job* job, const ort_scene* scene, int64_t n, const double* pos_in,
+                   const double* dir_in, double* pos_out, double* dir_out, int32_t* status,
+                   int32_t* bin_xy);
+
+/* The uniforms a ray sees: out[i] = uniform of slot `first_slot+i` (testing the generator). */
+int ort_uniforms(uint64_t seed, int32_t phase, int64_t ray, int32_t first_slot, int32_t n,
+                 double* out);
+
+/* FP64 FMA peak of device 0 measured with a DFMA micro-kernel (roofline denominator).
+ * Returns TFLOP/s in *tflops. */
+int ort_measure_fp64_peak(double* tflops, double* sm_clock_mhz);
+
+/* ---- host side of the drop-in surface (no device needed) -------------------------------- */
+int ort_load_plano(const char* path, double wavelength, double offset, ort_plano* out);
+int ort_load_doublet(const char* path, double wavelength, double offset, ort_doublet* out);
+int ort_load_bottle(const char* path, double wavelength, ort_bottle* out);
+int ort_read_settings(const char* path, ort_settings* out);
+/* Build the scene for one phase as src/main.f90 does: loads the three files named in the
+ * settings from `resdir`, the bottle at settings->wavelength and the lenses at
+ * `lens_wavelength` (785 nm settings value for the ring phase, 843e-9 for the point phase,
+ * src/main.f90:113-117), applies the offset guard (src/main.f90:54-58) and derives
+ * cos_theta_max, r1, r2, img_plane.  `pre_guard_offset` (may be NULL) receives
+ * bottle%centre%z before the guard (used by the output file name, src/main.f90:45-48). */
+int ort_build_scene(const ort_settings* settings, const char* resdir, double lens_wavelength,
+                    ort_scene* out, double* pre_guard_offset);
+int ort_job_from_settings(const ort_settings* settings, int32_t phase, ort_job* out);
+/* Output base name, src/main.f90:45-48 (without folder and without "_image-*.dat"). */
+int ort_output_basename(const ort_settings* settings, const ort_scene* scene,
+                        double pre_guard_offset, char* buf, size_t buflen);
+/* Three raw fp64 401x401 files <base>_image-{ring,point,total}.dat, src/imageMod.f90:93-114 */
+int ort_write_images(const char* base_with_folder, const uint64_t* ring, const uint64_t* point);
+/* Append one line to <folder>/trans-stats.dat, src/main.f90:168-178 */
+int ort_append_trans_stats(const char* folder, const ort_settings* settings,
+                           const ort_scene* scene_after, int64_t rcount, int64_t pcount);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORT_H */
