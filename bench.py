@@ -1,0 +1,291 @@
+#!/usr/bin/env python
+"""bench.py -- rays/s of the per-ray trace loop (BASELINE.json metric) on N B200s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            this framework (CUDA, C-ABI)
+  python bench.py --impl reference [...]                          the CPU arm (see below)
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   N > 1
+
+A "step" is one pass of the hot path over one batch of synthetic rays: the ring-source phase of
+BASELINE.json configs[1] (ring of point sources on the bottle surface, clearBottle-large +
+planoConvex-f39.9mm + achromaticDoublet-f50.0mm, 785 nm), RAYS_PER_GPU rays per GPU per step
+(weak scaling: every rank traces its own contiguous ray-index range of the job, rank 0
+receives the ncclReduce'd image).  Rays are generated on the device by the counter-based
+sources, so there are no input arrays: the only per-step traffic is the scene (H2D) and the
+401x401 uint64 image + status histogram (D2H).
+
+  value  = rays/s from CUDA events on the library's stream (image clear + trace kernel + NCCL
+           reduce), summed over the K steps, max over ranks
+  e2e    = rays/s from the host clock around the same K `ort_trace` calls with HOST buffers
+           (scene H2D, image D2H inside), barrier + device synchronize on both sides
+  roofline: FP64 ALU.  achieved = sum over final ray statuses of count x algorithmic flops
+           (SURVEY.md 8(d) stage table) / device time; peak = DFMA micro-kernel
+           measured in this run (MEASURED_PEAKS.json has no FP64 entry).
+  cpu_baseline / --impl reference: the reference is Fortran and no Fortran compiler exists in
+           this image, so the CPU arm is the C++/OpenMP oracle (kind "port": statement-by-
+           statement restatement of the Fortran path) on all host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOAD = ("config2-ring: ring source on clearBottle-large -> planoConvex-f39.9mm -> "
+            "achromaticDoublet-f50.0mm -> 401x401 detector, 785 nm")
+FILES = ("clearBottle-large.params", "planoConvex-f39.9mm.params", "achromaticDoublet-f50.0mm.params")
+RAYS_PER_GPU = 1 << 30
+CPU_SAMPLE = 30_000_000
+
+# Algorithmic fp64 flops by final status (SURVEY.md 8(d) convention: + - * / sqrt and libm calls
+# count 1, as written in the reference).  Stage table: ring 51 | point 11, bottle wall 98 each,
+# L2 flat: 14 to the aperture test + 56, L2 curved 104 (30 of it the intersection), L3 s1 108,
+# s2 104, s3 104, iris 14, plane move 9, makeImage 37.
+def flops_by_status(phase, use_bottle=True, iris_before=False, iris_after=False):
+    f = np.zeros(32)
+    src = 51.0 if phase == 1 else 11.0
+    b_in = b_out = 0.0
+    if phase == 2 and use_bottle:
+        f[1] = src + 24                 # inner wall miss: intersection only
+        f[4] = src + 98                 # reflected at the inner wall
+        f[5] = src + 98 + 24
+        f[8] = src + 196
+        b_in, b_out = 98.0, 98.0
+    s0 = src + b_in + b_out
+    f[9] = s0 + 14
+    f[10] = s0 + 14 + 56 + 30
+    f[11] = s0 + 14 + 56 + 104
+    l2 = s0 + 174
+    ib = 14.0 if iris_before else 0.0
+    f[12] = l2 + ib
+    f[13] = l2 + ib + 30
+    f[14] = l2 + ib + 40
+    f[15] = l2 + ib + 108
+    f[16] = l2 + ib + 108 + 30
+    f[17] = l2 + ib + 212
+    f[18] = l2 + ib + 212 + 30
+    f[19] = l2 + ib + 316
+    l3 = l2 + ib + 316
+    ia = 14.0 if iris_after else 0.0
+    f[20] = l3 + ia
+    f[21] = l3 + ia + 9 + 20
+    f[22] = f[23] = f[0] = l3 + ia + 9 + 37
+    return f
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 8:
+                continue
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_arm(nrays, threads, first_ray=0):
+    """Times the CPU oracle (C++/OpenMP restatement of the Fortran path) on `nrays` rays."""
+    from opticalraytrace_b200 import abi
+    from tests import oracle_lib as O
+    scene = O.make_scene(*FILES)
+    job = abi.default_job(abi.PHASE_RING, nrays, first_ray=first_ray)
+    t0 = time.perf_counter()
+    O.trace(job, scene, nthreads=threads)
+    return nrays / (time.perf_counter() - t0)
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    from tests import oracle_lib as O
+    O.lib()
+    cores = os.cpu_count() or 1
+    sample = CPU_SAMPLE
+    for _ in range(args.warmup):
+        cpu_arm(sample // 10, cores)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        cpu_arm(sample, cores, first_ray=k * sample)
+    dt = time.perf_counter() - t0
+    v = args.steps * sample / dt
+    line = {
+        "impl": "reference", "metric": "rays/sec", "value": v, "unit": "rays/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "rays_per_step": sample},
+        "cpu_baseline": {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",
+                         "sample": "%d rays per step, C++/OpenMP restatement of the Fortran path "
+                                   "(no Fortran compiler in this image)" % sample},
+        "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rays", type=int, default=RAYS_PER_GPU, help="rays per GPU per step")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank)
+
+    import torch
+    import torch.distributed as dist
+    from opticalraytrace_b200 import abi, lib
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the trace loop has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    nccl_id = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        box = [lib.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        nccl_id = box[0]
+    lib.init_rank(local, rank, world, nccl_id)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    st = lib.make_settings(*FILES, nphotons=args.rays)
+    scene, _ = lib.build_scene(st, os.path.join(ROOT, "res"))
+    n = args.rays
+
+    def step(k, want_image=True):
+        job = lib.job_from_settings(st, abi.PHASE_RING)
+        job.first_ray = (k * world + rank) * n
+        job.nrays = n
+        return lib.trace(job, scene, want_image=want_image)
+
+    for k in range(args.warmup):
+        step(k)
+    peak_tf, peak_mhz = lib.measure_fp64_peak()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    dev_s, red_s, launches, h2d, d2h = 0.0, 0.0, 0, 0, 0
+    hist = np.zeros(32, dtype=np.int64)
+    for k in range(args.steps):
+        _, _, h, tm = step(args.warmup + k)
+        dev_s += tm.trace_seconds + tm.reduce_seconds
+        red_s += tm.reduce_seconds
+        launches += tm.kernel_launches
+        h2d, d2h = tm.h2d_bytes, tm.d2h_bytes
+        if rank == 0:
+            hist += h[0]
+    barrier()
+    wall_s = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+
+    t = torch.tensor([dev_s, wall_s, red_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_s, wall_s, red_s = (float(x) for x in t.tolist())
+    total_rays = float(n) * world * args.steps
+
+    if rank == 0:
+        # rank 0's histogram holds the reduced counts of all ranks (it is the reduce root)
+        flops = float((flops_by_status(1) * hist).sum())
+        achieved = flops / dev_s * 1e-12
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            cores = os.cpu_count() or 1
+            cpu_arm(CPU_SAMPLE // 10, cores)
+            v = cpu_arm(CPU_SAMPLE * 4, cores, first_ray=1 << 40)
+            cpu = {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",
+                   "sample": "%d rays of the same workload, C++/OpenMP restatement of the Fortran "
+                             "path (oracle/), all host cores" % (CPU_SAMPLE * 4)}
+        line = {
+            "metric": "rays/sec", "value": total_rays / dev_s, "unit": "rays/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_s / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "rays_per_gpu_per_step": n,
+                       "rays_per_step": n * world, "parallelism": "ray-range x%d" % world,
+                       "l2": "no input arrays (rays are generated on the device); the 2.6 MB "
+                             "image buffer is re-zeroed every step",
+                       "seed": 123456789},
+            "e2e": {"value": total_rays / wall_s, "unit": "rays/s",
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches),
+            "reduce_ms_per_step": red_s / args.steps * 1e3,
+            "clocks": clocks,
+            "roofline": {"bound": "alu_fp64", "achieved": achieved, "peak": peak_tf,
+                         "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
+                         "traffic": None,
+                         "peak_source": "DFMA micro-kernel measured in this run at %.0f MHz "
+                                        "(MEASURED_PEAKS.json holds no FP64 figure)" % peak_mhz,
+                         "flops_per_launched_ray": flops / (total_rays)},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    lib.finalize()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -186,6 +186,9 @@ int ort_nccl_unique_id(void* out128);
 int ort_finalize(void);
 const char* ort_last_error(void);
 int ort_device_count(void);
+/* sizeof() of {ort_plano, ort_doublet, ort_bottle, ort_scene, ort_job, ort_timing, ort_settings}
+ * followed by ORT_VERSION -- lets a foreign-language binding verify its struct mirrors. */
+int ort_struct_sizes(int32_t out[8]);
 
 /* ---- the hot path -------------------------------------------------------------------- */
 /* Replaces one ray loop of reference src/main.f90 for `nscenes` optical configurations.

@@ -1,0 +1,550 @@
+/*
+ * ort_cuda.cu -- device half of the C-ABI declared in include/ort.h: device / stream / NCCL
+ * lifetime, scene flattening, kernel launches, the image reduce and the copies.
+ *
+ * There is no CPU fallback in this file or anywhere in the library: with no CUDA device every
+ * compute entry point fails with ORT_ENODEVICE.
+ */
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h> /* types and prototypes only: NCCL is dlopen()ed, never linked */
+
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "ort_internal.h"
+#include "ort_flatten.h"
+#include "ort_kernels.cuh"
+
+/* ------------------------------------------------------------------------------------------
+ * error text
+ * ---------------------------------------------------------------------------------------- */
+static char g_err[1024] = "";
+void ort_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+extern "C" const char* ort_last_error(void) { return g_err; }
+
+#define CK(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess) {                                                          \
+            ort_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return (e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver) ? ORT_ENODEVICE : ORT_ECUDA; \
+        }                                                                                 \
+    } while (0)
+
+/* ------------------------------------------------------------------------------------------
+ * NCCL, loaded at run time so the library has no link-time dependency on it and a process that
+ * already carries a libnccl.so.2 (e.g. a torch.distributed launcher) shares that copy.
+ * ---------------------------------------------------------------------------------------- */
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Reduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t,
+                           cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int nccl_load() {
+    if (g_nccl.handle) return ORT_OK;
+    const char* names[] = {"libnccl.so.2", "libnccl.so", "/usr/lib/x86_64-linux-gnu/libnccl.so.2"};
+    void* h = nullptr;
+    for (const char* n : names) {
+        h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) {
+        ort_set_error("NCCL not loadable: %s", dlerror());
+        return ORT_ENCCL;
+    }
+#define SYM(field, name)                                              \
+    *(void**)(&g_nccl.field) = dlsym(h, name);                        \
+    if (!g_nccl.field) {                                              \
+        ort_set_error("NCCL symbol %s missing", name);                \
+        return ORT_ENCCL;                                             \
+    }
+    SYM(GetUniqueId, "ncclGetUniqueId")
+    SYM(CommInitRank, "ncclCommInitRank")
+    SYM(CommInitAll, "ncclCommInitAll")
+    SYM(CommDestroy, "ncclCommDestroy")
+    SYM(Reduce, "ncclReduce")
+    SYM(GroupStart, "ncclGroupStart")
+    SYM(GroupEnd, "ncclGroupEnd")
+    SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+    g_nccl.handle = h;
+    return ORT_OK;
+}
+#define NK(call)                                                                              \
+    do {                                                                                      \
+        ncclResult_t r_ = (call);                                                             \
+        if (r_ != ncclSuccess) {                                                              \
+            ort_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString(r_)); \
+            return ORT_ENCCL;                                                                 \
+        }                                                                                     \
+    } while (0)
+
+/* ------------------------------------------------------------------------------------------
+ * library state
+ * ---------------------------------------------------------------------------------------- */
+struct DeviceCtx {
+    int dev = -1;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_traced = nullptr, ev_reduced = nullptr;
+    unsigned long long* d_buf = nullptr; /* [nscenes*BINS image][nscenes*NSTATUS counters] */
+    size_t d_elems = 0;
+    ncclComm_t comm = nullptr;
+};
+struct LibState {
+    bool ready = false;
+    bool rank_mode = false;
+    int rank = 0, nranks = 1;
+    std::vector<DeviceCtx> devs;
+    unsigned long long* h_pinned = nullptr;
+    size_t h_elems = 0;
+};
+static LibState g;
+
+extern "C" int ort_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+static int ctx_open(DeviceCtx& c, int dev) {
+    c.dev = dev;
+    CK(cudaSetDevice(dev));
+    CK(cudaDeviceGetAttribute(&c.num_sms, cudaDevAttrMultiProcessorCount, dev));
+    CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&c.ev_start));
+    CK(cudaEventCreate(&c.ev_traced));
+    CK(cudaEventCreate(&c.ev_reduced));
+    return ORT_OK;
+}
+
+extern "C" int ort_finalize(void) {
+    for (auto& c : g.devs) {
+        if (c.dev < 0) continue;
+        cudaSetDevice(c.dev);
+        if (c.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c.comm);
+        if (c.d_buf) cudaFree(c.d_buf);
+        if (c.ev_start) cudaEventDestroy(c.ev_start);
+        if (c.ev_traced) cudaEventDestroy(c.ev_traced);
+        if (c.ev_reduced) cudaEventDestroy(c.ev_reduced);
+        if (c.stream) cudaStreamDestroy(c.stream);
+    }
+    if (g.h_pinned) cudaFreeHost(g.h_pinned);
+    g = LibState();
+    return ORT_OK;
+}
+
+extern "C" int ort_init(int ngpus) {
+    if (g.ready) ort_finalize();
+    int n = ort_device_count();
+    if (n <= 0) {
+        ort_set_error("no CUDA device visible (this library has no CPU fallback)");
+        return ORT_ENODEVICE;
+    }
+    if (ngpus <= 0 || ngpus > n) ngpus = n;
+    g.devs.resize(ngpus);
+    for (int i = 0; i < ngpus; ++i) {
+        int rc = ctx_open(g.devs[i], i);
+        if (rc) return rc;
+    }
+    if (ngpus > 1) {
+        int rc = nccl_load();
+        if (rc) return rc;
+        std::vector<ncclComm_t> comms(ngpus);
+        std::vector<int> list(ngpus);
+        for (int i = 0; i < ngpus; ++i) list[i] = i;
+        NK(g_nccl.CommInitAll(comms.data(), ngpus, list.data()));
+        for (int i = 0; i < ngpus; ++i) g.devs[i].comm = comms[i];
+    }
+    g.rank_mode = false;
+    g.rank = 0;
+    g.nranks = 1;
+    g.ready = true;
+    return ngpus;
+}
+
+extern "C" int ort_nccl_unique_id(void* out128) {
+    if (!out128) return ORT_EINVAL;
+    int rc = nccl_load();
+    if (rc) return rc;
+    ncclUniqueId id;
+    NK(g_nccl.GetUniqueId(&id));
+    memcpy(out128, &id, sizeof id);
+    return ORT_OK;
+}
+
+extern "C" int ort_init_rank(int device, int rank, int nranks, const void* nccl_id) {
+    if (g.ready) ort_finalize();
+    if (nranks < 1 || rank < 0 || rank >= nranks) {
+        ort_set_error("ort_init_rank: bad rank %d / %d", rank, nranks);
+        return ORT_EINVAL;
+    }
+    int n = ort_device_count();
+    if (n <= 0) {
+        ort_set_error("no CUDA device visible (this library has no CPU fallback)");
+        return ORT_ENODEVICE;
+    }
+    if (device < 0 || device >= n) {
+        ort_set_error("ort_init_rank: device %d not in 0..%d", device, n - 1);
+        return ORT_EINVAL;
+    }
+    g.devs.resize(1);
+    int rc = ctx_open(g.devs[0], device);
+    if (rc) return rc;
+    if (nranks > 1) {
+        if (!nccl_id) {
+            ort_set_error("ort_init_rank: nranks > 1 needs the ncclUniqueId");
+            return ORT_EINVAL;
+        }
+        rc = nccl_load();
+        if (rc) return rc;
+        ncclUniqueId id;
+        memcpy(&id, nccl_id, sizeof id);
+        NK(g_nccl.CommInitRank(&g.devs[0].comm, nranks, id, rank));
+    }
+    g.rank_mode = true;
+    g.rank = rank;
+    g.nranks = nranks;
+    g.ready = true;
+    return 1;
+}
+
+static int validate_job(const ort_job* job) {
+    if (!job) {
+        ort_set_error("job is NULL");
+        return ORT_EINVAL;
+    }
+    if (job->phase != ORT_PHASE_RING && job->phase != ORT_PHASE_POINT) {
+        ort_set_error("job.phase must be 1 (ring) or 2 (point), got %d", job->phase);
+        return ORT_EINVAL;
+    }
+    if (job->precision != 64) {
+        ort_set_error("job.precision %d not supported (64 only)", job->precision);
+        return ORT_EINVAL;
+    }
+    if (job->nrays < 0 || job->first_ray < 0) {
+        ort_set_error("negative ray count / index");
+        return ORT_EINVAL;
+    }
+    if (!(job->image_diameter > 0.0)) {
+        ort_set_error("image_diameter must be > 0");
+        return ORT_EINVAL;
+    }
+    if (job->uniform_override >= 1.0) {
+        ort_set_error("uniform_override must be < 1");
+        return ORT_EINVAL;
+    }
+    return ORT_OK;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * kernel dispatch
+ * ---------------------------------------------------------------------------------------- */
+typedef void (*trace_kernel_t)(unsigned long long*, unsigned long long*);
+
+static trace_kernel_t pick_kernel(int phase, int bottle_mode, bool flat) {
+    if (phase == ORT_PHASE_RING)
+        return flat ? ort_trace_flat_kernel<ORT_PHASE_RING, 0> : ort_trace_kernel<ORT_PHASE_RING, 0>;
+    switch (bottle_mode) {
+        case 0: return flat ? ort_trace_flat_kernel<ORT_PHASE_POINT, 0> : ort_trace_kernel<ORT_PHASE_POINT, 0>;
+        case 1: return flat ? ort_trace_flat_kernel<ORT_PHASE_POINT, 1> : ort_trace_kernel<ORT_PHASE_POINT, 1>;
+        default: return flat ? ort_trace_flat_kernel<ORT_PHASE_POINT, 2> : ort_trace_kernel<ORT_PHASE_POINT, 2>;
+    }
+}
+
+static const int64_t ORT_CHUNK = (int64_t)1 << 31; /* rays per scene per launch (ids are 32-bit) */
+
+/* enqueue the trace of rays [first, first+n) of every scene on device ctx; returns launches */
+static int enqueue_trace(DeviceCtx& c, const ort_job& job, const std::vector<DevScene>& ds, int64_t first,
+                         int64_t n, int64_t* launches) {
+    const int nscenes = (int)ds.size();
+    CK(cudaSetDevice(c.dev));
+    size_t elems = (size_t)nscenes * (ORT_IMG_BINS + ORT_NSTATUS);
+    if (c.d_elems < elems) {
+        if (c.d_buf) CK(cudaFree(c.d_buf));
+        c.d_buf = nullptr;
+        CK(cudaMalloc(&c.d_buf, elems * sizeof(unsigned long long)));
+        c.d_elems = elems;
+    }
+    bool any_scatter = false;
+    for (auto& s : ds) any_scatter |= (s.scatter_b || s.scatter_c);
+    int bottle_mode = (job.phase == ORT_PHASE_POINT && job.use_bottle) ? (any_scatter ? 2 : 1) : 0;
+    bool flat = (job.flags & ORT_FLAG_NO_COMPACTION) != 0;
+    trace_kernel_t k = pick_kernel(job.phase, bottle_mode, flat);
+    size_t smem = flat ? 0 : (size_t)ORT_WPB * sizeof(WarpShared);
+    if (smem) CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, ORT_TPB, smem));
+    if (occ < 1) occ = 1;
+    int grid = c.num_sms * occ;
+
+    CK(cudaEventRecord(c.ev_start, c.stream));
+    CK(cudaMemsetAsync(c.d_buf, 0, elems * sizeof(unsigned long long), c.stream));
+    CK(cudaMemcpyToSymbolAsync(c_scenes, ds.data(), sizeof(DevScene) * nscenes, 0, cudaMemcpyHostToDevice,
+                               c.stream));
+    unsigned long long* d_img = c.d_buf;
+    unsigned long long* d_cnt = c.d_buf + (size_t)nscenes * ORT_IMG_BINS;
+    for (int64_t off = 0; off < n; off += ORT_CHUNK) {
+        int64_t m = n - off < ORT_CHUNK ? n - off : ORT_CHUNK;
+        DevJob dj;
+        ort_make_dev_job(job, nscenes, first + off, m, dj);
+        CK(cudaMemcpyToSymbolAsync(c_job, &dj, sizeof dj, 0, cudaMemcpyHostToDevice, c.stream));
+        int64_t batches = (m + 31) / 32;
+        int64_t want = (batches + ORT_WPB - 1) / ORT_WPB;
+        int gsz = (int)(want < grid ? (want > 0 ? want : 1) : grid);
+        k<<<gsz, ORT_TPB, smem, c.stream>>>(d_img, d_cnt);
+        CK(cudaGetLastError());
+        ++*launches;
+    }
+    CK(cudaEventRecord(c.ev_traced, c.stream));
+    return ORT_OK;
+}
+
+extern "C" int ort_trace(const ort_job* job, const ort_scene* scenes, int nscenes, uint64_t* image,
+                         int64_t* lost, int64_t* status_hist, ort_timing* timing) {
+    auto w0 = std::chrono::steady_clock::now();
+    if (!g.ready) {
+        ort_set_error("ort_trace: library not initialised (ort_init / ort_init_rank)");
+        return ORT_ENODEVICE;
+    }
+    int rc = validate_job(job);
+    if (rc) return rc;
+    if (!scenes || nscenes < 1 || nscenes > ORT_MAX_SCENES) {
+        ort_set_error("ort_trace: nscenes must be 1..%d", ORT_MAX_SCENES);
+        return ORT_EINVAL;
+    }
+    std::vector<DevScene> ds(nscenes);
+    for (int i = 0; i < nscenes; ++i) ort_flatten_scene(scenes[i], *job, ds[i]);
+
+    const int G = (int)g.devs.size();
+    const size_t elems = (size_t)nscenes * (ORT_IMG_BINS + ORT_NSTATUS);
+    int64_t launches = 0;
+    /* contiguous ray-index ranges per device; uniforms depend only on the ray
+     * index, so the summed image is identical for any G */
+    for (int d = 0; d < G; ++d) {
+        int64_t lo = job->nrays * d / G, hi = job->nrays * (d + 1) / G;
+        rc = enqueue_trace(g.devs[d], *job, ds, job->first_ray + lo, hi - lo, &launches);
+        if (rc) return rc;
+    }
+    /* one reduce of [images | counters] to device 0 / rank 0 */
+    bool reduced = false;
+    if (G > 1) {
+        NK(g_nccl.GroupStart());
+        for (int d = 0; d < G; ++d) {
+            DeviceCtx& c = g.devs[d];
+            NK(g_nccl.Reduce(c.d_buf, c.d_buf, elems, ncclUint64, ncclSum, 0, c.comm, c.stream));
+        }
+        NK(g_nccl.GroupEnd());
+        reduced = true;
+    } else if (g.rank_mode && g.nranks > 1 && !(job->flags & ORT_FLAG_NO_REDUCE)) {
+        DeviceCtx& c = g.devs[0];
+        CK(cudaSetDevice(c.dev));
+        NK(g_nccl.Reduce(c.d_buf, c.d_buf, elems, ncclUint64, ncclSum, 0, c.comm, c.stream));
+        reduced = true;
+    }
+    for (int d = 0; d < G; ++d) {
+        CK(cudaSetDevice(g.devs[d].dev));
+        CK(cudaEventRecord(g.devs[d].ev_reduced, g.devs[d].stream));
+    }
+    /* results back to the host */
+    DeviceCtx& c0 = g.devs[0];
+    CK(cudaSetDevice(c0.dev));
+    if (g.h_elems < elems) {
+        if (g.h_pinned) CK(cudaFreeHost(g.h_pinned));
+        g.h_pinned = nullptr;
+        CK(cudaHostAlloc(&g.h_pinned, elems * sizeof(unsigned long long), cudaHostAllocDefault));
+        g.h_elems = elems;
+    }
+    size_t img_elems = (size_t)nscenes * ORT_IMG_BINS;
+    size_t d2h = 0;
+    if (image) {
+        CK(cudaMemcpyAsync(g.h_pinned, c0.d_buf, img_elems * 8, cudaMemcpyDeviceToHost, c0.stream));
+        d2h += img_elems * 8;
+    }
+    CK(cudaMemcpyAsync(g.h_pinned + img_elems, c0.d_buf + img_elems, (size_t)nscenes * ORT_NSTATUS * 8,
+                       cudaMemcpyDeviceToHost, c0.stream));
+    d2h += (size_t)nscenes * ORT_NSTATUS * 8;
+    for (int d = 0; d < G; ++d) {
+        CK(cudaSetDevice(g.devs[d].dev));
+        CK(cudaStreamSynchronize(g.devs[d].stream));
+    }
+    if (image) memcpy(image, g.h_pinned, img_elems * 8);
+    bool trapped = false;
+    for (int s = 0; s < nscenes; ++s) {
+        const unsigned long long* h = g.h_pinned + img_elems + (size_t)s * ORT_NSTATUS;
+        int64_t l = 0;
+        for (int k = 0; k < ORT_NSTATUS; ++k) {
+            if (ORT_STATUS_IS_LOST(k)) l += (int64_t)h[k];
+            if (status_hist) status_hist[(size_t)s * ORT_NSTATUS + k] = (int64_t)h[k];
+        }
+        if (lost) lost[s] = l;
+        if (h[ORT_ST_L3_S3_MISS] || h[ORT_ST_TAUINT_MISS]) trapped = true;
+    }
+    if (timing) {
+        double tmax = 0.0, rmax = 0.0;
+        for (int d = 0; d < G; ++d) {
+            float a = 0.f, b = 0.f;
+            CK(cudaSetDevice(g.devs[d].dev));
+            CK(cudaEventElapsedTime(&a, g.devs[d].ev_start, g.devs[d].ev_traced));
+            CK(cudaEventElapsedTime(&b, g.devs[d].ev_traced, g.devs[d].ev_reduced));
+            if (a > tmax) tmax = a;
+            if (b > rmax) rmax = b;
+        }
+        timing->trace_seconds = tmax * 1e-3;
+        timing->reduce_seconds = reduced ? rmax * 1e-3 : 0.0;
+        timing->kernel_launches = launches;
+        timing->h2d_bytes = (int64_t)(G * (sizeof(DevScene) * nscenes + sizeof(DevJob) * ((job->nrays / G + ORT_CHUNK) / ORT_CHUNK)));
+        timing->d2h_bytes = (int64_t)d2h;
+        timing->wall_seconds =
+            std::chrono::duration<double>(std::chrono::steady_clock::now() - w0).count();
+    }
+    if (trapped) {
+        ort_set_error("trace hit a reference `error stop` invariant (status 18 or 24); results returned");
+        return ORT_ETRACE;
+    }
+    return ORT_OK;
+}
+
+extern "C" int ort_trace_rays(const ort_job* job, const ort_scene* scene, int64_t n, const double* pos_in,
+                              const double* dir_in, double* pos_out, double* dir_out, int32_t* status,
+                              int32_t* bin_xy) {
+    if (!g.ready) {
+        ort_set_error("ort_trace_rays: library not initialised (ort_init / ort_init_rank)");
+        return ORT_ENODEVICE;
+    }
+    int rc = validate_job(job);
+    if (rc) return rc;
+    if (!scene || n < 0 || n >= ((int64_t)1 << 31) || (pos_in == nullptr) != (dir_in == nullptr)) {
+        ort_set_error("ort_trace_rays: bad arguments");
+        return ORT_EINVAL;
+    }
+    if (n == 0) return ORT_OK;
+    DeviceCtx& c = g.devs[0];
+    CK(cudaSetDevice(c.dev));
+    DevScene ds;
+    ort_flatten_scene(*scene, *job, ds);
+    DevJob dj;
+    ort_make_dev_job(*job, 1, job->first_ray, n, dj);
+    CK(cudaMemcpyToSymbolAsync(c_scenes, &ds, sizeof ds, 0, cudaMemcpyHostToDevice, c.stream));
+    CK(cudaMemcpyToSymbolAsync(c_job, &dj, sizeof dj, 0, cudaMemcpyHostToDevice, c.stream));
+    double *d_in = nullptr, *d_out = nullptr;
+    int32_t* d_int = nullptr;
+    size_t vb = (size_t)3 * n * sizeof(double);
+    int ret = ORT_OK;
+    do {
+#define CKB(call)                                                                                  \
+    {                                                                                              \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            ort_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));    \
+            ret = ORT_ECUDA;                                                                       \
+            break;                                                                                 \
+        }                                                                                          \
+    }
+        if (pos_in) {
+            CKB(cudaMalloc(&d_in, 2 * vb));
+            CKB(cudaMemcpyAsync(d_in, pos_in, vb, cudaMemcpyHostToDevice, c.stream));
+            CKB(cudaMemcpyAsync(d_in + 3 * n, dir_in, vb, cudaMemcpyHostToDevice, c.stream));
+        }
+        CKB(cudaMalloc(&d_out, 2 * vb));
+        CKB(cudaMalloc(&d_int, (size_t)3 * n * sizeof(int32_t)));
+        int grid = (int)((n + ORT_TPB - 1) / ORT_TPB);
+        ort_rays_kernel<<<grid, ORT_TPB, 0, c.stream>>>(d_in, d_in ? d_in + 3 * n : nullptr, d_out, d_out + 3 * n,
+                                                        d_int, d_int + n, (long long)n);
+        CKB(cudaGetLastError());
+        if (pos_out) CKB(cudaMemcpyAsync(pos_out, d_out, vb, cudaMemcpyDeviceToHost, c.stream));
+        if (dir_out) CKB(cudaMemcpyAsync(dir_out, d_out + 3 * n, vb, cudaMemcpyDeviceToHost, c.stream));
+        if (status) CKB(cudaMemcpyAsync(status, d_int, n * sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+        if (bin_xy) CKB(cudaMemcpyAsync(bin_xy, d_int + n, 2 * n * sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+        CKB(cudaStreamSynchronize(c.stream));
+#undef CKB
+    } while (0);
+    if (d_in) cudaFree(d_in);
+    if (d_out) cudaFree(d_out);
+    if (d_int) cudaFree(d_int);
+    return ret;
+}
+
+extern "C" int ort_uniforms(uint64_t seed, int32_t phase, int64_t ray, int32_t first_slot, int32_t n,
+                            double* out) {
+    if (!g.ready) {
+        ort_set_error("ort_uniforms: library not initialised");
+        return ORT_ENODEVICE;
+    }
+    if (n <= 0 || !out || first_slot < 0) return ORT_EINVAL;
+    DeviceCtx& c = g.devs[0];
+    CK(cudaSetDevice(c.dev));
+    double* d = nullptr;
+    CK(cudaMalloc(&d, n * sizeof(double)));
+    ort_uniforms_kernel<<<(n + 127) / 128, 128, 0, c.stream>>>(seed, phase, ray, first_slot, n, d);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);
+    cudaFree(d);
+    if (e != cudaSuccess) {
+        ort_set_error("ort_uniforms: %s", cudaGetErrorString(e));
+        return ORT_ECUDA;
+    }
+    return ORT_OK;
+}
+
+extern "C" int ort_measure_fp64_peak(double* tflops, double* sm_clock_mhz) {
+    if (!g.ready) {
+        ort_set_error("ort_measure_fp64_peak: library not initialised");
+        return ORT_ENODEVICE;
+    }
+    DeviceCtx& c = g.devs[0];
+    CK(cudaSetDevice(c.dev));
+    double* d_out = nullptr;
+    long long* d_cyc = nullptr;
+    CK(cudaMalloc(&d_out, sizeof(double)));
+    CK(cudaMalloc(&d_cyc, sizeof(long long)));
+    const int grid = c.num_sms * 8, tpb = 256;
+    double best = 0.0, mhz = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        CK(cudaEventRecord(c.ev_start, c.stream));
+        ort_dfma_peak_kernel<<<grid, tpb, 0, c.stream>>>(d_out, 1.0 + rep, d_cyc);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(c.ev_traced, c.stream));
+        CK(cudaStreamSynchronize(c.stream));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, c.ev_start, c.ev_traced));
+        double flops = (double)grid * tpb * ORT_PEAK_ITERS * 8.0 * 2.0;
+        double tf = flops / (ms * 1e-3) * 1e-12;
+        if (rep >= 1 && tf > best) {
+            best = tf;
+            /* each SM hosts 8 of these 256-thread blocks at once: one block's cycle count spans
+             * the whole kernel, so cycles / time ~ the SM clock during the run */
+            long long cyc = 0;
+            CK(cudaMemcpy(&cyc, d_cyc, sizeof cyc, cudaMemcpyDeviceToHost));
+            mhz = (double)cyc / (ms * 1e-3) * 1e-6;
+        }
+    }
+    cudaFree(d_out);
+    cudaFree(d_cyc);
+    if (tflops) *tflops = best;
+    if (sm_clock_mhz) *sm_clock_mhz = mhz;
+    return ORT_OK;
+}

@@ -1,0 +1,74 @@
+/*
+ * ort_dev_types.h -- device-side (constant-memory) view of a scene and a job.
+ *
+ * The public structs of include/ort.h mirror the reference's derived types field by field; the
+ * kernels read this flattened form instead, in which everything that is invariant over a launch
+ * has been hoisted on the host once (squared radii, refractive-index ratios, plane positions,
+ * the cosine of the acceptance angle, 401/diameter ...), so that the per-ray code is only the
+ * work that depends on the ray.
+ */
+#ifndef ORT_DEV_TYPES_H
+#define ORT_DEV_TYPES_H
+
+#include <stdint.h>
+
+#include "../../include/ort.h"
+
+#define ORT_MAX_SCENES 64 /* scenes per launch held in __constant__ memory (64 * 712 B = 45 KiB) */
+
+/* One refracting interface n_a -> n_b */
+struct DevIface {
+    double na, nb;  /* refractive indices on the incoming / outgoing side */
+    double eta;     /* na / nb  (reference computes n1/n2 per call, src/surfaces.f90:279,352) */
+    double eta2;    /* eta * eta */
+};
+
+struct DevScene {
+    /* --- bottle (reference src/lens.f90:230-350) --- */
+    double bcx, bcy, bcz;         /* centre */
+    double b_in_r, b_in_r2;       /* inner cylinder radius Ra - th and its square */
+    double b_out_r, b_out_r2;     /* outer cylinder radius Ra */
+    double b_in_ia2, b_in_ib2;    /* inner ellipse 1/semia^2 (z), 1/semib^2 (y) */
+    double b_out_ia2, b_out_ib2;  /* outer ellipse (reference: Ra/2, Rb/2; fixed: Ra, Rb) */
+    DevIface b_in;                /* contents -> glass */
+    DevIface b_out;               /* glass -> air (1.0) */
+    double mutot_c, inv_mutot_c, albedo_c; /* contents: mua+mus, 1/(mua+mus), mus/(mus+mua) */
+    double mutot_b, inv_mutot_b, albedo_b; /* wall */
+    /* --- sources (reference src/sourceMod.f90:12-47,250-300) --- */
+    double cos_theta_max, one_m_ctm, point_offset;
+    double r1, r2_m_r1;           /* annulus: r = r1 + u (r2 - r1) */
+    double ra2, ra_over_rb;       /* Ra^2, Ra/Rb */
+    double lens_r2;               /* (L2.radius + 10e-3)^2 */
+    double l2_fb;                 /* z of the aim disc */
+    /* --- L2 plano-convex (reference src/lens.f90:425-481) --- */
+    double l2_cx, l2_cy, l2_cz;   /* sphere centre */
+    double l2_flat_z;             /* centre.z + R - thickness */
+    double l2_radius2;            /* aperture radius squared */
+    double l2_R2, l2_invR;        /* curve radius squared, 1/R */
+    double l2_fnx, l2_fny, l2_fnz;/* flat-face normal */
+    DevIface l2_in, l2_out;       /* n1 -> n2, n2 -> n1 */
+    /* --- L3 achromatic doublet (reference src/lens.f90:531-645) --- */
+    double l3_c1x, l3_c1y, l3_c1z, l3_c2x, l3_c2y, l3_c2z, l3_c3x, l3_c3y, l3_c3z;
+    double l3_R1_2, l3_R2_2, l3_R3_2, l3_invR1, l3_invR2, l3_invR3;
+    double l3_radius2;            /* aperture */
+    double l3_iris_r2;            /* (radius * iris_radius)^2 */
+    double l3_iris1_z, l3_iris2_z;/* centre1.z - R1, centre3.z + R3 */
+    DevIface l3_s1, l3_s2, l3_s3; /* n1->n2, n2->n3, n3->n1 */
+    /* --- image plane (reference src/optics_system.f90:48-49, src/imageMod.f90:19-58) --- */
+    double img_z;                 /* img_plane + fibre_offset */
+    double inv_binwid;            /* 401 / diameter */
+    double binwid;                /* diameter / 401 */
+    double cos_na2;               /* cos(asin(0.22))^2 */
+    int32_t ellipse, scatter_b, scatter_c, _pad;
+};
+
+struct DevJob {
+    uint64_t seed;
+    int64_t first_ray;   /* ray index of local ray 0 of this launch */
+    int64_t nrays;       /* rays per scene in this launch (< 2^32) */
+    double uniform_override;
+    int32_t phase, use_bottle, iris_before, iris_after;
+    int32_t nscenes, stop_after, flags, _pad;
+};
+
+#endif

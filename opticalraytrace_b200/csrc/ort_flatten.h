@@ -1,0 +1,109 @@
+/* ort_flatten.h -- host-only: public scene + job -> the flattened constant-memory form the
+ * kernels read (DevScene / DevJob, ort_dev_types.h).  Every launch-invariant scalar is hoisted
+ * here, once per launch. */
+#ifndef ORT_FLATTEN_H
+#define ORT_FLATTEN_H
+
+#include <cstring>
+
+#include "ort_dev_types.h"
+
+/* ------------------------------------------------------------------------------------------
+ * scene flattening (host, once per launch)
+ * ---------------------------------------------------------------------------------------- */
+inline DevIface ort_mk_iface(double na, double nb) {
+    DevIface f;
+    f.na = na;
+    f.nb = nb;
+    f.eta = na / nb;
+    f.eta2 = f.eta * f.eta;
+    return f;
+}
+inline double ort_sq(double x) { return x * x; }
+
+inline void ort_flatten_scene(const ort_scene& s, const ort_job& j, DevScene& d) {
+    memset(&d, 0, sizeof d);
+    const ort_bottle& b = s.bottle;
+    d.bcx = b.centre[0]; d.bcy = b.centre[1]; d.bcz = b.centre[2];
+    d.b_in_r = b.radiusa - b.thickness;
+    d.b_in_r2 = ort_sq(d.b_in_r);
+    d.b_out_r = b.radiusa;
+    d.b_out_r2 = ort_sq(b.radiusa);
+    d.b_in_ia2 = 1.0 / ort_sq(b.radiusa - b.thickness);
+    d.b_in_ib2 = 1.0 / ort_sq(b.radiusb - b.thickness);
+    if (j.flags & ORT_FLAG_FIX_OUTER_ELLIPSE) {
+        d.b_out_ia2 = 1.0 / ort_sq(b.radiusa);
+        d.b_out_ib2 = 1.0 / ort_sq(b.radiusb);
+    } else { /* reference src/lens.f90:301 halves the outer radii */
+        d.b_out_ia2 = 1.0 / ort_sq(b.radiusa / 2.0);
+        d.b_out_ib2 = 1.0 / ort_sq(b.radiusb / 2.0);
+    }
+    d.b_in = ort_mk_iface(b.ncontents, b.nbottle);
+    d.b_out = ort_mk_iface(b.nbottle, 1.0);
+    d.mutot_c = b.mua_c + b.mus_c;
+    d.inv_mutot_c = d.mutot_c != 0.0 ? 1.0 / d.mutot_c : 0.0;
+    d.albedo_c = d.mutot_c != 0.0 ? b.mus_c / (b.mus_c + b.mua_c) : 0.0;
+    d.mutot_b = b.mua_b + b.mus_b;
+    d.inv_mutot_b = d.mutot_b != 0.0 ? 1.0 / d.mutot_b : 0.0;
+    d.albedo_b = d.mutot_b != 0.0 ? b.mus_b / (b.mus_b + b.mua_b) : 0.0;
+    d.ellipse = b.ellipse;
+    d.scatter_b = b.scatter_b;
+    d.scatter_c = b.scatter_c;
+
+    d.cos_theta_max = s.cos_theta_max;
+    d.one_m_ctm = 1.0 - s.cos_theta_max;
+    d.point_offset = s.point_offset;
+    d.r1 = s.r1;
+    d.r2_m_r1 = s.r2 - s.r1;
+    d.ra2 = ort_sq(b.radiusa);
+    d.ra_over_rb = b.radiusa / b.radiusb;
+    d.lens_r2 = ort_sq(s.L2.radius + 10e-3);
+    d.l2_fb = s.L2.fb;
+
+    const ort_plano& p = s.L2;
+    d.l2_cx = p.centre[0]; d.l2_cy = p.centre[1]; d.l2_cz = p.centre[2];
+    d.l2_flat_z = p.centre[2] + p.curve_radius - p.thickness;
+    d.l2_radius2 = ort_sq(p.radius);
+    d.l2_R2 = ort_sq(p.curve_radius);
+    d.l2_invR = 1.0 / p.curve_radius;
+    d.l2_fnx = p.flat_normal[0]; d.l2_fny = p.flat_normal[1]; d.l2_fnz = p.flat_normal[2];
+    d.l2_in = ort_mk_iface(p.n1, p.n2);
+    d.l2_out = ort_mk_iface(p.n2, p.n1);
+
+    const ort_doublet& q = s.L3;
+    d.l3_c1x = q.centre1[0]; d.l3_c1y = q.centre1[1]; d.l3_c1z = q.centre1[2];
+    d.l3_c2x = q.centre2[0]; d.l3_c2y = q.centre2[1]; d.l3_c2z = q.centre2[2];
+    d.l3_c3x = q.centre3[0]; d.l3_c3y = q.centre3[1]; d.l3_c3z = q.centre3[2];
+    d.l3_R1_2 = ort_sq(q.R1); d.l3_R2_2 = ort_sq(q.R2); d.l3_R3_2 = ort_sq(q.R3);
+    d.l3_invR1 = 1.0 / q.R1; d.l3_invR2 = 1.0 / q.R2; d.l3_invR3 = 1.0 / q.R3;
+    d.l3_radius2 = ort_sq(q.radius * 1.0);
+    d.l3_iris_r2 = ort_sq(q.radius * j.iris_radius);
+    d.l3_iris1_z = q.centre1[2] - q.R1;
+    d.l3_iris2_z = q.centre3[2] + q.R3;
+    d.l3_s1 = ort_mk_iface(q.n1, q.n2);
+    d.l3_s2 = ort_mk_iface(q.n2, q.n3);
+    d.l3_s3 = ort_mk_iface(q.n3, q.n1);
+
+    d.img_z = s.img_plane + j.fibre_offset;
+    d.binwid = j.image_diameter / 401.0;
+    d.inv_binwid = 401.0 / j.image_diameter;
+    d.cos_na2 = 1.0 - 0.22 * 0.22; /* cos^2(asin(0.22)), reference src/imageMod.f90:40 */
+}
+
+inline void ort_make_dev_job(const ort_job& j, int nscenes, int64_t first, int64_t n, DevJob& d) {
+    memset(&d, 0, sizeof d);
+    d.seed = j.seed;
+    d.first_ray = first;
+    d.nrays = n;
+    d.uniform_override = j.uniform_override;
+    d.phase = j.phase;
+    d.use_bottle = j.use_bottle;
+    d.iris_before = j.iris_before;
+    d.iris_after = j.iris_after;
+    d.nscenes = nscenes;
+    d.stop_after = j.stop_after;
+    d.flags = j.flags;
+}
+
+
+#endif

@@ -1,0 +1,14 @@
+/* ort_internal.h -- declarations shared by the translation units of libort.so */
+#ifndef ORT_INTERNAL_H
+#define ORT_INTERNAL_H
+
+#include "../../include/ort.h"
+#include "ort_dev_types.h"
+
+#if defined(__GNUC__)
+__attribute__((format(printf, 1, 2)))
+#endif
+void ort_set_error(const char* fmt, ...);
+
+
+#endif

@@ -1,0 +1,285 @@
+/*
+ * ort_kernels.cuh -- the CUDA kernels of the trace loop (sm_100a).
+ *
+ *   ort_trace_kernel<PHASE,BOTTLE>   the production megakernel: persistent warps, one thread
+ *                                    per ray, warp-private shared-memory queues that compact
+ *                                    the live rays between surfaces, warp-aggregated 64-bit
+ *                                    reductions into the detector image.
+ *   ort_trace_flat_kernel<...>       the same path without compaction (diagnostic / evidence).
+ *   ort_rays_kernel                  explicit ray list, per-ray outputs (parity entry point).
+ *   ort_uniforms_kernel              exposes the counter-based generator.
+ *   ort_dfma_peak_kernel             FP64 FMA peak micro-benchmark (roofline denominator).
+ *
+ * Replaces the two `!$OMP do` loops of reference src/main.f90:90-109 and :127-162.
+ */
+#ifndef ORT_KERNELS_CUH
+#define ORT_KERNELS_CUH
+
+#include <cuda_runtime.h>
+
+#include "ort_optics.cuh"
+
+__constant__ DevScene c_scenes[ORT_MAX_SCENES];
+__constant__ DevJob c_job;
+
+#define ORT_TPB 256
+#define ORT_WPB (ORT_TPB / 32)
+#define ORT_QCAP 64 /* a queue holds < 32 leftovers + <= 32 new survivors */
+#define ORT_FULL 0xffffffffu
+
+/* structure-of-arrays ray queue private to one warp */
+struct WarpQueue {
+    double px[ORT_QCAP], py[ORT_QCAP], pz[ORT_QCAP], dx[ORT_QCAP], dy[ORT_QCAP], dz[ORT_QCAP];
+    uint32_t id[ORT_QCAP]; /* ray index relative to c_job.first_ray */
+};
+struct WarpShared {
+    WarpQueue q[2];
+    uint32_t hist[ORT_NSTATUS];
+};
+
+__device__ __forceinline__ OrtRng ort_make_rng(uint32_t local_id) {
+    OrtRng g;
+    unsigned long long ray = (unsigned long long)c_job.first_ray + local_id;
+    g.k0 = (uint32_t)c_job.seed;
+    g.k1 = (uint32_t)(c_job.seed >> 32);
+    g.r0 = (uint32_t)ray;
+    g.r1 = (uint32_t)(ray >> 32);
+    g.phase = (uint32_t)c_job.phase;
+    g.override_u = c_job.uniform_override;
+    return g;
+}
+
+__device__ __forceinline__ void ort_q_push(WarpQueue& q, int& n, bool alive, const OrtRay& r,
+                                           uint32_t id, unsigned lane) {
+    unsigned m = __ballot_sync(ORT_FULL, alive);
+    if (alive) {
+        int p = n + __popc(m & ((1u << lane) - 1u));
+        q.px[p] = r.px; q.py[p] = r.py; q.pz[p] = r.pz;
+        q.dx[p] = r.dx; q.dy[p] = r.dy; q.dz[p] = r.dz;
+        q.id[p] = id;
+    }
+    n += __popc(m);
+    __syncwarp();
+}
+__device__ __forceinline__ bool ort_q_pop(WarpQueue& q, int& n, OrtRay& r, uint32_t& id, unsigned lane) {
+    int cnt = n < 32 ? n : 32;
+    int base = n - cnt;
+    bool act = (int)lane < cnt;
+    if (act) {
+        int p = base + lane;
+        r.px = q.px[p]; r.py = q.py[p]; r.pz = q.pz[p];
+        r.dx = q.dx[p]; r.dy = q.dy[p]; r.dz = q.dz[p];
+        id = q.id[p];
+    }
+    n = base;
+    __syncwarp();
+    return act;
+}
+
+/* per-warp histogram of final statuses: one leader per distinct status adds the group size */
+__device__ __forceinline__ void ort_record(uint32_t* hist, int st, unsigned lane) {
+    unsigned m = __match_any_sync(ORT_FULL, st);
+    if (st >= 0 && (int)lane == __ffs(m) - 1) hist[st] += __popc(m);
+    __syncwarp();
+}
+
+/* detector increment, reference src/imageMod.f90:55 (`!$omp atomic`): lanes that hit the same
+ * bin are merged with match.any and one 64-bit RED is issued per distinct bin */
+__device__ __forceinline__ void ort_bin(unsigned long long* img, bool binned, int xp, int yp, unsigned lane) {
+    unsigned key = binned ? (unsigned)((yp + ORT_IMG_HALF) * ORT_IMG_N + (xp + ORT_IMG_HALF)) : 0xffffffffu;
+    unsigned m = __match_any_sync(ORT_FULL, key);
+    if (binned && (int)lane == __ffs(m) - 1) atomicAdd(img + key, (unsigned long long)__popc(m));
+}
+
+/* Stage 0: emit the ray, (point phase) take it through the bottle, carry it to the flat face
+ * of L2 and apply the aperture test.  0 = alive. */
+template <int PHASE, int BOTTLE>
+__device__ __forceinline__ int ort_stage0(const DevScene& S, const OrtRng& g, OrtRay& r) {
+    if (PHASE == ORT_PHASE_RING) {
+        ort_source_ring(S, g, r);
+    } else {
+        ort_source_point(S, g, r);
+        if (BOTTLE == 1) {
+            int st = ort_bottle_forward<false>(S, g, r);
+            if (st) return st;
+        } else if (BOTTLE == 2) {
+            int st = ort_bottle_forward<true>(S, g, r);
+            if (st) return st;
+        }
+    }
+    return ort_l2_enter(S, r);
+}
+/* Stage 1: through L2, up to and including the aperture test on L3's first surface */
+__device__ __forceinline__ int ort_stage1(const DevScene& S, const OrtRng& g, OrtRay& r) {
+    int st = ort_l2_body(S, g, r);
+    if (st) return st;
+    return ort_l3_enter(S, c_job.iris_before != 0, r);
+}
+/* Stage 2: the three refractions of L3, transfer to the image plane, acceptance + binning */
+__device__ __forceinline__ int ort_stage2(const DevScene& S, const OrtRng& g, OrtRay& r, int* xp, int* yp) {
+    int st = ort_l3_body(S, g, c_job.iris_after != 0, r);
+    if (st) return st;
+    return ort_image(S, r, xp, yp);
+}
+
+template <int PHASE, int BOTTLE>
+__global__ void __launch_bounds__(ORT_TPB, 2)
+ort_trace_kernel(unsigned long long* __restrict__ image, unsigned long long* __restrict__ counters) {
+    extern __shared__ __align__(16) unsigned char ort_smem[];
+    WarpShared& ws = reinterpret_cast<WarpShared*>(ort_smem)[threadIdx.x >> 5];
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t nwarps = gridDim.x * ORT_WPB;
+    const uint32_t gwarp = blockIdx.x * ORT_WPB + (threadIdx.x >> 5);
+    const uint32_t nrays = (uint32_t)c_job.nrays;
+    const uint32_t nbatches = (nrays + 31u) >> 5;
+
+    for (int sc = 0; sc < c_job.nscenes; ++sc) {
+        const DevScene& S = c_scenes[sc];
+        unsigned long long* img = image + (size_t)sc * ORT_IMG_BINS;
+        ws.hist[lane] = 0;
+        __syncwarp();
+        int n1 = 0, n2 = 0;
+        uint32_t b = gwarp;
+        for (;;) {
+            int stage;
+            if (n2 >= 32) stage = 2;
+            else if (n1 >= 32) stage = 1;
+            else if (b < nbatches) stage = 0;
+            else if (n2 > 0) stage = 2;
+            else if (n1 > 0) stage = 1;
+            else break;
+
+            OrtRay r;
+            uint32_t id = 0;
+            if (stage == 0) {
+                id = b * 32u + lane;
+                b += nwarps;
+                int st = -1;
+                if (id < nrays) {
+                    OrtRng g = ort_make_rng(id);
+                    st = ort_stage0<PHASE, BOTTLE>(S, g, r);
+                }
+                ort_q_push(ws.q[0], n1, st == 0, r, id, lane);
+                ort_record(ws.hist, st == 0 ? -1 : st, lane);
+            } else if (stage == 1) {
+                bool act = ort_q_pop(ws.q[0], n1, r, id, lane);
+                int st = -1;
+                if (act) {
+                    OrtRng g = ort_make_rng(id);
+                    st = ort_stage1(S, g, r);
+                }
+                ort_q_push(ws.q[1], n2, st == 0, r, id, lane);
+                ort_record(ws.hist, st == 0 ? -1 : st, lane);
+            } else {
+                bool act = ort_q_pop(ws.q[1], n2, r, id, lane);
+                int st = -1, xp = 0, yp = 0;
+                if (act) {
+                    OrtRng g = ort_make_rng(id);
+                    st = ort_stage2(S, g, r, &xp, &yp);
+                }
+                ort_bin(img, st == ORT_ST_BINNED, xp, yp, lane);
+                ort_record(ws.hist, st, lane);
+            }
+        }
+        __syncwarp();
+        if (ws.hist[lane]) atomicAdd(counters + sc * ORT_NSTATUS + lane, (unsigned long long)ws.hist[lane]);
+        __syncwarp();
+    }
+}
+
+/* The same path, one thread per ray from source to detector, no compaction: every early exit
+ * leaves its lane idle until the slowest lane of the warp is done.  Kept to measure what the
+ * compaction buys (warp execution efficiency in ncu) and as a cross-check of the megakernel. */
+template <int PHASE, int BOTTLE>
+__global__ void __launch_bounds__(ORT_TPB, 2)
+ort_trace_flat_kernel(unsigned long long* __restrict__ image, unsigned long long* __restrict__ counters) {
+    __shared__ uint32_t s_hist[ORT_WPB][ORT_NSTATUS];
+    const unsigned lane = threadIdx.x & 31u;
+    uint32_t* hist = s_hist[threadIdx.x >> 5];
+    const uint32_t nwarps = gridDim.x * ORT_WPB;
+    const uint32_t gwarp = blockIdx.x * ORT_WPB + (threadIdx.x >> 5);
+    const uint32_t nrays = (uint32_t)c_job.nrays;
+    const uint32_t nbatches = (nrays + 31u) >> 5;
+    for (int sc = 0; sc < c_job.nscenes; ++sc) {
+        const DevScene& S = c_scenes[sc];
+        unsigned long long* img = image + (size_t)sc * ORT_IMG_BINS;
+        hist[lane] = 0;
+        __syncwarp();
+        for (uint32_t b = gwarp; b < nbatches; b += nwarps) {
+            uint32_t id = b * 32u + lane;
+            int st = -1, xp = 0, yp = 0;
+            if (id < nrays) {
+                OrtRng g = ort_make_rng(id);
+                OrtRay r;
+                st = ort_stage0<PHASE, BOTTLE>(S, g, r);
+                if (st == 0) st = ort_stage1(S, g, r);
+                if (st == 0) st = ort_stage2(S, g, r, &xp, &yp);
+            }
+            ort_bin(img, st == ORT_ST_BINNED, xp, yp, lane);
+            ort_record(hist, st, lane);
+        }
+        __syncwarp();
+        if (hist[lane]) atomicAdd(counters + sc * ORT_NSTATUS + lane, (unsigned long long)hist[lane]);
+        __syncwarp();
+    }
+}
+
+/* Explicit ray list through scene 0; SoA in/out, see ort_trace_rays in include/ort.h */
+__global__ void __launch_bounds__(ORT_TPB)
+ort_rays_kernel(const double* __restrict__ pin, const double* __restrict__ din, double* __restrict__ pout,
+                double* __restrict__ dout, int32_t* __restrict__ status, int32_t* __restrict__ bin, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const DevScene& S = c_scenes[0];
+    OrtRng g = ort_make_rng((uint32_t)i);
+    OrtRay r;
+    int xp = INT32_MIN, yp = INT32_MIN, x = 0, y = 0;
+    const bool have_input = pin != nullptr;
+    if (have_input) {
+        r.px = pin[i]; r.py = pin[n + i]; r.pz = pin[2 * n + i];
+        r.dx = din[i]; r.dy = din[n + i]; r.dz = din[2 * n + i];
+    }
+    int st = ort_full_path(S, c_job, g, have_input, r, &x, &y);
+    if (st == ORT_ST_BINNED) { xp = x; yp = y; }
+    pout[i] = r.px; pout[n + i] = r.py; pout[2 * n + i] = r.pz;
+    dout[i] = r.dx; dout[n + i] = r.dy; dout[2 * n + i] = r.dz;
+    status[i] = st;
+    bin[i] = xp;
+    bin[n + i] = yp;
+}
+
+__global__ void ort_uniforms_kernel(uint64_t seed, int32_t phase, int64_t ray, int32_t first_slot, int32_t n,
+                                    double* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    OrtRng g;
+    g.k0 = (uint32_t)seed; g.k1 = (uint32_t)(seed >> 32);
+    g.r0 = (uint32_t)(uint64_t)ray; g.r1 = (uint32_t)((uint64_t)ray >> 32);
+    g.phase = (uint32_t)phase;
+    g.override_u = -1.0;
+    uint32_t slot = (uint32_t)(first_slot + i);
+    double a, b;
+    ort_draw2(g, slot >> 1, &a, &b);
+    out[i] = (slot & 1u) ? b : a;
+}
+
+/* FP64 FMA peak: 8 independent DFMA chains per thread, ITERS x 8 x 2 flops per thread */
+#define ORT_PEAK_ITERS 16384
+__global__ void __launch_bounds__(256) ort_dfma_peak_kernel(double* __restrict__ out, double seed,
+                                                            long long* __restrict__ cycles) {
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
+           a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 0.999999, c = 1e-9;
+    long long t0 = clock64();
+#pragma unroll 8
+    for (int i = 0; i < ORT_PEAK_ITERS; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    long long t1 = clock64();
+    double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 123.456) out[0] = s; /* keep the chains alive */
+    if (threadIdx.x == 0 && blockIdx.x == 0) cycles[0] = t1 - t0;
+}
+
+#endif /* ORT_KERNELS_CUH */

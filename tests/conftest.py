@@ -1,0 +1,73 @@
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+RES = os.path.join(ROOT, "res")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def orc():
+    """The CPU oracle (test infrastructure)."""
+    from tests import oracle_lib
+    oracle_lib.lib()
+    return oracle_lib
+
+
+@pytest.fixture(scope="session")
+def harness():
+    """Product optics header compiled for the host (test-only)."""
+    from opticalraytrace_b200 import abi
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests"), "-s"])
+    H = C.CDLL(os.path.join(ROOT, "tests", "libhost_harness.so"))
+    H.hh_trace_rays.argtypes = [C.POINTER(abi.Job), C.POINTER(abi.Scene), C.c_int64] + [C.c_void_p] * 6
+
+    def run(job, scene, n, pos_in=None, dir_in=None):
+        po, do = np.zeros((3, n)), np.zeros((3, n))
+        st, b = np.zeros(n, np.int32), np.zeros((2, n), np.int32)
+        pi = di = None
+        if pos_in is not None:
+            pin = np.ascontiguousarray(pos_in, dtype=np.float64)
+            din = np.ascontiguousarray(dir_in, dtype=np.float64)
+            pi, di = pin.ctypes.data, din.ctypes.data
+        H.hh_trace_rays(C.byref(job), C.byref(scene), n, pi, di, po.ctypes.data, do.ctypes.data,
+                        st.ctypes.data, b.ctypes.data)
+        return dict(pos=po, dir=do, status=st, bin=b)
+    return run
+
+
+@pytest.fixture(scope="session")
+def ortlib():
+    """libort.so built (no device needed)."""
+    from opticalraytrace_b200 import lib
+    so = lib.LIB_PATH
+    if not os.path.exists(so):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "opticalraytrace_b200", "csrc"), "-s"])
+    lib.load()
+    return lib
+
+
+@pytest.fixture(scope="session")
+def ort(ortlib):
+    """Initialised on cuda:0 -- fails loudly when there is no device (no CPU fallback)."""
+    ortlib.init(1)
+    yield ortlib
+    ortlib.finalize()
+
+
+def rel_err(a, b):
+    """per-ray max-abs difference relative to the vector's largest component"""
+    d = np.abs(a - b).max(axis=0)
+    s = np.maximum(np.abs(a).max(axis=0), 1e-300)
+    return d / s

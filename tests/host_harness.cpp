@@ -1,0 +1,45 @@
+/*
+ * host_harness.cpp -- TEST INFRASTRUCTURE ONLY (never part of libort.so, never a fallback).
+ *
+ * Compiles the product's per-ray optics header (opticalraytrace_b200/csrc/ort_optics.cuh) and
+ * scene flattening for the HOST, so the reformulated arithmetic the kernels run (one-division
+ * quadratics, fused Fresnel+Snell, hoisted normals, squared-radius tests ...) can be compared
+ * against the oracle on a machine without a GPU.  The GPU tests (-m gpu) then check the same
+ * header compiled for sm_100a through the real C-ABI.
+ */
+#include <cstdint>
+#include <cstring>
+
+#include "../opticalraytrace_b200/csrc/ort_flatten.h"
+#include "../opticalraytrace_b200/csrc/ort_optics.cuh"
+
+extern "C" int hh_trace_rays(const ort_job* job, const ort_scene* scene, int64_t n, const double* pin,
+                             const double* din, double* pout, double* dout, int32_t* status, int32_t* bin) {
+    DevScene S;
+    DevJob J;
+    ort_flatten_scene(*scene, *job, S);
+    ort_make_dev_job(*job, 1, job->first_ray, n, J);
+    const bool have = pin != nullptr;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        OrtRng g;
+        uint64_t ray = (uint64_t)J.first_ray + (uint64_t)i;
+        g.k0 = (uint32_t)J.seed; g.k1 = (uint32_t)(J.seed >> 32);
+        g.r0 = (uint32_t)ray; g.r1 = (uint32_t)(ray >> 32);
+        g.phase = (uint32_t)J.phase;
+        g.override_u = J.uniform_override;
+        OrtRay r = {0, 0, 0, 0, 0, 1};
+        if (have) {
+            r.px = pin[i]; r.py = pin[n + i]; r.pz = pin[2 * n + i];
+            r.dx = din[i]; r.dy = din[n + i]; r.dz = din[2 * n + i];
+        }
+        int x = 0, y = 0;
+        int st = ort_full_path(S, J, g, have, r, &x, &y);
+        pout[i] = r.px; pout[n + i] = r.py; pout[2 * n + i] = r.pz;
+        dout[i] = r.dx; dout[n + i] = r.dy; dout[2 * n + i] = r.dz;
+        status[i] = st;
+        bin[i] = st == ORT_ST_BINNED ? x : INT32_MIN;
+        bin[n + i] = st == ORT_ST_BINNED ? y : INT32_MIN;
+    }
+    return 0;
+}
