@@ -37,10 +37,15 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-WORKLOAD = ("config2-ring: ring source on clearBottle-large -> planoConvex-f39.9mm -> "
-            "achromaticDoublet-f50.0mm -> 401x401 detector, 785 nm")
+WORKLOADS = {
+    "ring": ("config2-ring: ring source on clearBottle-large -> planoConvex-f39.9mm -> "
+             "achromaticDoublet-f50.0mm -> 401x401 detector, 785 nm"),
+    "point": ("config2-point: point source in clearBottle-large -> planoConvex-f39.9mm -> "
+              "achromaticDoublet-f50.0mm (lenses at 843 nm) -> 401x401 detector"),
+}
+WORKLOAD = WORKLOADS["ring"]
 FILES = ("clearBottle-large.params", "planoConvex-f39.9mm.params", "achromaticDoublet-f50.0mm.params")
-RAYS_PER_GPU = 1 << 30
+RAYS_PER_GPU = 1 << 34
 CPU_SAMPLE = 30_000_000
 
 # Algorithmic fp64 flops by final status (SURVEY.md 8(d) convention: + - * / sqrt and libm calls
@@ -176,6 +181,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rays", type=int, default=RAYS_PER_GPU, help="rays per GPU per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--phase", default="ring", choices=["ring", "point"],
+                    help="ring = BASELINE.json configs[1] (the headline); point = the other loop")
+    ap.add_argument("--flat", action="store_true", help="diagnostic: kernel without compaction")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -208,14 +216,18 @@ def main():
         torch.cuda.synchronize()
 
     st = lib.make_settings(*FILES, nphotons=args.rays)
-    scene, _ = lib.build_scene(st, os.path.join(ROOT, "res"))
+    phase = abi.PHASE_RING if args.phase == "ring" else abi.PHASE_POINT
+    # the point loop runs with the lenses re-built at 843 nm (reference src/main.f90:113-117)
+    scene, _ = lib.build_scene(st, os.path.join(ROOT, "res"), None if phase == 1 else 843e-9)
     n = args.rays
 
-    def step(k, want_image=True):
-        job = lib.job_from_settings(st, abi.PHASE_RING)
-        job.first_ray = (k * world + rank) * n
-        job.nrays = n
-        return lib.trace(job, scene, want_image=want_image)
+    def step(k, want_image=True, ph=phase, sc=scene, nr=n):
+        job = lib.job_from_settings(st, ph)
+        job.first_ray = (k * world + rank) * nr
+        job.nrays = nr
+        if args.flat:
+            job.flags |= abi.FLAG_NO_COMPACTION
+        return lib.trace(job, sc, want_image=want_image)
 
     for k in range(args.warmup):
         step(k)
@@ -248,7 +260,7 @@ def main():
 
     if rank == 0:
         # rank 0's histogram holds the reduced counts of all ranks (it is the reduce root)
-        flops = float((flops_by_status(1) * hist).sum())
+        flops = float((flops_by_status(phase) * hist).sum())
         achieved = flops / dev_s * 1e-12
         cpu = None
         if world == 1 and not args.no_cpu:
@@ -263,7 +275,8 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_s / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "rays_per_gpu_per_step": n,
+            "config": {"workload": WORKLOADS[args.phase] + (" [no compaction]" if args.flat else ""),
+                       "rays_per_gpu_per_step": n,
                        "rays_per_step": n * world, "parallelism": "ray-range x%d" % world,
                        "l2": "no input arrays (rays are generated on the device); the 2.6 MB "
                              "image buffer is re-zeroed every step",
@@ -280,6 +293,8 @@ def main():
                                         "(MEASURED_PEAKS.json holds no FP64 figure)" % peak_mhz,
                          "flops_per_launched_ray": flops / (total_rays)},
             "cpu_baseline": cpu,
+            "status_fractions": {abi.STATUS_NAMES[i]: hist[i] / total_rays
+                                 for i in range(26) if hist[i]},
         }
         print(json.dumps(line), flush=True)
     lib.finalize()

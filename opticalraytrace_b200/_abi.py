@@ -1,7 +1,7 @@
 """ctypes mirror of include/ort.h -- field for field, same order.
 
-Kept free of any library loading so both the product binding (opticalraytrace_b200.lib) and the
-test-only oracle binding (tests/oracle_lib.py) can share the struct definitions.
+Kept free of any library loading so the product binding (opticalraytrace_b200.lib) and the
+test-only checker binding under tests/ can share the struct definitions.
 """
 import ctypes as C
 

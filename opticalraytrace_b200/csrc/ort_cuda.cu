@@ -518,12 +518,13 @@ extern "C" int ort_measure_fp64_peak(double* tflops, double* sm_clock_mhz) {
     DeviceCtx& c = g.devs[0];
     CK(cudaSetDevice(c.dev));
     double* d_out = nullptr;
-    long long* d_cyc = nullptr;
+    unsigned long long* d_cyc = nullptr;
     CK(cudaMalloc(&d_out, sizeof(double)));
-    CK(cudaMalloc(&d_cyc, sizeof(long long)));
+    CK(cudaMalloc(&d_cyc, sizeof(unsigned long long)));
     const int grid = c.num_sms * 8, tpb = 256;
     double best = 0.0, mhz = 0.0;
     for (int rep = 0; rep < 6; ++rep) {
+        CK(cudaMemsetAsync(d_cyc, 0, sizeof(unsigned long long), c.stream));
         CK(cudaEventRecord(c.ev_start, c.stream));
         ort_dfma_peak_kernel<<<grid, tpb, 0, c.stream>>>(d_out, 1.0 + rep, d_cyc);
         CK(cudaGetLastError());
@@ -535,9 +536,7 @@ extern "C" int ort_measure_fp64_peak(double* tflops, double* sm_clock_mhz) {
         double tf = flops / (ms * 1e-3) * 1e-12;
         if (rep >= 1 && tf > best) {
             best = tf;
-            /* each SM hosts 8 of these 256-thread blocks at once: one block's cycle count spans
-             * the whole kernel, so cycles / time ~ the SM clock during the run */
-            long long cyc = 0;
+            unsigned long long cyc = 0;
             CK(cudaMemcpy(&cyc, d_cyc, sizeof cyc, cudaMemcpyDeviceToHost));
             mhz = (double)cyc / (ms * 1e-3) * 1e-6;
         }

@@ -266,7 +266,7 @@ __global__ void ort_uniforms_kernel(uint64_t seed, int32_t phase, int64_t ray, i
 /* FP64 FMA peak: 8 independent DFMA chains per thread, ITERS x 8 x 2 flops per thread */
 #define ORT_PEAK_ITERS 16384
 __global__ void __launch_bounds__(256) ort_dfma_peak_kernel(double* __restrict__ out, double seed,
-                                                            long long* __restrict__ cycles) {
+                                                            unsigned long long* __restrict__ cycles) {
     double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
            a6 = a0 + 6, a7 = a0 + 7;
     const double m = 0.999999, c = 1e-9;
@@ -279,7 +279,9 @@ __global__ void __launch_bounds__(256) ort_dfma_peak_kernel(double* __restrict__
     long long t1 = clock64();
     double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
     if (s == 123.456) out[0] = s; /* keep the chains alive */
-    if (threadIdx.x == 0 && blockIdx.x == 0) cycles[0] = t1 - t0;
+    /* all blocks are resident from the start (8 x 256 threads per SM), so the longest-lived
+     * block spans the whole kernel: max(t1 - t0) / kernel time = SM clock under this load */
+    if (threadIdx.x == 0) atomicMax(cycles, (unsigned long long)(t1 - t0));
 }
 
 #endif /* ORT_KERNELS_CUH */
