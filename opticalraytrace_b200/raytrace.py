@@ -34,7 +34,7 @@ def run(settings_path, resdir, datadir=None, *, nphotons=None, write=True, verbo
                   " Deselecting tracking of packets\n ***************")
         st.use_tracker = 0
     src = st.source_type.decode()
-    if src not in ("point", "crs", "isors"):
+    if src != "point":  # crs / isors / image / spot emit differently in one of the two loops
         raise lib.OrtError(abi.ORT_EINVAL, "source type '%s' is not on the B200 path yet "
                                            "(point / ring phases only)" % src)
     scene_ring, pre_guard = lib.build_scene(st, resdir, st.wavelength)
