@@ -224,6 +224,10 @@ int ort_uniforms(uint64_t seed, int32_t phase, int64_t ray, int32_t first_slot, 
  * Returns TFLOP/s in *tflops. */
 int ort_measure_fp64_peak(double* tflops, double* sm_clock_mhz);
 
+/* Accuracy of the library's fast fp64 reciprocal / division / sqrt / rsqrt on device 0: worst
+ * error in units of the last place over n pseudo-random operands (order: rcp, div, sqrt, rsqrt). */
+int ort_math_selftest(int64_t n, uint64_t max_ulp[4]);
+
 /* ---- host side of the drop-in surface (no device needed) -------------------------------- */
 int ort_load_plano(const char* path, double wavelength, double offset, ort_plano* out);
 int ort_load_doublet(const char* path, double wavelength, double offset, ort_doublet* out);

@@ -262,7 +262,7 @@ static int validate_job(const ort_job* job) {
 /* ------------------------------------------------------------------------------------------
  * kernel dispatch
  * ---------------------------------------------------------------------------------------- */
-typedef void (*trace_kernel_t)(unsigned long long*, unsigned long long*);
+typedef void (*trace_kernel_t)(const DevScene, const DevJob, unsigned long long*, unsigned long long*);
 
 static trace_kernel_t pick_kernel(int phase, int bottle_mode, bool flat) {
     if (phase == ORT_PHASE_RING)
@@ -302,21 +302,23 @@ static int enqueue_trace(DeviceCtx& c, const ort_job& job, const std::vector<Dev
 
     CK(cudaEventRecord(c.ev_start, c.stream));
     CK(cudaMemsetAsync(c.d_buf, 0, elems * sizeof(unsigned long long), c.stream));
-    CK(cudaMemcpyToSymbolAsync(c_scenes, ds.data(), sizeof(DevScene) * nscenes, 0, cudaMemcpyHostToDevice,
-                               c.stream));
     unsigned long long* d_img = c.d_buf;
     unsigned long long* d_cnt = c.d_buf + (size_t)nscenes * ORT_IMG_BINS;
-    for (int64_t off = 0; off < n; off += ORT_CHUNK) {
-        int64_t m = n - off < ORT_CHUNK ? n - off : ORT_CHUNK;
-        DevJob dj;
-        ort_make_dev_job(job, nscenes, first + off, m, dj);
-        CK(cudaMemcpyToSymbolAsync(c_job, &dj, sizeof dj, 0, cudaMemcpyHostToDevice, c.stream));
-        int64_t batches = (m + 31) / 32;
-        int64_t want = (batches + ORT_WPB - 1) / ORT_WPB;
-        int gsz = (int)(want < grid ? (want > 0 ? want : 1) : grid);
-        k<<<gsz, ORT_TPB, smem, c.stream>>>(d_img, d_cnt);
-        CK(cudaGetLastError());
-        ++*launches;
+    /* one launch per scene and per <= 2^31-ray chunk, back to back on the stream; scene and job
+     * travel as kernel parameters, so there is nothing to upload between launches */
+    for (int sc = 0; sc < nscenes; ++sc) {
+        for (int64_t off = 0; off < n; off += ORT_CHUNK) {
+            int64_t m = n - off < ORT_CHUNK ? n - off : ORT_CHUNK;
+            DevJob dj;
+            ort_make_dev_job(job, nscenes, first + off, m, dj);
+            int64_t batches = (m + 31) / 32;
+            int64_t want = (batches + ORT_WPB - 1) / ORT_WPB;
+            int gsz = (int)(want < grid ? (want > 0 ? want : 1) : grid);
+            k<<<gsz, ORT_TPB, smem, c.stream>>>(ds[sc], dj, d_img + (size_t)sc * ORT_IMG_BINS,
+                                                d_cnt + (size_t)sc * ORT_NSTATUS);
+            CK(cudaGetLastError());
+            ++*launches;
+        }
     }
     CK(cudaEventRecord(c.ev_traced, c.stream));
     return ORT_OK;
@@ -415,7 +417,8 @@ extern "C" int ort_trace(const ort_job* job, const ort_scene* scenes, int nscene
         timing->trace_seconds = tmax * 1e-3;
         timing->reduce_seconds = reduced ? rmax * 1e-3 : 0.0;
         timing->kernel_launches = launches;
-        timing->h2d_bytes = (int64_t)(G * (sizeof(DevScene) * nscenes + sizeof(DevJob) * ((job->nrays / G + ORT_CHUNK) / ORT_CHUNK)));
+        /* scene + job of every launch travel host -> device as kernel parameters */
+        timing->h2d_bytes = (int64_t)(launches * (int64_t)(sizeof(DevScene) + sizeof(DevJob)));
         timing->d2h_bytes = (int64_t)d2h;
         timing->wall_seconds =
             std::chrono::duration<double>(std::chrono::steady_clock::now() - w0).count();
@@ -447,8 +450,6 @@ extern "C" int ort_trace_rays(const ort_job* job, const ort_scene* scene, int64_
     ort_flatten_scene(*scene, *job, ds);
     DevJob dj;
     ort_make_dev_job(*job, 1, job->first_ray, n, dj);
-    CK(cudaMemcpyToSymbolAsync(c_scenes, &ds, sizeof ds, 0, cudaMemcpyHostToDevice, c.stream));
-    CK(cudaMemcpyToSymbolAsync(c_job, &dj, sizeof dj, 0, cudaMemcpyHostToDevice, c.stream));
     double *d_in = nullptr, *d_out = nullptr;
     int32_t* d_int = nullptr;
     size_t vb = (size_t)3 * n * sizeof(double);
@@ -471,8 +472,8 @@ extern "C" int ort_trace_rays(const ort_job* job, const ort_scene* scene, int64_
         CKB(cudaMalloc(&d_out, 2 * vb));
         CKB(cudaMalloc(&d_int, (size_t)3 * n * sizeof(int32_t)));
         int grid = (int)((n + ORT_TPB - 1) / ORT_TPB);
-        ort_rays_kernel<<<grid, ORT_TPB, 0, c.stream>>>(d_in, d_in ? d_in + 3 * n : nullptr, d_out, d_out + 3 * n,
-                                                        d_int, d_int + n, (long long)n);
+        ort_rays_kernel<<<grid, ORT_TPB, 0, c.stream>>>(ds, dj, d_in, d_in ? d_in + 3 * n : nullptr, d_out,
+                                                        d_out + 3 * n, d_int, d_int + n, (long long)n);
         CKB(cudaGetLastError());
         if (pos_out) CKB(cudaMemcpyAsync(pos_out, d_out, vb, cudaMemcpyDeviceToHost, c.stream));
         if (dir_out) CKB(cudaMemcpyAsync(dir_out, d_out + 3 * n, vb, cudaMemcpyDeviceToHost, c.stream));
@@ -545,5 +546,30 @@ extern "C" int ort_measure_fp64_peak(double* tflops, double* sm_clock_mhz) {
     cudaFree(d_cyc);
     if (tflops) *tflops = best;
     if (sm_clock_mhz) *sm_clock_mhz = mhz;
+    return ORT_OK;
+}
+
+extern "C" int ort_math_selftest(int64_t n, uint64_t max_ulp[4]) {
+    if (!g.ready) {
+        ort_set_error("ort_math_selftest: library not initialised");
+        return ORT_ENODEVICE;
+    }
+    if (n <= 0 || !max_ulp) return ORT_EINVAL;
+    DeviceCtx& c = g.devs[0];
+    CK(cudaSetDevice(c.dev));
+    unsigned long long* d = nullptr;
+    CK(cudaMalloc(&d, 4 * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(d, 0, 4 * sizeof(unsigned long long), c.stream));
+    ort_math_selftest_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>((long long)n, d);
+    cudaError_t e = cudaGetLastError();
+    unsigned long long h[4] = {0, 0, 0, 0};
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, c.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);
+    cudaFree(d);
+    if (e != cudaSuccess) {
+        ort_set_error("ort_math_selftest: %s", cudaGetErrorString(e));
+        return ORT_ECUDA;
+    }
+    for (int i = 0; i < 4; ++i) max_ulp[i] = h[i];
     return ORT_OK;
 }

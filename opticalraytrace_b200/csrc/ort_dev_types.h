@@ -14,7 +14,8 @@
 
 #include "../../include/ort.h"
 
-#define ORT_MAX_SCENES 64 /* scenes per launch held in __constant__ memory (64 * 712 B = 45 KiB) */
+#define ORT_MAX_SCENES 4096 /* scenes per ort_trace call; each scene is its own kernel launch and
+                               travels as a __grid_constant__ kernel parameter (712 B) */
 
 /* One refracting interface n_a -> n_b */
 struct DevIface {
@@ -59,7 +60,10 @@ struct DevScene {
     double inv_binwid;            /* 401 / diameter */
     double binwid;                /* diameter / 401 */
     double cos_na2;               /* cos(asin(0.22))^2 */
-    int32_t ellipse, scatter_b, scatter_c, _pad;
+    int32_t ellipse, scatter_b, scatter_c;
+    int32_t ring_shortcut;        /* L2's flat face lies in the ring source's aim plane z = fb (true for
+                                     every lens the loaders build): the aperture test reduces to
+                                     u * lens_r2 > radius^2 and is taken before anything else */
 };
 
 struct DevJob {

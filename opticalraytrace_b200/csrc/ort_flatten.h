@@ -4,6 +4,7 @@
 #ifndef ORT_FLATTEN_H
 #define ORT_FLATTEN_H
 
+#include <cmath>
 #include <cstring>
 
 #include "ort_dev_types.h"
@@ -88,6 +89,9 @@ inline void ort_flatten_scene(const ort_scene& s, const ort_job& j, DevScene& d)
     d.binwid = j.image_diameter / 401.0;
     d.inv_binwid = 401.0 / j.image_diameter;
     d.cos_na2 = 1.0 - 0.22 * 0.22; /* cos^2(asin(0.22)), reference src/imageMod.f90:40 */
+    /* flat_z = (fb + th - R) + R - th: equal to fb up to rounding for loader-built lenses */
+    d.ring_shortcut = (p.centre[0] == 0.0 && p.centre[1] == 0.0 &&
+                       std::fabs(d.l2_flat_z - d.l2_fb) <= 4e-16 * std::fabs(d.l2_fb)) ? 1 : 0;
 }
 
 inline void ort_make_dev_job(const ort_job& j, int nscenes, int64_t first, int64_t n, DevJob& d) {

@@ -9,8 +9,14 @@
  *   ort_rays_kernel                  explicit ray list, per-ray outputs (parity entry point).
  *   ort_uniforms_kernel              exposes the counter-based generator.
  *   ort_dfma_peak_kernel             FP64 FMA peak micro-benchmark (roofline denominator).
+ *   ort_math_selftest_kernel         ulp error of the fast reciprocal / division / sqrt.
  *
  * Replaces the two `!$OMP do` loops of reference src/main.f90:90-109 and :127-162.
+ *
+ * Scene and job arrive as __grid_constant__ kernel parameters: they sit in the constant bank the
+ * launch already uses, so every scene scalar is an immediate c[0][off] operand of the DFMA that
+ * needs it (the first build indexed a __constant__ array with the scene number, which cost an
+ * LDC through the address-divergence unit per scalar: 16-19 % ADU utilisation in ncu).
  */
 #ifndef ORT_KERNELS_CUH
 #define ORT_KERNELS_CUH
@@ -19,33 +25,34 @@
 
 #include "ort_optics.cuh"
 
-__constant__ DevScene c_scenes[ORT_MAX_SCENES];
-__constant__ DevJob c_job;
-
+#ifndef ORT_TPB
 #define ORT_TPB 256
+#endif
 #define ORT_WPB (ORT_TPB / 32)
 #define ORT_QCAP 64 /* a queue holds < 32 leftovers + <= 32 new survivors */
 #define ORT_FULL 0xffffffffu
+#ifndef ORT_MIN_BLOCKS
+#define ORT_MIN_BLOCKS 2
+#endif
 
 /* structure-of-arrays ray queue private to one warp */
 struct WarpQueue {
     double px[ORT_QCAP], py[ORT_QCAP], pz[ORT_QCAP], dx[ORT_QCAP], dy[ORT_QCAP], dz[ORT_QCAP];
-    uint32_t id[ORT_QCAP]; /* ray index relative to c_job.first_ray */
+    uint32_t id[ORT_QCAP]; /* ray index relative to DevJob.first_ray */
 };
 struct WarpShared {
     WarpQueue q[2];
-    uint32_t hist[ORT_NSTATUS];
 };
 
-__device__ __forceinline__ OrtRng ort_make_rng(uint32_t local_id) {
+__device__ __forceinline__ OrtRng ort_make_rng(const DevJob& J, uint32_t local_id) {
     OrtRng g;
-    unsigned long long ray = (unsigned long long)c_job.first_ray + local_id;
-    g.k0 = (uint32_t)c_job.seed;
-    g.k1 = (uint32_t)(c_job.seed >> 32);
+    unsigned long long ray = (unsigned long long)J.first_ray + local_id;
+    g.k0 = (uint32_t)J.seed;
+    g.k1 = (uint32_t)(J.seed >> 32);
     g.r0 = (uint32_t)ray;
     g.r1 = (uint32_t)(ray >> 32);
-    g.phase = (uint32_t)c_job.phase;
-    g.override_u = c_job.uniform_override;
+    g.phase = (uint32_t)J.phase;
+    g.override_u = J.uniform_override;
     return g;
 }
 
@@ -76,26 +83,48 @@ __device__ __forceinline__ bool ort_q_pop(WarpQueue& q, int& n, OrtRay& r, uint3
     return act;
 }
 
-/* per-warp histogram of final statuses: one leader per distinct status adds the group size */
-__device__ __forceinline__ void ort_record(uint32_t* hist, int st, unsigned lane) {
-    unsigned m = __match_any_sync(ORT_FULL, st);
-    if (st >= 0 && (int)lane == __ffs(m) - 1) hist[st] += __popc(m);
-    __syncwarp();
+/* Histogram of final ray statuses, kept in registers: lane s of the warp owns the counter of
+ * status s.  A stage can only end a ray with a handful of statuses known at compile time, so
+ * the update is one ballot + popc per candidate (no atomics, no match.any, no shared memory). */
+template <int K>
+__device__ __forceinline__ void ort_count_one(unsigned& mine, int st, unsigned lane) {
+    unsigned c = __popc(__ballot_sync(ORT_FULL, st == K));
+    if (lane == (unsigned)K) mine += c;
+}
+template <int... KS>
+__device__ __forceinline__ void ort_count(unsigned& mine, int st, unsigned lane) {
+    if (__any_sync(ORT_FULL, st >= 0)) {
+        (ort_count_one<KS>(mine, st, lane), ...);
+    }
 }
 
 /* detector increment, reference src/imageMod.f90:55 (`!$omp atomic`): lanes that hit the same
  * bin are merged with match.any and one 64-bit RED is issued per distinct bin */
 __device__ __forceinline__ void ort_bin(unsigned long long* img, bool binned, int xp, int yp, unsigned lane) {
+    if (!__any_sync(ORT_FULL, binned)) return;
     unsigned key = binned ? (unsigned)((yp + ORT_IMG_HALF) * ORT_IMG_N + (xp + ORT_IMG_HALF)) : 0xffffffffu;
     unsigned m = __match_any_sync(ORT_FULL, key);
     if (binned && (int)lane == __ffs(m) - 1) atomicAdd(img + key, (unsigned long long)__popc(m));
 }
 
-/* Stage 0: emit the ray, (point phase) take it through the bottle, carry it to the flat face
- * of L2 and apply the aperture test.  0 = alive. */
+/* ---- stages ------------------------------------------------------------------------------
+ * A: emit.  Ring phase with the aim-plane shortcut: draw the aim point only and drop the 69 % of
+ *    rays aimed outside L2's aperture (the survivors carry (u2,u3) in the queue).  Otherwise:
+ *    full source, (point phase) both bottle walls, carry to L2's flat face, aperture test.
+ * B: (ring shortcut: the rest of the source, then) through L2, up to and including the aperture
+ *    test on L3's first surface.
+ * C: the three refractions of L3, transfer to the image plane, acceptance + binning. */
 template <int PHASE, int BOTTLE>
-__device__ __forceinline__ int ort_stage0(const DevScene& S, const OrtRng& g, OrtRay& r) {
+__device__ __forceinline__ int ort_stage_a(const DevScene& S, const OrtRng& g, OrtRay& r) {
     if (PHASE == ORT_PHASE_RING) {
+        if (S.ring_shortcut) {
+            double u2, u3;
+            ort_draw2(g, 1, &u2, &u3);
+            r.px = u2;
+            r.py = u3;
+            r.pz = r.dx = r.dy = r.dz = 0.0;
+            return ort_ring_aims_outside_aperture(S, u2) ? ORT_ST_L2_APERTURE : 0;
+        }
         ort_source_ring(S, g, r);
     } else {
         ort_source_point(S, g, r);
@@ -109,129 +138,138 @@ __device__ __forceinline__ int ort_stage0(const DevScene& S, const OrtRng& g, Or
     }
     return ort_l2_enter(S, r);
 }
-/* Stage 1: through L2, up to and including the aperture test on L3's first surface */
-__device__ __forceinline__ int ort_stage1(const DevScene& S, const OrtRng& g, OrtRay& r) {
+template <int PHASE>
+__device__ __forceinline__ int ort_stage_b(const DevScene& S, const DevJob& J, const OrtRng& g, OrtRay& r) {
+    if (PHASE == ORT_PHASE_RING && S.ring_shortcut) {
+        double u0, u1, u2 = r.px, u3 = r.py;
+        ort_draw2(g, 0, &u0, &u1);
+        ort_source_ring_u(S, u0, u1, u2, u3, r);
+        int st0 = ort_l2_enter(S, r); /* same arithmetic as the general path; cannot fail except
+                                         within rounding of the aperture edge */
+        if (st0) return st0;
+    }
     int st = ort_l2_body(S, g, r);
     if (st) return st;
-    return ort_l3_enter(S, c_job.iris_before != 0, r);
+    return ort_l3_enter(S, J.iris_before != 0, r);
 }
-/* Stage 2: the three refractions of L3, transfer to the image plane, acceptance + binning */
-__device__ __forceinline__ int ort_stage2(const DevScene& S, const OrtRng& g, OrtRay& r, int* xp, int* yp) {
-    int st = ort_l3_body(S, g, c_job.iris_after != 0, r);
+__device__ __forceinline__ int ort_stage_c(const DevScene& S, const DevJob& J, const OrtRng& g, OrtRay& r,
+                                           int* xp, int* yp) {
+    int st = ort_l3_body(S, g, J.iris_after != 0, r);
     if (st) return st;
     return ort_image(S, r, xp, yp);
 }
 
+/* statuses a ray can end with, per stage */
+#define ORT_COUNT_A(mine, st, lane) ort_count<1, 2, 3, 4, 5, 6, 7, 8, 9, 24>(mine, st, lane)
+#define ORT_COUNT_A_RING(mine, st, lane) ort_count<9>(mine, st, lane)
+#define ORT_COUNT_A_CLEAR(mine, st, lane) ort_count<1, 4, 5, 8, 9>(mine, st, lane)
+#define ORT_COUNT_B(mine, st, lane) ort_count<9, 10, 11, 12, 13, 14>(mine, st, lane)
+#define ORT_COUNT_C(mine, st, lane) ort_count<0, 15, 16, 17, 18, 19, 20, 21, 22, 23>(mine, st, lane)
+
 template <int PHASE, int BOTTLE>
-__global__ void __launch_bounds__(ORT_TPB, 2)
-ort_trace_kernel(unsigned long long* __restrict__ image, unsigned long long* __restrict__ counters) {
+__device__ __forceinline__ void ort_count_a(unsigned& mine, int st, unsigned lane) {
+    if (PHASE == ORT_PHASE_RING || BOTTLE == 0) ORT_COUNT_A_RING(mine, st, lane);
+    else if (BOTTLE == 1) ORT_COUNT_A_CLEAR(mine, st, lane);
+    else ORT_COUNT_A(mine, st, lane);
+}
+
+template <int PHASE, int BOTTLE>
+__global__ void __launch_bounds__(ORT_TPB, ORT_MIN_BLOCKS)
+ort_trace_kernel(const __grid_constant__ DevScene S, const __grid_constant__ DevJob J,
+                 unsigned long long* __restrict__ img, unsigned long long* __restrict__ counters) {
     extern __shared__ __align__(16) unsigned char ort_smem[];
     WarpShared& ws = reinterpret_cast<WarpShared*>(ort_smem)[threadIdx.x >> 5];
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t nwarps = gridDim.x * ORT_WPB;
     const uint32_t gwarp = blockIdx.x * ORT_WPB + (threadIdx.x >> 5);
-    const uint32_t nrays = (uint32_t)c_job.nrays;
+    const uint32_t nrays = (uint32_t)J.nrays;
     const uint32_t nbatches = (nrays + 31u) >> 5;
 
-    for (int sc = 0; sc < c_job.nscenes; ++sc) {
-        const DevScene& S = c_scenes[sc];
-        unsigned long long* img = image + (size_t)sc * ORT_IMG_BINS;
-        ws.hist[lane] = 0;
-        __syncwarp();
-        int n1 = 0, n2 = 0;
-        uint32_t b = gwarp;
-        for (;;) {
-            int stage;
-            if (n2 >= 32) stage = 2;
-            else if (n1 >= 32) stage = 1;
-            else if (b < nbatches) stage = 0;
-            else if (n2 > 0) stage = 2;
-            else if (n1 > 0) stage = 1;
-            else break;
+    unsigned mine = 0; /* count of rays that ended with status == lane */
+    int n1 = 0, n2 = 0;
+    uint32_t b = gwarp;
+    for (;;) {
+        int stage;
+        if (n2 >= 32) stage = 2;
+        else if (n1 >= 32) stage = 1;
+        else if (b < nbatches) stage = 0;
+        else if (n2 > 0) stage = 2;
+        else if (n1 > 0) stage = 1;
+        else break;
 
-            OrtRay r;
-            uint32_t id = 0;
-            if (stage == 0) {
-                id = b * 32u + lane;
-                b += nwarps;
-                int st = -1;
-                if (id < nrays) {
-                    OrtRng g = ort_make_rng(id);
-                    st = ort_stage0<PHASE, BOTTLE>(S, g, r);
-                }
-                ort_q_push(ws.q[0], n1, st == 0, r, id, lane);
-                ort_record(ws.hist, st == 0 ? -1 : st, lane);
-            } else if (stage == 1) {
-                bool act = ort_q_pop(ws.q[0], n1, r, id, lane);
-                int st = -1;
-                if (act) {
-                    OrtRng g = ort_make_rng(id);
-                    st = ort_stage1(S, g, r);
-                }
-                ort_q_push(ws.q[1], n2, st == 0, r, id, lane);
-                ort_record(ws.hist, st == 0 ? -1 : st, lane);
-            } else {
-                bool act = ort_q_pop(ws.q[1], n2, r, id, lane);
-                int st = -1, xp = 0, yp = 0;
-                if (act) {
-                    OrtRng g = ort_make_rng(id);
-                    st = ort_stage2(S, g, r, &xp, &yp);
-                }
-                ort_bin(img, st == ORT_ST_BINNED, xp, yp, lane);
-                ort_record(ws.hist, st, lane);
+        OrtRay r;
+        uint32_t id = 0;
+        if (stage == 0) {
+            id = b * 32u + lane;
+            b += nwarps;
+            int st = -1;
+            if (id < nrays) {
+                OrtRng g = ort_make_rng(J, id);
+                st = ort_stage_a<PHASE, BOTTLE>(S, g, r);
             }
+            ort_q_push(ws.q[0], n1, st == 0, r, id, lane);
+            ort_count_a<PHASE, BOTTLE>(mine, st == 0 ? -1 : st, lane);
+        } else if (stage == 1) {
+            bool act = ort_q_pop(ws.q[0], n1, r, id, lane);
+            int st = -1;
+            if (act) {
+                OrtRng g = ort_make_rng(J, id);
+                st = ort_stage_b<PHASE>(S, J, g, r);
+            }
+            ort_q_push(ws.q[1], n2, st == 0, r, id, lane);
+            ORT_COUNT_B(mine, st == 0 ? -1 : st, lane);
+        } else {
+            bool act = ort_q_pop(ws.q[1], n2, r, id, lane);
+            int st = -1, xp = 0, yp = 0;
+            if (act) {
+                OrtRng g = ort_make_rng(J, id);
+                st = ort_stage_c(S, J, g, r, &xp, &yp);
+            }
+            ort_bin(img, st == ORT_ST_BINNED, xp, yp, lane);
+            ORT_COUNT_C(mine, st, lane);
         }
-        __syncwarp();
-        if (ws.hist[lane]) atomicAdd(counters + sc * ORT_NSTATUS + lane, (unsigned long long)ws.hist[lane]);
-        __syncwarp();
     }
+    if (mine) atomicAdd(counters + lane, (unsigned long long)mine);
 }
 
 /* The same path, one thread per ray from source to detector, no compaction: every early exit
  * leaves its lane idle until the slowest lane of the warp is done.  Kept to measure what the
  * compaction buys (warp execution efficiency in ncu) and as a cross-check of the megakernel. */
 template <int PHASE, int BOTTLE>
-__global__ void __launch_bounds__(ORT_TPB, 2)
-ort_trace_flat_kernel(unsigned long long* __restrict__ image, unsigned long long* __restrict__ counters) {
-    __shared__ uint32_t s_hist[ORT_WPB][ORT_NSTATUS];
+__global__ void __launch_bounds__(ORT_TPB, ORT_MIN_BLOCKS)
+ort_trace_flat_kernel(const __grid_constant__ DevScene S, const __grid_constant__ DevJob J,
+                      unsigned long long* __restrict__ img, unsigned long long* __restrict__ counters) {
     const unsigned lane = threadIdx.x & 31u;
-    uint32_t* hist = s_hist[threadIdx.x >> 5];
     const uint32_t nwarps = gridDim.x * ORT_WPB;
     const uint32_t gwarp = blockIdx.x * ORT_WPB + (threadIdx.x >> 5);
-    const uint32_t nrays = (uint32_t)c_job.nrays;
+    const uint32_t nrays = (uint32_t)J.nrays;
     const uint32_t nbatches = (nrays + 31u) >> 5;
-    for (int sc = 0; sc < c_job.nscenes; ++sc) {
-        const DevScene& S = c_scenes[sc];
-        unsigned long long* img = image + (size_t)sc * ORT_IMG_BINS;
-        hist[lane] = 0;
-        __syncwarp();
-        for (uint32_t b = gwarp; b < nbatches; b += nwarps) {
-            uint32_t id = b * 32u + lane;
-            int st = -1, xp = 0, yp = 0;
-            if (id < nrays) {
-                OrtRng g = ort_make_rng(id);
-                OrtRay r;
-                st = ort_stage0<PHASE, BOTTLE>(S, g, r);
-                if (st == 0) st = ort_stage1(S, g, r);
-                if (st == 0) st = ort_stage2(S, g, r, &xp, &yp);
-            }
-            ort_bin(img, st == ORT_ST_BINNED, xp, yp, lane);
-            ort_record(hist, st, lane);
+    unsigned mine = 0;
+    for (uint32_t b = gwarp; b < nbatches; b += nwarps) {
+        uint32_t id = b * 32u + lane;
+        int st = -1, xp = 0, yp = 0;
+        if (id < nrays) {
+            OrtRng g = ort_make_rng(J, id);
+            OrtRay r;
+            st = ort_stage_a<PHASE, BOTTLE>(S, g, r);
+            if (st == 0) st = ort_stage_b<PHASE>(S, J, g, r);
+            if (st == 0) st = ort_stage_c(S, J, g, r, &xp, &yp);
         }
-        __syncwarp();
-        if (hist[lane]) atomicAdd(counters + sc * ORT_NSTATUS + lane, (unsigned long long)hist[lane]);
-        __syncwarp();
+        ort_bin(img, st == ORT_ST_BINNED, xp, yp, lane);
+        ort_count<0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24>(
+            mine, st, lane);
     }
+    if (mine) atomicAdd(counters + lane, (unsigned long long)mine);
 }
 
-/* Explicit ray list through scene 0; SoA in/out, see ort_trace_rays in include/ort.h */
+/* Explicit ray list; SoA in/out, see ort_trace_rays in include/ort.h */
 __global__ void __launch_bounds__(ORT_TPB)
-ort_rays_kernel(const double* __restrict__ pin, const double* __restrict__ din, double* __restrict__ pout,
+ort_rays_kernel(const __grid_constant__ DevScene S, const __grid_constant__ DevJob J,
+                const double* __restrict__ pin, const double* __restrict__ din, double* __restrict__ pout,
                 double* __restrict__ dout, int32_t* __restrict__ status, int32_t* __restrict__ bin, long long n) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const DevScene& S = c_scenes[0];
-    OrtRng g = ort_make_rng((uint32_t)i);
+    OrtRng g = ort_make_rng(J, (uint32_t)i);
     OrtRay r;
     int xp = INT32_MIN, yp = INT32_MIN, x = 0, y = 0;
     const bool have_input = pin != nullptr;
@@ -239,7 +277,7 @@ ort_rays_kernel(const double* __restrict__ pin, const double* __restrict__ din, 
         r.px = pin[i]; r.py = pin[n + i]; r.pz = pin[2 * n + i];
         r.dx = din[i]; r.dy = din[n + i]; r.dz = din[2 * n + i];
     }
-    int st = ort_full_path(S, c_job, g, have_input, r, &x, &y);
+    int st = ort_full_path(S, J, g, have_input, r, &x, &y);
     if (st == ORT_ST_BINNED) { xp = x; yp = y; }
     pout[i] = r.px; pout[n + i] = r.py; pout[2 * n + i] = r.pz;
     dout[i] = r.dx; dout[n + i] = r.dy; dout[2 * n + i] = r.dz;
@@ -282,6 +320,29 @@ __global__ void __launch_bounds__(256) ort_dfma_peak_kernel(double* __restrict__
     /* all blocks are resident from the start (8 x 256 threads per SM), so the longest-lived
      * block spans the whole kernel: max(t1 - t0) / kernel time = SM clock under this load */
     if (threadIdx.x == 0) atomicMax(cycles, (unsigned long long)(t1 - t0));
+}
+
+/* max error, in units of the last place, of ort_rcp / ort_div / ort_sqrt / ort_rsqrt against the
+ * correctly rounded operators, over log-uniform operands in [2^-40, 2^40) */
+__device__ __forceinline__ unsigned long long ort_ulp_diff(double a, double b) {
+    long long ia = __double_as_longlong(a), ib = __double_as_longlong(b);
+    long long d = ia - ib;
+    return (unsigned long long)(d < 0 ? -d : d);
+}
+__global__ void ort_math_selftest_kernel(long long n, unsigned long long* __restrict__ worst) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    OrtRng g;
+    g.k0 = 0x5eedu; g.k1 = 0; g.r0 = (uint32_t)i; g.r1 = (uint32_t)(i >> 32); g.phase = 7; g.override_u = -1.0;
+    double u0, u1, u2, u3;
+    ort_draw2(g, 0, &u0, &u1);
+    ort_draw2(g, 1, &u2, &u3);
+    double x = exp2(80.0 * u0 - 40.0) * (1.0 + u1);
+    double a = (exp2(80.0 * u2 - 40.0) * (1.0 + u3)) * ((i & 1) ? -1.0 : 1.0);
+    atomicMax(worst + 0, ort_ulp_diff(ort_rcp(x), 1.0 / x));
+    atomicMax(worst + 1, ort_ulp_diff(ort_div(a, x), a / x));
+    atomicMax(worst + 2, ort_ulp_diff(ort_sqrt(x), sqrt(x)));
+    atomicMax(worst + 3, ort_ulp_diff(ort_rsqrt(x), 1.0 / sqrt(x)));
 }
 
 #endif /* ORT_KERNELS_CUH */

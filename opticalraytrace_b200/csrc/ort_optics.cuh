@@ -41,13 +41,6 @@
 /* -------------------------------------------------------------------------------------------
  * small wrappers over device intrinsics (host versions only serve the test harness)
  * ----------------------------------------------------------------------------------------- */
-ORT_HD double ort_rsqrt(double x) {
-#ifdef __CUDA_ARCH__
-    return rsqrt(x);
-#else
-    return 1.0 / sqrt(x);
-#endif
-}
 ORT_HD void ort_sincospi(double x, double* s, double* c) {
 #ifdef __CUDA_ARCH__
     sincospi(x, s, c);
@@ -69,6 +62,99 @@ ORT_HD uint32_t ort_mulhi(uint32_t a, uint32_t b) {
     return __umulhi(a, b);
 #else
     return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+
+/* -------------------------------------------------------------------------------------------
+ * fp64 reciprocal / division / square root without the compiler's special-case slow paths.
+ * nvcc's `a / b` and `sqrt(x)` are correctly rounded and carry a range check plus a call into a
+ * denormal/overflow subroutine (a BSSY/CALL/BSYNC cluster per use -- the 41 CALLs of the first
+ * build).  Every operand on this path is a normal number between ~1e-12 and ~1e3, so the
+ * MUFU seed + Newton/Goldschmidt refinement below is enough: <= 1 ulp (measured on the device by
+ * ort_math_selftest), far inside the 1e-9 parity tolerance.  Zero and NaN keep the meaning the
+ * callers rely on: ort_sqrt(0) = 0, ort_sqrt(<0) = NaN, ort_div(x, 0) = +-inf.
+ * ----------------------------------------------------------------------------------------- */
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ double ort_mufu_rcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+}
+__device__ __forceinline__ double ort_mufu_rsq(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+}
+#endif
+ORT_HD double ort_rcp(double x) {
+#ifdef __CUDA_ARCH__
+    double y = ort_mufu_rcp(x);
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+#else
+    return 1.0 / x;
+#endif
+}
+ORT_HD double ort_div(double a, double b) {
+#ifdef __CUDA_ARCH__
+    double y = ort_rcp(b);
+    double q = a * y;
+    double r = fma(-b, q, a);
+    return fma(r, y, q);
+#else
+    return a / b;
+#endif
+}
+/* division whose divisor may be exactly zero (ray parallel to a plane): +-inf like IEEE */
+ORT_HD double ort_div_z(double a, double b) {
+#ifdef __CUDA_ARCH__
+    double q = ort_div(a, b);
+    if (b == 0.0) q = (a > 0.0) ? INFINITY : ((a < 0.0) ? -INFINITY : NAN);
+    return q;
+#else
+    return a / b;
+#endif
+}
+ORT_HD double ort_rsqrt(double x) {
+#ifdef __CUDA_ARCH__
+    double y = ort_mufu_rsq(x);
+    double g = x * y, h = 0.5 * y;
+    double r = fma(-g, h, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    r = fma(-g, h, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    r = fma(-g, h, 0.5);
+    h = fma(h, r, h);
+    return h + h;
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
+/* Goldschmidt: g -> sqrt(x), h -> 1/(2 sqrt(x)) */
+ORT_HD double ort_sqrt(double x) {
+#ifdef __CUDA_ARCH__
+    double y = ort_mufu_rsq(x);
+    double g = x * y, h = 0.5 * y;
+    double r = fma(-g, h, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    r = fma(-g, h, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    r = fma(-g, h, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    double d = fma(-g, g, x);
+    g = fma(d, h, g);
+    return (x == 0.0) ? 0.0 : g;
+#else
+    return sqrt(x);
 #endif
 }
 
@@ -149,10 +235,10 @@ ORT_HD bool ort_pick_root_unit(double h, double c, double* t) {
     /* a == 1 (unit direction): roots q and c/q */
     double disc = fma(h, h, -c);
     if (disc < 0.0) return false;
-    double s = sqrt(disc);
+    double s = ort_sqrt(disc);
     double q = (h > 0.0) ? -(h + s) : (s - h);
     double x0 = q;
-    double x1 = (disc == 0.0) ? q : c / q;
+    double x1 = (disc == 0.0) ? q : ort_div(c, q);
     double t0 = fmin(x0, x1), t1 = fmax(x0, x1);
     double tt = (t0 < 0.0) ? t1 : t0;
     if (tt < 0.0) return false;
@@ -162,13 +248,13 @@ ORT_HD bool ort_pick_root_unit(double h, double c, double* t) {
 ORT_HD bool ort_pick_root(double a, double h, double c, double* t) {
     double disc = fma(h, h, -a * c);
     if (disc < 0.0) return false;
-    double s = sqrt(disc);
+    double s = ort_sqrt(disc);
     double q = (h > 0.0) ? -(h + s) : (s - h);
     double x0, x1;
     if (disc == 0.0) {
-        x0 = x1 = -h / a;
+        x0 = x1 = ort_div(-h, a);
     } else {
-        double r = 1.0 / (a * q); /* q/a and c/q from one reciprocal */
+        double r = ort_rcp(a * q); /* q/a and c/q from one reciprocal */
         x0 = q * q * r;
         x1 = c * a * r;
     }
@@ -222,7 +308,7 @@ ORT_HD bool ort_interface(OrtRay& r, double nx, double ny, double nz, const DevI
     double costt = fabs(c);
     double s2 = fma(-costt, costt, 1.0); /* sin^2(theta_i) */
     double st2 = f.eta2 * s2;            /* sin^2(theta_t) */
-    double cost2 = sqrt(fmax(1.0 - st2, 0.0));
+    double cost2 = ort_sqrt(fmax(1.0 - st2, 0.0));
     double R;
     if (st2 > 1.0 || s2 < 0.0) {
         R = 1.0;
@@ -233,7 +319,7 @@ ORT_HD bool ort_interface(OrtRay& r, double nx, double ny, double nz, const DevI
         double a2 = f.na * cost2, b2 = f.nb * costt;
         double A = a1 - b1, B = a1 + b1, C = a2 - b2, D = a2 + b2;
         double A2 = A * A, B2 = B * B, C2 = C * C, D2 = D * D;
-        R = 0.5 * fma(A2, D2, C2 * B2) / (B2 * D2);
+        R = 0.5 * fma(A2, D2, C2 * B2) * ort_rcp(B2 * D2);
         if (!(R >= 0.0 && R <= 1.0)) R = 1.0;
     }
     if (u <= R) { /* reflect, src/surfaces.f90:285-300 */
@@ -261,7 +347,7 @@ ORT_HD void ort_source_point(const DevScene& S, const OrtRng& g, OrtRay& r) {
     ort_draw2(g, 0, &u0, &u1);
     ort_sincospi(2.0 * u0, &sp, &cp);
     double cost = fma(u1, S.cos_theta_max, 1.0 - u1);
-    double sint = sqrt(fma(-cost, cost, 1.0));
+    double sint = ort_sqrt(fma(-cost, cost, 1.0));
     r.dx = sint * cp;
     r.dy = sint * sp;
     r.dz = cost;
@@ -270,17 +356,16 @@ ORT_HD void ort_source_point(const DevScene& S, const OrtRng& g, OrtRay& r) {
     r.pz = S.point_offset;
 }
 
-/* ring, src/sourceMod.f90:250-300 */
-ORT_HD void ort_source_ring(const DevScene& S, const OrtRng& g, OrtRay& r) {
-    double u0, u1, u2, u3, s, c;
-    ort_draw2(g, 0, &u0, &u1);
-    ort_draw2(g, 1, &u2, &u3);
-    double rr = sqrt(fma(u0, S.r2_m_r1, S.r1));
+/* ring, src/sourceMod.f90:250-300; (u0,u1) place the ray on the annulus, (u2,u3) pick the aim
+ * point on the disc of radius L2.radius + 10 mm in the plane z = L2.fb */
+ORT_HD void ort_source_ring_u(const DevScene& S, double u0, double u1, double u2, double u3, OrtRay& r) {
+    double s, c;
+    double rr = ort_sqrt(fma(u0, S.r2_m_r1, S.r1));
     ort_sincospi(2.0 * u1, &s, &c);
     double px = rr * c, py = rr * s;
     double q = S.ellipse ? py * S.ra_over_rb : py;
-    double pz = S.bcz + sqrt(fma(-q, q, S.ra2));
-    double rl = sqrt(u2 * S.lens_r2);
+    double pz = S.bcz + ort_sqrt(fma(-q, q, S.ra2));
+    double rl = ort_sqrt(u2 * S.lens_r2);
     ort_sincospi(2.0 * u3, &s, &c);
     double ex = fma(rl, c, -px), ey = fma(rl, s, -py), ez = S.l2_fb - pz;
     double inv = ort_rsqrt(fma(ex, ex, fma(ey, ey, ez * ez)));
@@ -290,6 +375,19 @@ ORT_HD void ort_source_ring(const DevScene& S, const OrtRng& g, OrtRay& r) {
     r.dx = ex * inv;
     r.dy = ey * inv;
     r.dz = ez * inv;
+}
+ORT_HD void ort_source_ring(const DevScene& S, const OrtRng& g, OrtRay& r) {
+    double u0, u1, u2, u3;
+    ort_draw2(g, 0, &u0, &u1);
+    ort_draw2(g, 1, &u2, &u3);
+    ort_source_ring_u(S, u0, u1, u2, u3, r);
+}
+/* When L2's flat face lies in the aim plane (DevScene.ring_shortcut) the ray meets that face AT
+ * its aim point, so the aperture test of src/lens.f90:450-454 is a test on u2 alone: 69 % of the
+ * ring rays of the shipped geometries end here, before any position, direction, sqrt or sincos
+ * has been computed. */
+ORT_HD bool ort_ring_aims_outside_aperture(const DevScene& S, double u2) {
+    return u2 * S.lens_r2 > S.l2_radius2;
 }
 
 /* -------------------------------------------------------------------------------------------
@@ -448,7 +546,7 @@ ORT_HD int ort_bottle_forward(const DevScene& S, const OrtRng& g, OrtRay& r) {
  * plano_convex%forward, src/lens.f90:425-481, split at the aperture test
  * ----------------------------------------------------------------------------------------- */
 ORT_HD int ort_l2_enter(const DevScene& S, OrtRay& r) { /* :447-454 */
-    double d = (S.l2_flat_z - r.pz) / r.dz;
+    double d = ort_div_z(S.l2_flat_z - r.pz, r.dz);
     ort_advance(r, d);
     if (fma(r.px, r.px, r.py * r.py) > S.l2_radius2) return ORT_ST_L2_APERTURE;
     return 0;
@@ -472,7 +570,7 @@ ORT_HD int ort_l2_body(const DevScene& S, const OrtRng& g, OrtRay& r) { /* :458-
 ORT_HD int ort_l3_enter(const DevScene& S, bool iris_before, OrtRay& r) { /* :551-580 */
     double t;
     if (iris_before) {
-        t = (S.l3_iris1_z - r.pz) / r.dz;
+        t = ort_div_z(S.l3_iris1_z - r.pz, r.dz);
         double x = fma(r.dx, t, r.px), y = fma(r.dy, t, r.py);
         if (fma(x, x, y * y) > S.l3_iris_r2) { /* the reference leaves pos on the iris plane */
             r.px = x; r.py = y; r.pz = fma(r.dz, t, r.pz);
@@ -503,7 +601,7 @@ ORT_HD int ort_l3_body(const DevScene& S, const OrtRng& g, bool iris_after, OrtR
                       (S.l3_c3z - r.pz) * S.l3_invR3, S.l3_s3, u3))
         return ORT_ST_L3_S3_REFLECT;
     if (iris_after) {
-        t = (S.l3_iris2_z - r.pz) / r.dz;
+        t = ort_div_z(S.l3_iris2_z - r.pz, r.dz);
         double x = fma(r.dx, t, r.px), y = fma(r.dy, t, r.py);
         if (fma(x, x, y * y) > S.l3_iris_r2) {
             r.px = x; r.py = y; r.pz = fma(r.dz, t, r.pz);
@@ -518,7 +616,7 @@ ORT_HD int ort_l3_body(const DevScene& S, const OrtRng& g, bool iris_after, OrtR
  * (src/imageMod.f90:19-58).  Returns the status; *bin = (yp+200)*401 + (xp+200) when binned.
  * ----------------------------------------------------------------------------------------- */
 ORT_HD int ort_image(const DevScene& S, OrtRay& r, int* xp, int* yp) {
-    double d = (S.img_z - r.pz) / r.dz;
+    double d = ort_div_z(S.img_z - r.pz, r.dz);
     ort_advance(r, d);
     /* angle = acos(dz/|d|) > asin(0.22)  <=>  dz < cos_na |d|;  a NaN angle passes (reference) */
     double dd = fma(r.dx, r.dx, fma(r.dy, r.dy, r.dz * r.dz));

@@ -11,13 +11,14 @@ import numpy as np
 from . import _abi as abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libort.so")
+# ORT_LIB lets a tuning run pick an experimental build of the same library; default = the product
+LIB_PATH = os.environ.get("ORT_LIB") or os.path.join(_HERE, "libort.so")
 _lib = None
 
 # every symbol include/ort.h declares (tests/test_abi.py checks the header against this list)
 EXPORTS = [
     "ort_init", "ort_init_rank", "ort_nccl_unique_id", "ort_finalize", "ort_last_error",
-    "ort_device_count", "ort_struct_sizes", "ort_trace", "ort_trace_rays", "ort_uniforms", "ort_measure_fp64_peak",
+    "ort_device_count", "ort_struct_sizes", "ort_trace", "ort_trace_rays", "ort_uniforms", "ort_measure_fp64_peak", "ort_math_selftest",
     "ort_load_plano", "ort_load_doublet", "ort_load_bottle", "ort_read_settings",
     "ort_build_scene", "ort_job_from_settings", "ort_output_basename", "ort_write_images",
     "ort_append_trans_stats",
@@ -51,6 +52,7 @@ def load():
                                  C.c_void_p]
     L.ort_uniforms.argtypes = [C.c_uint64, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]
     L.ort_measure_fp64_peak.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.ort_math_selftest.argtypes = [C.c_int64, C.POINTER(C.c_uint64)]
     L.ort_load_plano.argtypes = [C.c_char_p, C.c_double, C.c_double, C.POINTER(abi.Plano)]
     L.ort_load_doublet.argtypes = [C.c_char_p, C.c_double, C.c_double, C.POINTER(abi.Doublet)]
     L.ort_load_bottle.argtypes = [C.c_char_p, C.c_double, C.POINTER(abi.Bottle)]
@@ -202,6 +204,12 @@ def uniforms(seed, phase, ray, first_slot, n):
     out = np.zeros(n, dtype=np.float64)
     check(load().ort_uniforms(seed, phase, ray, first_slot, n, out.ctypes.data))
     return out
+
+
+def math_selftest(n=1 << 24):
+    out = (C.c_uint64 * 4)()
+    check(load().ort_math_selftest(n, out))
+    return dict(zip(("rcp", "div", "sqrt", "rsqrt"), (int(v) for v in out)))
 
 
 def measure_fp64_peak():

@@ -207,4 +207,11 @@ def test_bad_arguments(ort, orc):
     with pytest.raises(OrtError):
         ort.trace(j, scene)
     with pytest.raises(OrtError):
-        ort.trace(abi.default_job(1, 10), [scene] * 65)
+        ort.trace(abi.default_job(1, 10), [])
+
+
+def test_fast_math_accuracy(ort):
+    """The library's slow-path-free reciprocal / division / sqrt / rsqrt: <= 2 ulp on the device."""
+    worst = ort.math_selftest(1 << 24)
+    print("max ulp error:", worst)
+    assert worst["rcp"] <= 2 and worst["div"] <= 2 and worst["sqrt"] <= 2 and worst["rsqrt"] <= 3, worst
