@@ -86,22 +86,33 @@ __device__ __forceinline__ double ort_mufu_rsq(double x) {
     return y;
 }
 #endif
+#ifndef ORT_NR
+#define ORT_NR 2 /* Newton / Goldschmidt refinement steps after the MUFU seed */
+#endif
 ORT_HD double ort_rcp(double x) {
 #ifdef __CUDA_ARCH__
     double y = ort_mufu_rcp(x);
-    double e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-x, y, 1.0);
-    return fma(y, e, y);
+#pragma unroll
+    for (int i = 0; i < ORT_NR; ++i) {
+        double e = fma(-x, y, 1.0);
+        y = fma(y, e, y);
+    }
+    return y;
 #else
     return 1.0 / x;
 #endif
 }
 ORT_HD double ort_div(double a, double b) {
 #ifdef __CUDA_ARCH__
-    double y = ort_rcp(b);
+    /* one Newton step on the reciprocal, then the residual correction of the quotient (itself a
+     * quadratic step): the seed's ~2^-23 becomes < 2^-60 */
+    double y = ort_mufu_rcp(b);
+    double e = fma(-b, y, 1.0);
+    y = fma(y, e, y);
+#if ORT_NR >= 3
+    e = fma(-b, y, 1.0);
+    y = fma(y, e, y);
+#endif
     double q = a * y;
     double r = fma(-b, q, a);
     return fma(r, y, q);
@@ -123,14 +134,12 @@ ORT_HD double ort_rsqrt(double x) {
 #ifdef __CUDA_ARCH__
     double y = ort_mufu_rsq(x);
     double g = x * y, h = 0.5 * y;
-    double r = fma(-g, h, 0.5);
-    g = fma(g, r, g);
-    h = fma(h, r, h);
-    r = fma(-g, h, 0.5);
-    g = fma(g, r, g);
-    h = fma(h, r, h);
-    r = fma(-g, h, 0.5);
-    h = fma(h, r, h);
+#pragma unroll
+    for (int i = 0; i < ORT_NR; ++i) {
+        double r = fma(-g, h, 0.5);
+        if (i + 1 < ORT_NR) g = fma(g, r, g);
+        h = fma(h, r, h);
+    }
     return h + h;
 #else
     return 1.0 / sqrt(x);
@@ -139,17 +148,15 @@ ORT_HD double ort_rsqrt(double x) {
 /* Goldschmidt: g -> sqrt(x), h -> 1/(2 sqrt(x)) */
 ORT_HD double ort_sqrt(double x) {
 #ifdef __CUDA_ARCH__
+    /* one Goldschmidt step, then the Newton correction of the root (also quadratic) */
     double y = ort_mufu_rsq(x);
     double g = x * y, h = 0.5 * y;
-    double r = fma(-g, h, 0.5);
-    g = fma(g, r, g);
-    h = fma(h, r, h);
-    r = fma(-g, h, 0.5);
-    g = fma(g, r, g);
-    h = fma(h, r, h);
-    r = fma(-g, h, 0.5);
-    g = fma(g, r, g);
-    h = fma(h, r, h);
+#pragma unroll
+    for (int i = 0; i < ORT_NR - 1; ++i) {
+        double r = fma(-g, h, 0.5);
+        g = fma(g, r, g);
+        h = fma(h, r, h);
+    }
     double d = fma(-g, g, x);
     g = fma(d, h, g);
     return (x == 0.0) ? 0.0 : g;
@@ -231,36 +238,59 @@ struct OrtRay {
  * reference's intersect_* (src/surfaces.f90:227-260 and :74-87).  Half-b form:
  * a t^2 + 2 h t + c = 0.  `inv_aq_needed`: a != 1 (cylinder / ellipse).
  * ----------------------------------------------------------------------------------------- */
+/* sign-bit tests on the high word: integer ALU work instead of a DSETP on the FP64 pipe.  Only
+ * used where a signed zero cannot occur (differences of distinct quantities). */
+ORT_HD bool ort_signbit(double x) {
+#ifdef __CUDA_ARCH__
+    return __double2hiint(x) < 0;
+#else
+    return signbit(x);
+#endif
+}
+ORT_HD bool ort_either_negative(double x, double y) {
+#ifdef __CUDA_ARCH__
+    return (__double2hiint(x) | __double2hiint(y)) < 0;
+#else
+    return signbit(x) || signbit(y);
+#endif
+}
+ORT_HD bool ort_is_zero(double x) { /* +0 only */
+#ifdef __CUDA_ARCH__
+    return __double_as_longlong(x) == 0ll;
+#else
+    return x == 0.0 && !signbit(x);
+#endif
+}
+
+/* The reference sorts the two roots, takes the smaller unless it is negative, and misses when
+ * both are (src/surfaces.f90:75-84).  With the stable pair q = -(h + sgn(h) s), {q/a, c/q} the
+ * outcome is decided by the signs of h and c alone, and only ONE quotient is ever needed:
+ *   h > 0 : q < 0, so q/a < 0 and c/q has the sign of -c:  c > 0 -> miss, else t = c/q
+ *   h <= 0: q >= 0:  c < 0 -> c/q < 0, t = q/a ;  c >= 0 -> both >= 0 and c/q is the smaller */
 ORT_HD bool ort_pick_root_unit(double h, double c, double* t) {
-    /* a == 1 (unit direction): roots q and c/q */
+    /* a == 1 (unit direction): q/a = q */
     double disc = fma(h, h, -c);
-    if (disc < 0.0) return false;
+    if (ort_signbit(disc)) return false;
     double s = ort_sqrt(disc);
-    double q = (h > 0.0) ? -(h + s) : (s - h);
-    double x0 = q;
-    double x1 = (disc == 0.0) ? q : ort_div(c, q);
-    double t0 = fmin(x0, x1), t1 = fmax(x0, x1);
-    double tt = (t0 < 0.0) ? t1 : t0;
-    if (tt < 0.0) return false;
+    bool hpos = h > 0.0;
+    if (hpos && c > 0.0) return false;
+    double q = hpos ? -(h + s) : (s - h);
+    double x1 = ort_div(c, q);
+    double tt = (!hpos && c < 0.0) ? q : x1;
+    if (q == 0.0) tt = 0.0; /* h = c = 0: the ray starts on the surface, tangent */
     *t = tt;
     return true;
 }
 ORT_HD bool ort_pick_root(double a, double h, double c, double* t) {
     double disc = fma(h, h, -a * c);
-    if (disc < 0.0) return false;
+    if (ort_signbit(disc)) return false;
     double s = ort_sqrt(disc);
-    double q = (h > 0.0) ? -(h + s) : (s - h);
-    double x0, x1;
-    if (disc == 0.0) {
-        x0 = x1 = ort_div(-h, a);
-    } else {
-        double r = ort_rcp(a * q); /* q/a and c/q from one reciprocal */
-        x0 = q * q * r;
-        x1 = c * a * r;
-    }
-    double t0 = fmin(x0, x1), t1 = fmax(x0, x1);
-    double tt = (t0 < 0.0) ? t1 : t0;
-    if (!(tt >= 0.0)) return false;
+    bool hpos = h > 0.0;
+    if (hpos && c > 0.0) return false;
+    double q = hpos ? -(h + s) : (s - h);
+    bool use_q = !hpos && c < 0.0;
+    double tt = ort_div(use_q ? q : c, use_q ? a : q);
+    if (!(tt >= 0.0)) return false; /* a = 0 (ray along the axis) or q = 0 */
     *t = tt;
     return true;
 }
@@ -307,22 +337,23 @@ ORT_HD bool ort_interface(OrtRay& r, double nx, double ny, double nz, const DevI
     double c = fma(nx, r.dx, fma(ny, r.dy, nz * r.dz)); /* N . I */
     double costt = fabs(c);
     double s2 = fma(-costt, costt, 1.0); /* sin^2(theta_i) */
-    double st2 = f.eta2 * s2;            /* sin^2(theta_t) */
-    double cost2 = ort_sqrt(fmax(1.0 - st2, 0.0));
+    double ct2 = fma(-f.eta2, s2, 1.0);  /* cos^2(theta_t) = 1 - eta^2 sin^2 */
+    double cost2 = ort_sqrt(fmax(ct2, 0.0));
     double R;
-    if (st2 > 1.0 || s2 < 0.0) {
+    if (ort_either_negative(ct2, s2)) { /* TIR, or |N.I| > 1 by rounding (reference: NaN -> 1) */
         R = 1.0;
-    } else if (costt == 1.0) {
+    } else if (ort_is_zero(s2)) { /* exactly normal incidence: the reference returns 0 */
         R = 0.0;
     } else {
         double a1 = f.na * costt, b1 = f.nb * cost2;
         double a2 = f.na * cost2, b2 = f.nb * costt;
         double A = a1 - b1, B = a1 + b1, C = a2 - b2, D = a2 + b2;
         double A2 = A * A, B2 = B * B, C2 = C * C, D2 = D * D;
+        /* 0 <= R <= 1 by construction (|A| <= B, |C| <= D); a NaN fails `u > R` and reflects,
+         * which is what the reference's NaN guard does */
         R = 0.5 * fma(A2, D2, C2 * B2) * ort_rcp(B2 * D2);
-        if (!(R >= 0.0 && R <= 1.0)) R = 1.0;
     }
-    if (u <= R) { /* reflect, src/surfaces.f90:285-300 */
+    if (!(u > R)) { /* reflect, src/surfaces.f90:285-300 */
         double k = -2.0 * c;
         r.dx = fma(k, nx, r.dx);
         r.dy = fma(k, ny, r.dy);
