@@ -37,14 +37,35 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-WORKLOADS = {
-    "ring": ("config2-ring: ring source on clearBottle-large -> planoConvex-f39.9mm -> "
-             "achromaticDoublet-f50.0mm -> 401x401 detector, 785 nm"),
-    "point": ("config2-point: point source in clearBottle-large -> planoConvex-f39.9mm -> "
-              "achromaticDoublet-f50.0mm (lenses at 843 nm) -> 401x401 detector"),
+# BASELINE.json configs (index = position in its `configs` list + 1); config 2 / ring is the
+# headline (configs[1]); the others are reported in BASELINE.md and exercised by the parity tests
+CONFIGS = {
+    1: dict(bottles=["clearBottle-small.params"], l2="planoConvex.params", l3="achromaticDoublet.params",
+            text="clearBottle-small -> planoConvex -> achromaticDoublet"),
+    2: dict(bottles=["clearBottle-large.params"], l2="planoConvex-f39.9mm.params",
+            l3="achromaticDoublet-f50.0mm.params",
+            text="clearBottle-large -> planoConvex-f39.9mm -> achromaticDoublet-f50.0mm"),
+    3: dict(bottles=["clearBottle-large_%dmm.params" % mm for mm in range(-14, 15, 2)],
+            l2="planoConvex-f39.9mm.params", l3="achromaticDoublet-f50.0mm.params",
+            text="15 clearBottle-large offset files (-14..+14 mm) in one ort_trace call -> "
+                 "planoConvex-f39.9mm -> achromaticDoublet-f50.0mm"),
+    4: dict(bottles=["scatterBottle-ellipse-long.params"], l2="planoConvex-f39.9mm.params",
+            l3="achromaticDoublet-f50.0mm.params",
+            text="scatterBottle-ellipse-long (mu_a 1, mu_s 30 1/m contents: tauint + stokes) -> "
+                 "planoConvex-f39.9mm -> achromaticDoublet-f50.0mm"),
 }
-WORKLOAD = WORKLOADS["ring"]
-FILES = ("clearBottle-large.params", "planoConvex-f39.9mm.params", "achromaticDoublet-f50.0mm.params")
+
+
+def workload_text(cfg, phase, flat=False, fix=False):
+    src = ("ring source on the bottle surface, 785 nm" if phase == "ring"
+           else "point source at the bottle centre, lenses at 843 nm")
+    return "config%d-%s: %s; %s -> 401x401 detector%s%s" % (
+        cfg, phase, src, CONFIGS[cfg]["text"], " [fixed outer ellipse]" if fix else "",
+        " [no compaction]" if flat else "")
+
+
+WORKLOAD = workload_text(2, "ring")
+FILES = (CONFIGS[2]["bottles"][0], CONFIGS[2]["l2"], CONFIGS[2]["l3"])
 RAYS_PER_GPU = 1 << 34
 CPU_SAMPLE = 30_000_000
 
@@ -58,6 +79,8 @@ def flops_by_status(phase, use_bottle=True, iris_before=False, iris_after=False)
     b_in = b_out = 0.0
     if phase == 2 and use_bottle:
         f[1] = src + 24                 # inner wall miss: intersection only
+        f[2] = f[3] = f[24] = src + 24  # scatter loop endings: lower bound (tauint ~28 and stokes
+        f[6] = f[7] = src + 98 + 24     #   ~60 flops per scatter event are not counted)
         f[4] = src + 98                 # reflected at the inner wall
         f[5] = src + 98 + 24
         f[8] = src + 196
@@ -184,6 +207,10 @@ def main():
     ap.add_argument("--phase", default="ring", choices=["ring", "point"],
                     help="ring = BASELINE.json configs[1] (the headline); point = the other loop")
     ap.add_argument("--flat", action="store_true", help="diagnostic: kernel without compaction")
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4],
+                    help="BASELINE.json config (2 = the headline)")
+    ap.add_argument("--fix-ellipse", action="store_true",
+                    help="config 4: opt-in outer-ellipse fix instead of the reference's half radii")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -215,11 +242,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    st = lib.make_settings(*FILES, nphotons=args.rays)
+    cfg = CONFIGS[args.config]
     phase = abi.PHASE_RING if args.phase == "ring" else abi.PHASE_POINT
-    # the point loop runs with the lenses re-built at 843 nm (reference src/main.f90:113-117)
-    scene, _ = lib.build_scene(st, os.path.join(ROOT, "res"), None if phase == 1 else 843e-9)
-    n = args.rays
+    nsc = len(cfg["bottles"])
+    n = args.rays // nsc          # rays per scene per GPU per step
+    scene = []
+    for bottle in cfg["bottles"]:
+        st = lib.make_settings(bottle, cfg["l2"], cfg["l3"], nphotons=n)
+        # the point loop runs with the lenses re-built at 843 nm (reference src/main.f90:113-117)
+        scene.append(lib.build_scene(st, os.path.join(ROOT, "res"), None if phase == 1 else 843e-9)[0])
 
     def step(k, want_image=True, ph=phase, sc=scene, nr=n):
         job = lib.job_from_settings(st, ph)
@@ -227,6 +258,8 @@ def main():
         job.nrays = nr
         if args.flat:
             job.flags |= abi.FLAG_NO_COMPACTION
+        if args.fix_ellipse:
+            job.flags |= abi.FLAG_FIX_OUTER_ELLIPSE
         return lib.trace(job, sc, want_image=want_image)
 
     for k in range(args.warmup):
@@ -247,7 +280,7 @@ def main():
         launches += tm.kernel_launches
         h2d, d2h = tm.h2d_bytes, tm.d2h_bytes
         if rank == 0:
-            hist += h[0]
+            hist += h.sum(axis=0)
     barrier()
     wall_s = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
@@ -256,14 +289,14 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_s, wall_s, red_s = (float(x) for x in t.tolist())
-    total_rays = float(n) * world * args.steps
+    total_rays = float(n) * nsc * world * args.steps
 
     if rank == 0:
         # rank 0's histogram holds the reduced counts of all ranks (it is the reduce root)
         flops = float((flops_by_status(phase) * hist).sum())
         achieved = flops / dev_s * 1e-12
         cpu = None
-        if world == 1 and not args.no_cpu:
+        if world == 1 and not args.no_cpu and args.config == 2 and args.phase == "ring":
             cores = os.cpu_count() or 1
             cpu_arm(CPU_SAMPLE // 10, cores)
             v = cpu_arm(CPU_SAMPLE * 4, cores, first_ray=1 << 40)
@@ -275,9 +308,9 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_s / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOADS[args.phase] + (" [no compaction]" if args.flat else ""),
-                       "rays_per_gpu_per_step": n,
-                       "rays_per_step": n * world, "parallelism": "ray-range x%d" % world,
+            "config": {"workload": workload_text(args.config, args.phase, args.flat, args.fix_ellipse),
+                       "rays_per_gpu_per_step": n * nsc, "scenes": nsc,
+                       "rays_per_step": n * nsc * world, "parallelism": "ray-range x%d" % world,
                        "l2": "no input arrays (rays are generated on the device); the 2.6 MB "
                              "image buffer is re-zeroed every step",
                        "seed": 123456789},
@@ -286,11 +319,11 @@ def main():
             "gpu_launches": int(launches),
             "reduce_ms_per_step": red_s / args.steps * 1e3,
             "clocks": clocks,
-            "roofline": {"bound": "alu_fp64", "achieved": achieved, "peak": peak_tf,
-                         "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
+            "roofline": {"bound": "alu_fp64", "achieved": achieved, "peak": peak_tf * world,
+                         "unit": "TFLOP/s", "frac": achieved / (peak_tf * world) if peak_tf else None,
                          "traffic": None,
-                         "peak_source": "DFMA micro-kernel measured in this run at %.0f MHz "
-                                        "(MEASURED_PEAKS.json holds no FP64 figure)" % peak_mhz,
+                         "peak_source": "DFMA micro-kernel measured in this run on rank 0 at %.0f MHz, "
+                                        "x n_gpus (MEASURED_PEAKS.json holds no FP64 figure)" % peak_mhz,
                          "flops_per_launched_ray": flops / (total_rays)},
             "cpu_baseline": cpu,
             "status_fractions": {abi.STATUS_NAMES[i]: hist[i] / total_rays

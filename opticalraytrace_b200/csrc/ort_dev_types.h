@@ -29,6 +29,7 @@ struct DevScene {
     double bcx, bcy, bcz;         /* centre */
     double b_in_r, b_in_r2;       /* inner cylinder radius Ra - th and its square */
     double b_out_r, b_out_r2;     /* outer cylinder radius Ra */
+    double b_in_invr, b_out_invr; /* 1/radius: the radial normal of a clear cylindrical wall */
     double b_in_ia2, b_in_ib2;    /* inner ellipse 1/semia^2 (z), 1/semib^2 (y) */
     double b_out_ia2, b_out_ib2;  /* outer ellipse (reference: Ra/2, Rb/2; fixed: Ra, Rb) */
     DevIface b_in;                /* contents -> glass */

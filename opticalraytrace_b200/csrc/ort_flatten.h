@@ -30,6 +30,8 @@ inline void ort_flatten_scene(const ort_scene& s, const ort_job& j, DevScene& d)
     d.b_in_r2 = ort_sq(d.b_in_r);
     d.b_out_r = b.radiusa;
     d.b_out_r2 = ort_sq(b.radiusa);
+    d.b_in_invr = 1.0 / d.b_in_r;
+    d.b_out_invr = 1.0 / d.b_out_r;
     d.b_in_ia2 = 1.0 / ort_sq(b.radiusa - b.thickness);
     d.b_in_ib2 = 1.0 / ort_sq(b.radiusb - b.thickness);
     if (j.flags & ORT_FLAG_FIX_OUTER_ELLIPSE) {

@@ -124,7 +124,7 @@ ORT_HD double ort_div(double a, double b) {
 ORT_HD double ort_div_z(double a, double b) {
 #ifdef __CUDA_ARCH__
     double q = ort_div(a, b);
-    if (b == 0.0) q = (a > 0.0) ? INFINITY : ((a < 0.0) ? -INFINITY : NAN);
+    if ((__double_as_longlong(b) << 1) == 0ll) q = (a > 0.0) ? INFINITY : ((a < 0.0) ? -INFINITY : NAN);
     return q;
 #else
     return a / b;
@@ -339,21 +339,20 @@ ORT_HD bool ort_interface(OrtRay& r, double nx, double ny, double nz, const DevI
     double s2 = fma(-costt, costt, 1.0); /* sin^2(theta_i) */
     double ct2 = fma(-f.eta2, s2, 1.0);  /* cos^2(theta_t) = 1 - eta^2 sin^2 */
     double cost2 = ort_sqrt(fmax(ct2, 0.0));
-    double R;
-    if (ort_either_negative(ct2, s2)) { /* TIR, or |N.I| > 1 by rounding (reference: NaN -> 1) */
-        R = 1.0;
-    } else if (ort_is_zero(s2)) { /* exactly normal incidence: the reference returns 0 */
-        R = 0.0;
-    } else {
-        double a1 = f.na * costt, b1 = f.nb * cost2;
-        double a2 = f.na * cost2, b2 = f.nb * costt;
-        double A = a1 - b1, B = a1 + b1, C = a2 - b2, D = a2 + b2;
-        double A2 = A * A, B2 = B * B, C2 = C * C, D2 = D * D;
-        /* 0 <= R <= 1 by construction (|A| <= B, |C| <= D); a NaN fails `u > R` and reflects,
-         * which is what the reference's NaN guard does */
-        R = 0.5 * fma(A2, D2, C2 * B2) * ort_rcp(B2 * D2);
-    }
-    if (!(u > R)) { /* reflect, src/surfaces.f90:285-300 */
+    /* Fresnel amplitudes in units of nb (the ratios do not change): A/B = r_s, C/D = r_p.
+     * R = (A^2 D^2 + C^2 B^2) / (2 B^2 D^2); the draw is compared without forming the quotient:
+     *   u > R  <=>  2u B^2 D^2 > A^2 D^2 + C^2 B^2.
+     * 0 <= R <= 1 by construction (|A| <= B, |C| <= D); a NaN fails the comparison and reflects,
+     * which is what the reference's NaN guard (R = 1) does. */
+    double ec = f.eta * costt, e2 = f.eta * cost2;
+    double A = ec - cost2, B = ec + cost2, C = e2 - costt, D = e2 + costt;
+    double B2 = B * B, D2 = D * D;
+    double num = fma(A * A, D2, (C * C) * B2);
+    double lhs = (u + u) * (B2 * D2);
+    bool transmit = lhs > num;
+    if (ort_either_negative(ct2, s2)) transmit = false; /* TIR, or |N.I| > 1 by rounding (reference: NaN -> R = 1) */
+    else if (ort_is_zero(s2)) transmit = u > 0.0;      /* exactly normal incidence: the reference returns R = 0 */
+    if (!transmit) { /* reflect, src/surfaces.f90:285-300 */
         double k = -2.0 * c;
         r.dx = fma(k, nx, r.dx);
         r.dy = fma(k, ny, r.dy);
@@ -361,8 +360,7 @@ ORT_HD bool ort_interface(OrtRay& r, double nx, double ny, double nz, const DevI
         return true;
     }
     /* refract, src/surfaces.f90:303-333: T = eta I + (eta c1 - c2) N', N' opposing I */
-    double k = fma(f.eta, costt, -cost2);
-    k = (c < 0.0) ? k : -k;
+    double k = (c < 0.0) ? A : -A; /* eta c1 - c2 */
     r.dx = fma(f.eta, r.dx, k * nx);
     r.dy = fma(f.eta, r.dy, k * ny);
     r.dz = fma(f.eta, r.dz, k * nz);
@@ -553,7 +551,9 @@ ORT_HD int ort_bottle_forward(const DevScene& S, const OrtRng& g, OrtRay& r) {
     ort_draw2(g, 1, &u_in, &u_out);
     {   /* radial normal in the (y,z) plane, also for the ellipse (src/lens.f90:288-290) */
         double ny = S.bcy - r.py, nz = S.bcz - r.pz;
-        double inv = ort_rsqrt(fma(ny, ny, nz * nz));
+        /* on a clear cylindrical wall the hit point is on the cylinder: |(ny,nz)| = radius.  After
+         * a scatter loop (quirk 4) or on an ellipse it is not, and the length is computed. */
+        double inv = (SCATTER || S.ellipse) ? ort_rsqrt(fma(ny, ny, nz * nz)) : S.b_in_invr;
         if (ort_interface(r, 0.0, ny * inv, nz * inv, S.b_in, u_in)) return ORT_ST_BOTTLE_INNER_REFLECT;
     }
     hit = S.ellipse ? ort_hit_ellipse(r, S.bcy, S.bcz, S.b_out_ia2, S.b_out_ib2, &t)
@@ -567,7 +567,7 @@ ORT_HD int ort_bottle_forward(const DevScene& S, const OrtRng& g, OrtRay& r) {
     ort_advance(r, t);
     {
         double ny = S.bcy - r.py, nz = S.bcz - r.pz;
-        double inv = ort_rsqrt(fma(ny, ny, nz * nz));
+        double inv = (SCATTER || S.ellipse) ? ort_rsqrt(fma(ny, ny, nz * nz)) : S.b_out_invr;
         if (ort_interface(r, 0.0, ny * inv, nz * inv, S.b_out, u_out)) return ORT_ST_BOTTLE_OUTER_REFLECT;
     }
     return 0;
