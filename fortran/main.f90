@@ -3,8 +3,8 @@ program raytrace
 ! Everything else -- setup_sim, the loaders and dispersion laws of src/lens.f90, the scalar
 ! prologue, trans-stats.dat, the transmission prints, writeImage -- is the reference's own code,
 ! linked unmodified (constants, utils, vector_class, stackMod, random_mod, stokes, imageMod,
-! surfaces, lens, sourceMod, setupMod).  Only point-source settings take this path for now
-! (SURVEY.md section 8(f) lists the other sources as next).
+! surfaces, lens, sourceMod, setupMod).  source_type point, crs, isors and spot take this path;
+! image (SURVEY.md section 8(f)) does not yet.
 !
 ! Not compiled in this repository's image (no Fortran compiler); see INTEGRATION.md.
 
@@ -42,7 +42,7 @@ program raytrace
     image = 0
 
     call setup_sim(L2, L3, bottle, imgin, nphotonsLocal)
-    if(.not. point_source)error stop "B200 path: only the point source_type is wired up yet"
+    if(image_source)error stop "B200 path: the image source_type is not wired up yet"
 
     filename = trim(adjustl(source_type))//"_bottle_"//str(use_bottle)//"_Ra_"// &
             str(bottle%radiusa,7)//"_Rb_"//str(bottle%radiusb,7)//"_offset_"//&
@@ -57,7 +57,11 @@ program raytrace
         bottle%centre%z = L2%fb - bottle%radiusa - 2d-3
         print*,"Now bottle set at z position:",bottle%centre%z
     end if
-    distance = (bottle%radiusa + bottle%centre%z)
+    if(isors_source)then
+        distance = bottle%radiusa + isors_offset
+    else
+        distance = (bottle%radiusa + bottle%centre%z)
+    end if
     besselDiameter = distance*97.3d-3*tan(alpha* (n - 1)) /(l2%fb)
     r1 = besselDiameter - ringWidth
     r2 = (besselDiameter / 2.d0)**2
@@ -74,14 +78,18 @@ program raytrace
 
     job%use_bottle = merge(1, 0, use_bottle)
     job%iris_before = merge(1, 0, iris(1));  job%iris_after = merge(1, 0, iris(2))
-    job%precision = 64;  job%flags = 0;  job%stop_after = 0;  job%pad_ = 0
+    job%precision = 64;  job%flags = 0;  job%stop_after = 0
+    job%source_kind = ORT_SRC_POINT
+    if(crs_source)job%source_kind = ORT_SRC_CRS
+    if(isors_source)job%source_kind = ORT_SRC_ISORS
+    if(spot_source)job%source_kind = ORT_SRC_SPOT
     job%iris_radius = iris_radius;  job%fibre_offset = fibre_offset;  job%image_diameter = image_diameter
     job%uniform_override = -1.d0
     job%seed = 123456789_c_int64_t          ! init_rng(123456789), src/main.f90:79
-    job%first_ray = 0;  job%nrays = nphotons
+    job%first_ray = 0;  job%nrays = nphotons;  job%total_rays = nphotons
 
     ! ---- ring loop, was src/main.f90:90-109 ------------------------------------------------------
-    call ort_pack_scene(bottle, L2, L3, cosThetaMax, r1, r2, img_plane_1, 0.d0, scene)
+    call ort_pack_scene(bottle, L2, L3, cosThetaMax, r1, r2, img_plane_1, 0.d0, scene, spot_size, isors_offset, ringWidth)
     job%phase = ORT_PHASE_RING
     rc = ort_trace(job, [scene], 1_c_int, counts, lost, hist, timing)
     if(rc /= 0 .and. rc /= ORT_ETRACE)error stop "ort_trace (ring) failed"
@@ -94,7 +102,8 @@ program raytrace
     L3 = achromatic_doublet("../res/"//trim(L3file), wavelength, 2.*L2%fb+ L2%thickness)
 
     ! ---- point loop, was src/main.f90:127-162 --------------------------------------------------
-    call ort_pack_scene(bottle, L2, L3, cosThetaMax, r1, r2, img_plane_1, 0.d0, scene)
+    call ort_pack_scene(bottle, L2, L3, cosThetaMax, r1, r2, img_plane_1, merge(bottle%centre%z, 0.d0, isors_source), scene, &
+                        spot_size, isors_offset, ringWidth)
     job%phase = ORT_PHASE_POINT
     rc = ort_trace(job, [scene], 1_c_int, counts, lost, hist, timing)
     if(rc /= 0 .and. rc /= ORT_ETRACE)error stop "ort_trace (point) failed"

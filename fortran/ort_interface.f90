@@ -19,6 +19,7 @@ module ort_interface
     integer(c_int), parameter :: ORT_PHASE_RING = 1, ORT_PHASE_POINT = 2
     integer(c_int), parameter :: ORT_IMG_N = 401, ORT_IMG_BINS = 401*401, ORT_NSTATUS = 32
     integer(c_int), parameter :: ORT_ETRACE = -7
+    integer(c_int), parameter :: ORT_SRC_POINT = 0, ORT_SRC_CRS = 1, ORT_SRC_ISORS = 2, ORT_SRC_SPOT = 3
 
     type, bind(C) :: ort_plano                 ! reference src/lens.f90:8-20
         real(c_double) :: thickness, diameter, radius, fb, f, n1, n2, curve_radius
@@ -43,12 +44,13 @@ module ort_interface
         type(ort_plano)   :: L2
         type(ort_doublet) :: L3
         real(c_double) :: cos_theta_max, r1, r2, img_plane, point_offset
+        real(c_double) :: spot_size, isors_offset, ring_width
     end type ort_scene
 
     type, bind(C) :: ort_job
-        integer(c_int32_t) :: phase, use_bottle, iris_before, iris_after, precision, flags, stop_after, pad_
+        integer(c_int32_t) :: phase, use_bottle, iris_before, iris_after, precision, flags, stop_after, source_kind
         real(c_double)     :: iris_radius, fibre_offset, image_diameter, uniform_override
-        integer(c_int64_t) :: seed, first_ray, nrays
+        integer(c_int64_t) :: seed, first_ray, nrays, total_rays
     end type ort_job
 
     type, bind(C) :: ort_timing
@@ -110,7 +112,8 @@ contains
 
     ! Copy the reference's derived types into the POD scene.  `use lensMod` types come from the
     ! UNMODIFIED reference src/lens.f90, whose loaders keep doing the file parsing + dispersion.
-    subroutine ort_pack_scene(bottle, L2, L3, cosThetaMax, r1, r2, img_plane, point_offset, s)
+    subroutine ort_pack_scene(bottle, L2, L3, cosThetaMax, r1, r2, img_plane, point_offset, s, &
+                              spot_size, isors_offset, ring_width)
         use lensMod, only : plano_convex, achromatic_doublet, glass_bottle
         type(glass_bottle),       intent(in)  :: bottle
         type(plano_convex),       intent(in)  :: L2
@@ -147,6 +150,10 @@ contains
         s%r1 = r1;  s%r2 = r2
         s%img_plane = img_plane
         s%point_offset = point_offset
+        s%spot_size = 0.d0;  s%isors_offset = 0.d0;  s%ring_width = 0.d0
+        if(present(spot_size))s%spot_size = spot_size
+        if(present(isors_offset))s%isors_offset = isors_offset
+        if(present(ring_width))s%ring_width = ring_width
     end subroutine ort_pack_scene
 
 end module ort_interface

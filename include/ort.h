@@ -57,6 +57,19 @@ extern "C" {
 #define ORT_FLAG_NO_COMPACTION 4     /* diagnostic: one-thread-per-ray kernel without the
                                         warp-level live-ray compaction */
 
+/* ort_job.source_kind = settings.params source_type.  Which routine emits, per loop
+ * (reference src/main.f90:95-101 and :132-142):
+ *                 ring loop (phase 1)                      point loop (phase 2)
+ *   POINT         ring()             sourceMod.f90:250     point()            :12
+ *   CRS           point_on_bottle()  :50                   point()
+ *   ISORS         iSORS(ring=.true.) :162                  point(offset = bottle centre z)
+ *   SPOT          ring()                                   create_spot()      :122
+ *   (image: emit_image() in the point loop -- not on the B200 path yet) */
+#define ORT_SRC_POINT 0
+#define ORT_SRC_CRS 1
+#define ORT_SRC_ISORS 2
+#define ORT_SRC_SPOT 3
+
 /* ort_job.stop_after (explicit-ray entry point only): where pos_out/dir_out are sampled */
 #define ORT_STOP_NONE 0   /* full path, sampled at the image plane */
 #define ORT_STOP_SOURCE 1 /* after ring()/point() */
@@ -91,12 +104,14 @@ enum ort_status {
     ORT_ST_FAR = 22,                 /* src/imageMod.f90:48, plus non-finite positions */
     ORT_ST_OFF_DETECTOR = 23,        /* src/imageMod.f90:52-54 */
     ORT_ST_TAUINT_MISS = 24,         /* src/surfaces.f90:33-39 `error stop "no intersection"` */
-    ORT_ST_STOPPED = 25              /* explicit-ray mode: reached ort_job.stop_after alive */
+    ORT_ST_STOPPED = 25,             /* explicit-ray mode: reached ort_job.stop_after alive */
+    ORT_ST_SOURCE_MISS = 26          /* iSORS: src/sourceMod.f90:216-218 `error stop "no intersection
+                                        with bottle!"`; crs: spot point beside the bottle */
 };
 #define ORT_NSTATUS 32
 /* statuses 1..20 and 24 are what the reference adds to rcount / pcount
- * (src/optics_system.f90:32,42 and src/main.f90:150-151) */
-#define ORT_STATUS_IS_LOST(s) (((s) >= 1 && (s) <= 20) || (s) == 24)
+ * (src/optics_system.f90:32,42 and src/main.f90:150-151); 26 is an abort there */
+#define ORT_STATUS_IS_LOST(s) (((s) >= 1 && (s) <= 20) || (s) == 24 || (s) == 26)
 
 /* reference src/lens.f90:8-20 (type lens + plano_convex) */
 typedef struct {
@@ -131,6 +146,10 @@ typedef struct {
     double r1, r2;        /* squared annulus radii, src/main.f90:66-70 */
     double img_plane;     /* src/main.f90:81 */
     double point_offset;  /* z of the point source (0; bottle centre z for isors, main.f90:140) */
+    double spot_size;     /* crs: sigma of the Gaussian spot on the bottle, already rescaled as in
+                             src/setupMod.f90:135-136 */
+    double isors_offset;  /* isors: ring / spot separation, src/setupMod.f90:132 */
+    double ring_width;    /* isors: beam width on the axicon (ringWidth, src/setupMod.f90:57) */
 } ort_scene;
 
 /* One launch of a ray loop. */
@@ -142,7 +161,7 @@ typedef struct {
     int32_t precision;   /* 64 (fp64, the reference's arithmetic) */
     int32_t flags;       /* ORT_FLAG_* */
     int32_t stop_after;  /* ORT_STOP_* (ort_trace_rays only) */
-    int32_t _pad;
+    int32_t source_kind; /* ORT_SRC_*: which of the reference's sources feeds the loop */
     double iris_radius;      /* fraction of the lens radius, src/setupMod.f90:101 */
     double fibre_offset;     /* src/setupMod.f90:84 */
     double image_diameter;   /* src/setupMod.f90:83 */
@@ -153,6 +172,8 @@ typedef struct {
     int64_t first_ray; /* index of the first ray; uniforms are a pure function of
                           (seed, phase, ray index, draw slot) */
     int64_t nrays;     /* rays per scene */
+    int64_t total_rays; /* nphotons of the whole job (only create_spot depends on it,
+                           src/sourceMod.f90:134-143); 0 means nrays */
 } ort_job;
 
 typedef struct {

@@ -16,6 +16,8 @@ ORT_OK, ORT_EINVAL, ORT_ENODEVICE, ORT_ECUDA, ORT_ENCCL, ORT_EIO, ORT_EPARSE, OR
 PHASE_RING, PHASE_POINT = 1, 2
 FLAG_FIX_OUTER_ELLIPSE, FLAG_NO_REDUCE, FLAG_NO_COMPACTION = 1, 2, 4
 STOP_NONE, STOP_SOURCE, STOP_BOTTLE, STOP_L2, STOP_L3 = 0, 1, 2, 3, 4
+SRC_POINT, SRC_CRS, SRC_ISORS, SRC_SPOT = 0, 1, 2, 3
+SOURCE_KINDS = {"point": SRC_POINT, "crs": SRC_CRS, "isors": SRC_ISORS, "spot": SRC_SPOT}
 
 STATUS_NAMES = [
     "binned", "bottle_inner_miss", "contents_absorbed", "contents_backward",
@@ -23,7 +25,7 @@ STATUS_NAMES = [
     "bottle_outer_reflect", "l2_aperture", "l2_sphere_miss", "l2_curved_reflect",
     "l3_iris_before", "l3_s1_miss", "l3_aperture", "l3_s1_reflect", "l3_s2_miss",
     "l3_s2_reflect", "l3_s3_miss", "l3_s3_reflect", "l3_iris_after", "na_reject", "far",
-    "off_detector", "tauint_miss", "stopped",
+    "off_detector", "tauint_miss", "stopped", "source_miss",
 ]
 ST_BINNED = 0
 ST_STOPPED = 25
@@ -31,7 +33,7 @@ NO_BIN = -2 ** 31
 
 
 def status_is_lost(s):
-    return (1 <= s <= 20) or s == 24
+    return (1 <= s <= 20) or s == 24 or s == 26
 
 
 class Plano(C.Structure):
@@ -59,16 +61,18 @@ class Bottle(C.Structure):
 class Scene(C.Structure):
     _fields_ = [("bottle", Bottle), ("L2", Plano), ("L3", Doublet),
                 ("cos_theta_max", C.c_double), ("r1", C.c_double), ("r2", C.c_double),
-                ("img_plane", C.c_double), ("point_offset", C.c_double)]
+                ("img_plane", C.c_double), ("point_offset", C.c_double),
+                ("spot_size", C.c_double), ("isors_offset", C.c_double), ("ring_width", C.c_double)]
 
 
 class Job(C.Structure):
     _fields_ = [("phase", C.c_int32), ("use_bottle", C.c_int32), ("iris_before", C.c_int32),
                 ("iris_after", C.c_int32), ("precision", C.c_int32), ("flags", C.c_int32),
-                ("stop_after", C.c_int32), ("_pad", C.c_int32),
+                ("stop_after", C.c_int32), ("source_kind", C.c_int32),
                 ("iris_radius", C.c_double), ("fibre_offset", C.c_double),
                 ("image_diameter", C.c_double), ("uniform_override", C.c_double),
-                ("seed", C.c_uint64), ("first_ray", C.c_int64), ("nrays", C.c_int64)]
+                ("seed", C.c_uint64), ("first_ray", C.c_int64), ("nrays", C.c_int64),
+                ("total_rays", C.c_int64)]
 
 
 class Timing(C.Structure):
@@ -91,7 +95,7 @@ class Settings(C.Structure):
 
 def default_job(phase, nrays=0, *, use_bottle=True, iris="none", iris_radius=1.0,
                 fibre_offset=0.0, image_diameter=1e-2, seed=123456789, first_ray=0,
-                flags=0, stop_after=0, uniform_override=-1.0):
+                flags=0, stop_after=0, uniform_override=-1.0, source="point", total_rays=0):
     """A Job with the values the reference's settings.params ships (src/setupMod.f90:57-133)."""
     j = Job()
     j.phase = phase
@@ -101,6 +105,8 @@ def default_job(phase, nrays=0, *, use_bottle=True, iris="none", iris_radius=1.0
     j.precision = 64
     j.flags = flags
     j.stop_after = stop_after
+    j.source_kind = SOURCE_KINDS[source]
+    j.total_rays = total_rays
     j.iris_radius = iris_radius
     j.fibre_offset = fibre_offset
     j.image_diameter = image_diameter

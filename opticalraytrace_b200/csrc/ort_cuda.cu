@@ -252,6 +252,10 @@ static int validate_job(const ort_job* job) {
         ort_set_error("image_diameter must be > 0");
         return ORT_EINVAL;
     }
+    if (job->source_kind < ORT_SRC_POINT || job->source_kind > ORT_SRC_SPOT) {
+        ort_set_error("job.source_kind %d unknown", job->source_kind);
+        return ORT_EINVAL;
+    }
     if (job->uniform_override >= 1.0) {
         ort_set_error("uniform_override must be < 1");
         return ORT_EINVAL;
@@ -264,13 +268,27 @@ static int validate_job(const ort_job* job) {
  * ---------------------------------------------------------------------------------------- */
 typedef void (*trace_kernel_t)(const DevScene, const DevJob, unsigned long long*, unsigned long long*);
 
-static trace_kernel_t pick_kernel(int phase, int bottle_mode, bool flat) {
-    if (phase == ORT_PHASE_RING)
-        return flat ? ort_trace_flat_kernel<ORT_PHASE_RING, 0> : ort_trace_kernel<ORT_PHASE_RING, 0>;
+static trace_kernel_t pick_kernel(int phase, int bottle_mode, int src, bool flat) {
+    if (flat) { /* diagnostic kernel: default sources only */
+        if (phase == ORT_PHASE_RING) return ort_trace_flat_kernel<ORT_PHASE_RING, 0>;
+        switch (bottle_mode) {
+            case 0: return ort_trace_flat_kernel<ORT_PHASE_POINT, 0>;
+            case 1: return ort_trace_flat_kernel<ORT_PHASE_POINT, 1>;
+            default: return ort_trace_flat_kernel<ORT_PHASE_POINT, 2>;
+        }
+    }
+    if (phase == ORT_PHASE_RING) {
+        switch (src) {
+            case ORT_SRC_CRS: return ort_trace_kernel<ORT_PHASE_RING, 0, ORT_SRC_CRS>;
+            case ORT_SRC_ISORS: return ort_trace_kernel<ORT_PHASE_RING, 0, ORT_SRC_ISORS>;
+            default: return ort_trace_kernel<ORT_PHASE_RING, 0, ORT_SRC_POINT>; /* point, spot: ring() */
+        }
+    }
+    const bool spot = src == ORT_SRC_SPOT; /* crs, isors: point() in the point loop */
     switch (bottle_mode) {
-        case 0: return flat ? ort_trace_flat_kernel<ORT_PHASE_POINT, 0> : ort_trace_kernel<ORT_PHASE_POINT, 0>;
-        case 1: return flat ? ort_trace_flat_kernel<ORT_PHASE_POINT, 1> : ort_trace_kernel<ORT_PHASE_POINT, 1>;
-        default: return flat ? ort_trace_flat_kernel<ORT_PHASE_POINT, 2> : ort_trace_kernel<ORT_PHASE_POINT, 2>;
+        case 0: return spot ? ort_trace_kernel<ORT_PHASE_POINT, 0, ORT_SRC_SPOT> : ort_trace_kernel<ORT_PHASE_POINT, 0, ORT_SRC_POINT>;
+        case 1: return spot ? ort_trace_kernel<ORT_PHASE_POINT, 1, ORT_SRC_SPOT> : ort_trace_kernel<ORT_PHASE_POINT, 1, ORT_SRC_POINT>;
+        default: return spot ? ort_trace_kernel<ORT_PHASE_POINT, 2, ORT_SRC_SPOT> : ort_trace_kernel<ORT_PHASE_POINT, 2, ORT_SRC_POINT>;
     }
 }
 
@@ -291,8 +309,8 @@ static int enqueue_trace(DeviceCtx& c, const ort_job& job, const std::vector<Dev
     bool any_scatter = false;
     for (auto& s : ds) any_scatter |= (s.scatter_b || s.scatter_c);
     int bottle_mode = (job.phase == ORT_PHASE_POINT && job.use_bottle) ? (any_scatter ? 2 : 1) : 0;
-    bool flat = (job.flags & ORT_FLAG_NO_COMPACTION) != 0;
-    trace_kernel_t k = pick_kernel(job.phase, bottle_mode, flat);
+    bool flat = (job.flags & ORT_FLAG_NO_COMPACTION) != 0 && job.source_kind == ORT_SRC_POINT;
+    trace_kernel_t k = pick_kernel(job.phase, bottle_mode, job.source_kind, flat);
     size_t smem = flat ? 0 : (size_t)ORT_WPB * sizeof(WarpShared);
     if (smem) CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
@@ -402,7 +420,7 @@ extern "C" int ort_trace(const ort_job* job, const ort_scene* scenes, int nscene
             if (status_hist) status_hist[(size_t)s * ORT_NSTATUS + k] = (int64_t)h[k];
         }
         if (lost) lost[s] = l;
-        if (h[ORT_ST_L3_S3_MISS] || h[ORT_ST_TAUINT_MISS]) trapped = true;
+        if (h[ORT_ST_L3_S3_MISS] || h[ORT_ST_TAUINT_MISS] || h[ORT_ST_SOURCE_MISS]) trapped = true;
     }
     if (timing) {
         double tmax = 0.0, rmax = 0.0;
@@ -424,7 +442,7 @@ extern "C" int ort_trace(const ort_job* job, const ort_scene* scenes, int nscene
             std::chrono::duration<double>(std::chrono::steady_clock::now() - w0).count();
     }
     if (trapped) {
-        ort_set_error("trace hit a reference `error stop` invariant (status 18 or 24); results returned");
+        ort_set_error("trace hit a reference `error stop` invariant (status 18, 24 or 26); results returned");
         return ORT_ETRACE;
     }
     return ORT_OK;

@@ -42,6 +42,15 @@ struct DevScene {
     double ra2, ra_over_rb;       /* Ra^2, Ra/Rb */
     double lens_r2;               /* (L2.radius + 10e-3)^2 */
     double l2_fb;                 /* z of the aim disc */
+    /* --- crs / isors sources (reference src/sourceMod.f90:50-89,162-247) --- */
+    double spot_size;             /* crs: sigma of the spot (already rescaled) */
+    double crs_r2;                /* crs: (Ra + thickness)^2, the cylinder the spot is projected on */
+    double isors_beam;            /* isors: beam width (sigma of the Gaussian on the axicon) */
+    double isors_base;            /* isors: (separation + beam) / tan(alpha (n_axicon - 1)) */
+    double isors_k, isors_h;      /* isors: axicon (radius/height)^2 and height */
+    double isors_z;               /* isors: Ra + bottle z + epsilon(1.) */
+    double isors_lens_r2;         /* isors: L2.radius^2 (aim disc) */
+    DevIface isors_axicon;        /* 1.4 -> 1.0 */
     /* --- L2 plano-convex (reference src/lens.f90:425-481) --- */
     double l2_cx, l2_cy, l2_cz;   /* sphere centre */
     double l2_flat_z;             /* centre.z + R - thickness */
@@ -73,7 +82,8 @@ struct DevJob {
     int64_t nrays;       /* rays per scene in this launch (< 2^32) */
     double uniform_override;
     int32_t phase, use_bottle, iris_before, iris_after;
-    int32_t nscenes, stop_after, flags, _pad;
+    int32_t nscenes, stop_after, flags, source_kind;
+    int64_t total_rays;  /* nphotons of the whole job (create_spot) */
 };
 
 #endif

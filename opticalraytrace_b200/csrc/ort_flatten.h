@@ -63,6 +63,19 @@ inline void ort_flatten_scene(const ort_scene& s, const ort_job& j, DevScene& d)
     d.lens_r2 = ort_sq(s.L2.radius + 10e-3);
     d.l2_fb = s.L2.fb;
 
+    { /* crs: src/sourceMod.f90:82; isors: src/sourceMod.f90:180-188,206 */
+        const double axicon_n = 1.4, radius = 12.7e-3, height = 1.1e-3;
+        d.spot_size = s.spot_size;
+        d.crs_r2 = ort_sq(b.radiusa + b.thickness);
+        d.isors_beam = s.ring_width;
+        double alpha = std::atan(height / radius);
+        d.isors_base = (s.isors_offset + s.ring_width) / std::tan(alpha * (axicon_n - 1.));
+        d.isors_k = ort_sq(radius / height);
+        d.isors_h = height;
+        d.isors_z = b.radiusa + b.centre[2] + 2.220446049250313e-16;
+        d.isors_lens_r2 = ort_sq(s.L2.radius);
+        d.isors_axicon = ort_mk_iface(axicon_n, 1.0);
+    }
     const ort_plano& p = s.L2;
     d.l2_cx = p.centre[0]; d.l2_cy = p.centre[1]; d.l2_cz = p.centre[2];
     d.l2_flat_z = p.centre[2] + p.curve_radius - p.thickness;
@@ -109,6 +122,8 @@ inline void ort_make_dev_job(const ort_job& j, int nscenes, int64_t first, int64
     d.nscenes = nscenes;
     d.stop_after = j.stop_after;
     d.flags = j.flags;
+    d.source_kind = j.source_kind;
+    d.total_rays = j.total_rays > 0 ? j.total_rays : j.nrays;
 }
 
 

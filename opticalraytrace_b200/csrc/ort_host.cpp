@@ -341,6 +341,12 @@ int ort_build_scene(const ort_settings* st, const char* resdir, double lens_wave
                           2. * out->L2.fb + out->L2.thickness, &out->L3);
     if (rc) return rc;
     if (pre_guard_offset) *pre_guard_offset = out->bottle.centre[2];
+    { /* src/setupMod.f90:135-136: the crs spot radius is rescaled before main's offset guard */
+        double offset = out->bottle.radiusa + out->bottle.centre[2];
+        out->spot_size = (st->spot_size * (out->L2.fb - offset)) / out->L2.fb;
+        out->isors_offset = st->isors_offset;
+        out->ring_width = st->ring_width;
+    }
 
     const double pi = 3.14159265358979323846;
     const bool isors = std::strcmp(st->source_type, "isors") == 0;
@@ -372,6 +378,11 @@ int ort_job_from_settings(const ort_settings* st, int32_t phase, ort_job* out) {
     out->fibre_offset = st->fibre_offset;
     out->image_diameter = st->image_diameter;
     out->uniform_override = -1.0;
+    if (std::strcmp(st->source_type, "crs") == 0) out->source_kind = ORT_SRC_CRS;
+    else if (std::strcmp(st->source_type, "isors") == 0) out->source_kind = ORT_SRC_ISORS;
+    else if (std::strcmp(st->source_type, "spot") == 0) out->source_kind = ORT_SRC_SPOT;
+    else out->source_kind = ORT_SRC_POINT; /* "image": not on this path, callers must check */
+    out->total_rays = st->nphotons;
     out->seed = 123456789ull; /* src/main.f90:79 */
     out->first_ray = 0;
     out->nrays = st->nphotons;

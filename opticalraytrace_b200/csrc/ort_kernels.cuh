@@ -114,20 +114,20 @@ __device__ __forceinline__ void ort_bin(unsigned long long* img, bool binned, in
  * B: (ring shortcut: the rest of the source, then) through L2, up to and including the aperture
  *    test on L3's first surface.
  * C: the three refractions of L3, transfer to the image plane, acceptance + binning. */
-template <int PHASE, int BOTTLE>
-__device__ __forceinline__ int ort_stage_a(const DevScene& S, const OrtRng& g, OrtRay& r) {
-    if (PHASE == ORT_PHASE_RING) {
-        if (S.ring_shortcut) {
-            double u2, u3;
-            ort_draw2(g, 1, &u2, &u3);
-            r.px = u2;
-            r.py = u3;
-            r.pz = r.dx = r.dy = r.dz = 0.0;
-            return ort_ring_aims_outside_aperture(S, u2) ? ORT_ST_L2_APERTURE : 0;
-        }
-        ort_source_ring(S, g, r);
-    } else {
-        ort_source_point(S, g, r);
+template <int PHASE, int BOTTLE, int SRC>
+__device__ __forceinline__ int ort_stage_a(const DevScene& S, const DevJob& J, const OrtRng& g, uint32_t id,
+                                           OrtRay& r) {
+    if (PHASE == ORT_PHASE_RING && SRC == ORT_SRC_POINT && S.ring_shortcut) {
+        double u2, u3;
+        ort_draw2(g, 1, &u2, &u3);
+        r.px = u2;
+        r.py = u3;
+        r.pz = r.dx = r.dy = r.dz = 0.0;
+        return ort_ring_aims_outside_aperture(S, u2) ? ORT_ST_L2_APERTURE : 0;
+    }
+    int es = ort_emit<PHASE, SRC>(S, J, g, J.first_ray + (long long)id, r);
+    if (es) return es;
+    if (PHASE == ORT_PHASE_POINT) {
         if (BOTTLE == 1) {
             int st = ort_bottle_forward<false>(S, g, r);
             if (st) return st;
@@ -138,9 +138,9 @@ __device__ __forceinline__ int ort_stage_a(const DevScene& S, const OrtRng& g, O
     }
     return ort_l2_enter(S, r);
 }
-template <int PHASE>
+template <int PHASE, int SRC>
 __device__ __forceinline__ int ort_stage_b(const DevScene& S, const DevJob& J, const OrtRng& g, OrtRay& r) {
-    if (PHASE == ORT_PHASE_RING && S.ring_shortcut) {
+    if (PHASE == ORT_PHASE_RING && SRC == ORT_SRC_POINT && S.ring_shortcut) {
         double u0, u1, u2 = r.px, u3 = r.py;
         ort_draw2(g, 0, &u0, &u1);
         ort_source_ring_u(S, u0, u1, u2, u3, r);
@@ -161,7 +161,7 @@ __device__ __forceinline__ int ort_stage_c(const DevScene& S, const DevJob& J, c
 
 /* statuses a ray can end with, per stage */
 #define ORT_COUNT_A(mine, st, lane) ort_count<1, 2, 3, 4, 5, 6, 7, 8, 9, 24>(mine, st, lane)
-#define ORT_COUNT_A_RING(mine, st, lane) ort_count<9>(mine, st, lane)
+#define ORT_COUNT_A_RING(mine, st, lane) ort_count<9, 26>(mine, st, lane)
 #define ORT_COUNT_A_CLEAR(mine, st, lane) ort_count<1, 4, 5, 8, 9>(mine, st, lane)
 #define ORT_COUNT_B(mine, st, lane) ort_count<9, 10, 11, 12, 13, 14>(mine, st, lane)
 #define ORT_COUNT_C(mine, st, lane) ort_count<0, 15, 16, 17, 18, 19, 20, 21, 22, 23>(mine, st, lane)
@@ -173,7 +173,7 @@ __device__ __forceinline__ void ort_count_a(unsigned& mine, int st, unsigned lan
     else ORT_COUNT_A(mine, st, lane);
 }
 
-template <int PHASE, int BOTTLE>
+template <int PHASE, int BOTTLE, int SRC>
 __global__ void __launch_bounds__(ORT_TPB, ORT_MIN_BLOCKS)
 ort_trace_kernel(const __grid_constant__ DevScene S, const __grid_constant__ DevJob J,
                  unsigned long long* __restrict__ img, unsigned long long* __restrict__ counters) {
@@ -205,7 +205,7 @@ ort_trace_kernel(const __grid_constant__ DevScene S, const __grid_constant__ Dev
             int st = -1;
             if (id < nrays) {
                 OrtRng g = ort_make_rng(J, id);
-                st = ort_stage_a<PHASE, BOTTLE>(S, g, r);
+                st = ort_stage_a<PHASE, BOTTLE, SRC>(S, J, g, id, r);
             }
             ort_q_push(ws.q[0], n1, st == 0, r, id, lane);
             ort_count_a<PHASE, BOTTLE>(mine, st == 0 ? -1 : st, lane);
@@ -214,7 +214,7 @@ ort_trace_kernel(const __grid_constant__ DevScene S, const __grid_constant__ Dev
             int st = -1;
             if (act) {
                 OrtRng g = ort_make_rng(J, id);
-                st = ort_stage_b<PHASE>(S, J, g, r);
+                st = ort_stage_b<PHASE, SRC>(S, J, g, r);
             }
             ort_q_push(ws.q[1], n2, st == 0, r, id, lane);
             ORT_COUNT_B(mine, st == 0 ? -1 : st, lane);
@@ -251,8 +251,8 @@ ort_trace_flat_kernel(const __grid_constant__ DevScene S, const __grid_constant_
         if (id < nrays) {
             OrtRng g = ort_make_rng(J, id);
             OrtRay r;
-            st = ort_stage_a<PHASE, BOTTLE>(S, g, r);
-            if (st == 0) st = ort_stage_b<PHASE>(S, J, g, r);
+            st = ort_stage_a<PHASE, BOTTLE, ORT_SRC_POINT>(S, J, g, id, r);
+            if (st == 0) st = ort_stage_b<PHASE, ORT_SRC_POINT>(S, J, g, r);
             if (st == 0) st = ort_stage_c(S, J, g, r, &xp, &yp);
         }
         ort_bin(img, st == ORT_ST_BINNED, xp, yp, lane);

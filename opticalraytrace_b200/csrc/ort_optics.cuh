@@ -262,6 +262,26 @@ ORT_HD bool ort_is_zero(double x) { /* +0 only */
 #endif
 }
 
+ORT_HD bool ort_both_zero(double x, double y) { /* +-0 */
+#ifdef __CUDA_ARCH__
+    return ((__double_as_longlong(x) | __double_as_longlong(y)) << 1) == 0ll;
+#else
+    return x == 0.0 && y == 0.0;
+#endif
+}
+
+/* Unit normal of a sphere at a point on it: (centre - pos) / R with 1/R hoisted.  A ray that runs
+ * exactly along the axis must see EXACTLY (0,0,+-1): the reference normalises by the computed
+ * length, gets |N.I| == 1 bit for bit, and its fresnel() then returns 0 -- the
+ * on-axis rays of create_spot and of the known-answer tests depend on it. */
+ORT_HD void ort_sphere_normal(const OrtRay& r, double cx, double cy, double cz, double invR, double* nx,
+                              double* ny, double* nz) {
+    double vx = cx - r.px, vy = cy - r.py, vz = cz - r.pz;
+    *nx = vx * invR;
+    *ny = vy * invR;
+    *nz = ort_both_zero(vx, vy) ? copysign(1.0, vz) : vz * invR;
+}
+
 /* The reference sorts the two roots, takes the smaller unless it is negative, and misses when
  * both are (src/surfaces.f90:75-84).  With the stable pair q = -(h + sgn(h) s), {q/a, c/q} the
  * outcome is decided by the signs of h and c alone, and only ONE quotient is ever needed:
@@ -419,6 +439,127 @@ ORT_HD bool ort_ring_aims_outside_aperture(const DevScene& S, double u2) {
     return u2 * S.lens_r2 > S.l2_radius2;
 }
 
+/* ---- the other sources of settings.params ---------------------------- */
+/* rang, src/random_mod.f90:59-85: polar Box-Muller; its rejection loop takes the sequential
+ * draws (slots 16, 17, ...) */
+ORT_HD void ort_rang(const OrtRng& g, OrtScatterRng& sr, double sigma, double* x, double* y) {
+    double a, b, s;
+    do {
+        a = fma(ort_scatter_draw(g, sr), 2.0, -1.0);
+        b = fma(ort_scatter_draw(g, sr), 2.0, -1.0);
+        s = fma(b, b, a * a);
+    } while (s >= 1.0 && g.override_u < 0.0);
+    double cst = sqrt(-2.0 * log(s) / s);
+    *x = sigma * (a * cst);
+    *y = sigma * (b * cst);
+}
+
+/* point_on_bottle, src/sourceMod.f90:50-89 (crs, ring loop): a Gaussian spot projected along -z
+ * onto the cylinder of radius Ra + thickness, emitting into the cone of point() */
+ORT_HD bool ort_source_crs(const DevScene& S, const OrtRng& g, OrtRay& r) {
+    OrtScatterRng sr;
+    sr.next = 16;
+    sr.spare = 0.0;
+    ort_source_point(S, g, r); /* same two draws, same direction formulas (:65-77) */
+    double dx = r.dx, dy = r.dy, dz = r.dz, x, y, t;
+    ort_rang(g, sr, S.spot_size, &x, &y);
+    OrtRay probe = {x, y, 1.0, 0.0, 0.0, -1.0};
+    if (!ort_hit_cylinder(probe, S.bcy, S.bcz, S.crs_r2, &t)) return false;
+    r.px = x;
+    r.py = y;
+    r.pz = 1.0 - t;
+    r.dx = dx;
+    r.dy = dy;
+    r.dz = dz;
+    return true;
+}
+
+/* create_spot, src/sourceMod.f90:122-159 (spot, point loop): deterministic angular grid;
+ * n = 1-based loop index, nrays = nphotons */
+ORT_HD void ort_source_spot(const DevScene& S, long long nrays, long long n, OrtRay& r) {
+    double nrays_sqrt = sqrt((double)nrays);
+    double dphi = ORT_TWOPI / nrays_sqrt;
+    double dtheta = acos(S.cos_theta_max) / nrays_sqrt;
+    double phi = dphi * (double)(n % 10), theta = dtheta * (double)(n / 10);
+    double sp, cp, st_, ct;
+    ort_sincos(phi, &sp, &cp);
+    ort_sincos(theta, &st_, &ct);
+    double sint = sqrt(fma(-ct, ct, 1.0));
+    r.dx = sint * cp;
+    r.dy = sint * sp;
+    r.dz = ct;
+    r.px = r.py = r.pz = 0.0;
+}
+
+/* intersect_cone, src/surfaces.f90:179-224, for the axicon of iSORS */
+ORT_HD bool ort_hit_cone(const OrtRay& r, double k, double height, double* t) {
+    double lz = r.pz - height;
+    double a = fma(r.dx, r.dx, fma(r.dy, r.dy, -k * r.dz * r.dz));
+    double h = fma(r.dx, r.px, fma(r.dy, r.py, -k * r.dz * lz));
+    double c = fma(r.px, r.px, fma(r.py, r.py, -k * lz * lz));
+    /* a < 0 here (steep ray), so the sign logic of ort_pick_root does not apply: both roots */
+    double disc = fma(h, h, -a * c);
+    if (disc < 0.0) return false;
+    double s = sqrt(disc);
+    double q = (h > 0.0) ? -(h + s) : (s - h);
+    double x0 = (disc == 0.0) ? -h / a : q / a, x1 = (disc == 0.0) ? x0 : c / q;
+    double t0 = fmin(x0, x1), t1 = fmax(x0, x1);
+    double tt = (t0 < 0.0) ? t1 : t0;
+    if (tt < 0.0) return false;
+    *t = tt;
+    return true;
+}
+
+/* iSORS(ring = .true.), src/sourceMod.f90:162-247 (isors, ring loop).  false = the reference's
+ * `error stop "no intersection with bottle!"` (every ray the axicon face reflects, ~2.8 %). */
+ORT_HD bool ort_source_isors(const DevScene& S, const OrtRng& g, OrtRay& r) {
+    OrtScatterRng sr;
+    sr.next = 16;
+    sr.spare = 0.0;
+    double x, y, t, u_r, u_th, u_ax, unused;
+    ort_rang(g, sr, S.isors_beam, &x, &y);
+    r.px = x; r.py = y; r.pz = 2.0 * S.isors_h;
+    r.dx = 0.0; r.dy = 0.0; r.dz = -1.0;
+    ort_draw2(g, 0, &u_r, &u_th);
+    ort_draw2(g, 1, &u_ax, &unused);
+    if (ort_hit_cone(r, S.isors_k, S.isors_h, &t)) {
+        ort_advance(r, t);
+        /* gradient of the cone, inverted (upper nappe), normalised */
+        double nx = -(2.0 * r.px / S.isors_k), ny = -(2.0 * r.py / S.isors_k), nz = -(-2.0 * r.pz + 2.0 * S.isors_h);
+        double inv = 1.0 / sqrt(fma(nx, nx, fma(ny, ny, nz * nz)));
+        (void)ort_interface(r, nx * inv, ny * inv, nz * inv, S.isors_axicon, u_ax); /* flag ignored */
+        ort_advance(r, S.isors_base / r.dz);
+        r.pz = S.isors_z;
+        bool hit = S.ellipse ? ort_hit_ellipse(r, S.bcy, S.bcz, S.b_in_ia2, S.b_in_ib2, &t)
+                             : ort_hit_cylinder(r, S.bcy, S.bcz, S.b_in_r2, &t);
+        if (!hit) return false;
+        ort_advance(r, t);
+    }
+    double rl = sqrt(u_r * S.isors_lens_r2), s, c;
+    ort_sincospi(2.0 * u_th, &s, &c);
+    double ex = fma(rl, c, -r.px), ey = fma(rl, s, -r.py), ez = S.l2_fb - r.pz;
+    double inv = 1.0 / sqrt(fma(ex, ex, fma(ey, ey, ez * ez)));
+    r.dx = ex * inv;
+    r.dy = ey * inv;
+    r.dz = ez * inv;
+    return true;
+}
+
+/* source dispatch of src/main.f90:95-101 (ring loop) and :132-142 (point loop); SRC is
+ * ort_job.source_kind.  Returns 0 or ORT_ST_SOURCE_MISS. */
+template <int PHASE, int SRC>
+ORT_HD int ort_emit(const DevScene& S, const DevJob& J, const OrtRng& g, long long ray, OrtRay& r) {
+    if (PHASE == ORT_PHASE_RING) {
+        if (SRC == ORT_SRC_CRS) return ort_source_crs(S, g, r) ? 0 : ORT_ST_SOURCE_MISS;
+        if (SRC == ORT_SRC_ISORS) return ort_source_isors(S, g, r) ? 0 : ORT_ST_SOURCE_MISS;
+        ort_source_ring(S, g, r);
+    } else {
+        if (SRC == ORT_SRC_SPOT) ort_source_spot(S, J.total_rays, ray + 1, r);
+        else ort_source_point(S, g, r);
+    }
+    return 0;
+}
+
 /* -------------------------------------------------------------------------------------------
  * Scatter: tauint (src/surfaces.f90:13-50) and stokes (src/stokes.f90:7-166)
  * ----------------------------------------------------------------------------------------- */
@@ -554,7 +695,8 @@ ORT_HD int ort_bottle_forward(const DevScene& S, const OrtRng& g, OrtRay& r) {
         /* on a clear cylindrical wall the hit point is on the cylinder: |(ny,nz)| = radius.  After
          * a scatter loop (quirk 4) or on an ellipse it is not, and the length is computed. */
         double inv = (SCATTER || S.ellipse) ? ort_rsqrt(fma(ny, ny, nz * nz)) : S.b_in_invr;
-        if (ort_interface(r, 0.0, ny * inv, nz * inv, S.b_in, u_in)) return ORT_ST_BOTTLE_INNER_REFLECT;
+        double nzu = ort_both_zero(ny, 0.0) ? copysign(1.0, nz) : nz * inv; /* on-axis ray: exactly +-1 */
+        if (ort_interface(r, 0.0, ny * inv, nzu, S.b_in, u_in)) return ORT_ST_BOTTLE_INNER_REFLECT;
     }
     hit = S.ellipse ? ort_hit_ellipse(r, S.bcy, S.bcz, S.b_out_ia2, S.b_out_ib2, &t)
                     : ort_hit_cylinder(r, S.bcy, S.bcz, S.b_out_r2, &t);
@@ -568,7 +710,8 @@ ORT_HD int ort_bottle_forward(const DevScene& S, const OrtRng& g, OrtRay& r) {
     {
         double ny = S.bcy - r.py, nz = S.bcz - r.pz;
         double inv = (SCATTER || S.ellipse) ? ort_rsqrt(fma(ny, ny, nz * nz)) : S.b_out_invr;
-        if (ort_interface(r, 0.0, ny * inv, nz * inv, S.b_out, u_out)) return ORT_ST_BOTTLE_OUTER_REFLECT;
+        double nzu = ort_both_zero(ny, 0.0) ? copysign(1.0, nz) : nz * inv;
+        if (ort_interface(r, 0.0, ny * inv, nzu, S.b_out, u_out)) return ORT_ST_BOTTLE_OUTER_REFLECT;
     }
     return 0;
 }
@@ -589,9 +732,9 @@ ORT_HD int ort_l2_body(const DevScene& S, const OrtRng& g, OrtRay& r) { /* :458-
     (void)ort_interface(r, S.l2_fnx, S.l2_fny, S.l2_fnz, S.l2_in, u_flat);
     if (!ort_hit_sphere(r, S.l2_cx, S.l2_cy, S.l2_cz, S.l2_R2, &t)) return ORT_ST_L2_SPHERE_MISS;
     ort_advance(r, t);
-    if (ort_interface(r, (S.l2_cx - r.px) * S.l2_invR, (S.l2_cy - r.py) * S.l2_invR,
-                      (S.l2_cz - r.pz) * S.l2_invR, S.l2_out, u_curved))
-        return ORT_ST_L2_CURVED_REFLECT;
+    double nx, ny, nz;
+    ort_sphere_normal(r, S.l2_cx, S.l2_cy, S.l2_cz, S.l2_invR, &nx, &ny, &nz);
+    if (ort_interface(r, nx, ny, nz, S.l2_out, u_curved)) return ORT_ST_L2_CURVED_REFLECT;
     return 0;
 }
 
@@ -614,23 +757,20 @@ ORT_HD int ort_l3_enter(const DevScene& S, bool iris_before, OrtRay& r) { /* :55
     return 0;
 }
 ORT_HD int ort_l3_body(const DevScene& S, const OrtRng& g, bool iris_after, OrtRay& r) { /* :582-644 */
-    double u1, u2, u3, unused, t;
+    double u1, u2, u3, unused, t, nx, ny, nz;
     ort_draw2(g, 3, &u1, &u2);
-    if (ort_interface(r, (r.px - S.l3_c1x) * S.l3_invR1, (r.py - S.l3_c1y) * S.l3_invR1,
-                      (r.pz - S.l3_c1z) * S.l3_invR1, S.l3_s1, u1))
-        return ORT_ST_L3_S1_REFLECT;
+    ort_sphere_normal(r, S.l3_c1x, S.l3_c1y, S.l3_c1z, S.l3_invR1, &nx, &ny, &nz);
+    if (ort_interface(r, nx, ny, nz, S.l3_s1, u1)) return ORT_ST_L3_S1_REFLECT;
     if (!ort_hit_sphere(r, S.l3_c2x, S.l3_c2y, S.l3_c2z, S.l3_R2_2, &t)) return ORT_ST_L3_S2_MISS;
     ort_advance(r, t);
-    if (ort_interface(r, (S.l3_c2x - r.px) * S.l3_invR2, (S.l3_c2y - r.py) * S.l3_invR2,
-                      (S.l3_c2z - r.pz) * S.l3_invR2, S.l3_s2, u2))
-        return ORT_ST_L3_S2_REFLECT;
+    ort_sphere_normal(r, S.l3_c2x, S.l3_c2y, S.l3_c2z, S.l3_invR2, &nx, &ny, &nz);
+    if (ort_interface(r, nx, ny, nz, S.l3_s2, u2)) return ORT_ST_L3_S2_REFLECT;
     /* the reference aborts here on a miss (error stop "Help3", :617); we count it */
     if (!ort_hit_sphere(r, S.l3_c3x, S.l3_c3y, S.l3_c3z, S.l3_R3_2, &t)) return ORT_ST_L3_S3_MISS;
     ort_advance(r, t);
     ort_draw2(g, 4, &u3, &unused);
-    if (ort_interface(r, (S.l3_c3x - r.px) * S.l3_invR3, (S.l3_c3y - r.py) * S.l3_invR3,
-                      (S.l3_c3z - r.pz) * S.l3_invR3, S.l3_s3, u3))
-        return ORT_ST_L3_S3_REFLECT;
+    ort_sphere_normal(r, S.l3_c3x, S.l3_c3y, S.l3_c3z, S.l3_invR3, &nx, &ny, &nz);
+    if (ort_interface(r, nx, ny, nz, S.l3_s3, u3)) return ORT_ST_L3_S3_REFLECT;
     if (iris_after) {
         t = ort_div_z(S.l3_iris2_z - r.pz, r.dz);
         double x = fma(r.dx, t, r.px), y = fma(r.dy, t, r.py);
@@ -671,8 +811,17 @@ ORT_HD int ort_full_path(const DevScene& S, const DevJob& J, const OrtRng& g, bo
     const int stop = J.stop_after;
     int st;
     if (!have_input) {
-        if (J.phase == ORT_PHASE_RING) ort_source_ring(S, g, r);
-        else ort_source_point(S, g, r);
+        long long ray = ((long long)g.r1 << 32) | g.r0;
+        int es;
+        if (J.phase == ORT_PHASE_RING) {
+            es = J.source_kind == ORT_SRC_CRS ? ort_emit<ORT_PHASE_RING, ORT_SRC_CRS>(S, J, g, ray, r)
+               : J.source_kind == ORT_SRC_ISORS ? ort_emit<ORT_PHASE_RING, ORT_SRC_ISORS>(S, J, g, ray, r)
+                                                : ort_emit<ORT_PHASE_RING, ORT_SRC_POINT>(S, J, g, ray, r);
+        } else {
+            es = J.source_kind == ORT_SRC_SPOT ? ort_emit<ORT_PHASE_POINT, ORT_SRC_SPOT>(S, J, g, ray, r)
+                                               : ort_emit<ORT_PHASE_POINT, ORT_SRC_POINT>(S, J, g, ray, r);
+        }
+        if (es) return es;
     }
     if (stop == ORT_STOP_SOURCE) return ORT_ST_STOPPED;
     if (J.phase == ORT_PHASE_POINT && J.use_bottle) {

@@ -34,9 +34,8 @@ def run(settings_path, resdir, datadir=None, *, nphotons=None, write=True, verbo
                   " Deselecting tracking of packets\n ***************")
         st.use_tracker = 0
     src = st.source_type.decode()
-    if src != "point":  # crs / isors / image / spot emit differently in one of the two loops
-        raise lib.OrtError(abi.ORT_EINVAL, "source type '%s' is not on the B200 path yet "
-                                           "(point / ring phases only)" % src)
+    if src == "image":  # emit_image (src/sourceMod.f90:303-361) is the one emitter still missing
+        raise lib.OrtError(abi.ORT_EINVAL, "source type 'image' is not on the B200 path yet")
     scene_ring, pre_guard = lib.build_scene(st, resdir, st.wavelength)
     scene_point, _ = lib.build_scene(st, resdir, 843e-9)
     if verbose and scene_ring.bottle.centre[2] != pre_guard:
@@ -45,9 +44,9 @@ def run(settings_path, resdir, datadir=None, *, nphotons=None, write=True, verbo
     name = lib.output_basename(st, scene_ring, pre_guard)
 
     jr = lib.job_from_settings(st, abi.PHASE_RING)
-    ring, rlost, rhist, rt = lib.trace(jr, scene_ring)
+    ring, rlost, rhist, rt = lib.trace(jr, scene_ring, allow_trap=True)
     jp = lib.job_from_settings(st, abi.PHASE_POINT)
-    point, plost, phist, pt = lib.trace(jp, scene_point)
+    point, plost, phist, pt = lib.trace(jp, scene_point, allow_trap=True)
     rcount, pcount = int(rlost[0]), int(plost[0])
     n = float(st.nphotons) if st.nphotons else float("nan")
     out = dict(ring=ring[0], point=point[0], rcount=rcount, pcount=pcount, name=name,

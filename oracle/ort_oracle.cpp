@@ -52,6 +52,8 @@ inline vec magnitude(vec a) { /* :175-186 -- despite the name, this normalises *
     return a / tmp;
 }
 
+inline vec v3(const double* p) { return {p[0], p[1], p[2]}; }
+
 /* reference src/constants.f90:5 -- 4.*atan(1.) folds to the correctly rounded pi */
 const double PI = 3.14159265358979323846;
 const double TWOPI = 2.0 * 3.14159265358979323846;
@@ -186,6 +188,17 @@ inline bool intersect_ellipse(vec orig, vec dir, double& t, vec centre, double s
     double a = semia2div * (dir.z * dir.z) + semib2div * (dir.y * dir.y);
     double b = 2 * (semia2div * dir.z * L.z + semib2div * dir.y * L.y);
     double c = semia2div * (L.z * L.z) + semib2div * (L.y * L.y) - 1;
+    return pick_root(a, b, c, t);
+}
+
+/* intersect_cone, src/surfaces.f90:179-224 */
+inline bool intersect_cone(vec orig, vec dir, double& t, vec centre, double radius, double height) {
+    double k = radius / height;
+    k = k * k;
+    vec L = orig - centre;
+    double a = dir.x * dir.x + dir.y * dir.y - (k * (dir.z * dir.z));
+    double b = 2. * ((dir.x * L.x) + (dir.y * L.y) - (k * dir.z * (L.z - height)));
+    double c = L.x * L.x + L.y * L.y - (k * ((L.z - height) * (L.z - height)));
     return pick_root(a, b, c, t);
 }
 
@@ -414,10 +427,112 @@ inline void source_ring(vec& pos, vec& dir, const ort_plano& lens, double r1, do
     dir = magnitude(dir);
 }
 
+/* rang, src/random_mod.f90:59-85: polar Box-Muller; the rejection loop consumes the sequential
+ * draws (slots 16, 17, ...) */
+inline void rang(double& x, double& y, double avg, double sigma, Draws& rng) {
+    double s = 1.;
+    while (s >= 1.) {
+        x = -1. + rng.scatter() * (1. - -1.);
+        y = -1. + rng.scatter() * (1. - -1.);
+        s = y * y + x * x;
+        if (rng.override_u >= 0.) break; /* constant test draws would never leave the loop */
+    }
+    double cst = std::sqrt(-2. * std::log(s) / s);
+    double tmp = x * cst;
+    x = avg + sigma * tmp;
+    tmp = y * cst;
+    y = avg + sigma * tmp;
+}
+
+/* point_on_bottle, src/sourceMod.f90:50-89 (crs source of the ring loop).  Returns false when
+ * the spot point misses the cylinder (the reference then uses an undefined t). */
+inline bool source_crs(vec& pos, vec& dir, double cosThetaMax, const ort_bottle& B, double spot_radius,
+                       Draws& rng) {
+    double phi = TWOPI * rng.slot(SLOT_SRC0);
+    double cosp = std::cos(phi);
+    double sinp = std::sin(phi);
+    double ran = rng.slot(SLOT_SRC1);
+    double cost = (1.0 - ran) + ran * cosThetaMax;
+    double sint = std::sqrt(1.0 - cost * cost);
+    double nxp = sint * cosp, nyp = sint * sinp, nzp = cost;
+    double tmp1, tmp2;
+    rang(tmp1, tmp2, 0., spot_radius, rng);
+    pos = {tmp1, tmp2, 1.0};
+    dir = {0., 0., -1.};
+    double t = 0.;
+    bool flag = intersect_cylinder(pos, dir, t, v3(B.centre), B.radiusa + B.thickness);
+    if (!flag) return false;
+    pos = pos + dir * t;
+    dir = {nxp, nyp, nzp};
+    return true;
+}
+
+/* create_spot, src/sourceMod.f90:122-159; n is the 1-based loop index, nrays = nphotons */
+inline void source_spot(vec& pos, vec& dir, double cosThetaMax, int64_t nrays, int64_t n) {
+    double nrays_sqrt = std::sqrt((double)nrays);
+    double phimax = TWOPI;
+    double thetaMax = std::acos(cosThetaMax);
+    double deltaPhi = phimax / nrays_sqrt;
+    double deltaTheta = thetaMax / nrays_sqrt;
+    double phi = deltaPhi * (double)(n % 10);
+    double theta = deltaTheta * (double)(n / 10);
+    double sinp = std::sin(phi), cosp = std::cos(phi);
+    double cost = std::cos(theta);
+    double sint = std::sqrt(1. - cost * cost);
+    dir = {sint * cosp, sint * sinp, cost};
+    pos = {0., 0., 0.};
+}
+
+/* iSORS with ring = .true., src/sourceMod.f90:162-247.  Returns false at the reference's
+ * `error stop "no intersection with bottle!"`. */
+inline bool source_isors(vec& pos, vec& dir, const ort_bottle& B, const ort_plano& L1, double seperation,
+                         double beam_width, Draws& rng) {
+    double axicon_n = 1.4;
+    double radius = 12.7e-3;
+    double height = 1.1e-3;
+    double alpha = std::atan(height / radius);
+    double k = (radius / height) * (radius / height);
+    double base_pos = (seperation + beam_width) / std::tan(alpha * (axicon_n - 1.));
+    vec centre = {0., 0., 0.};
+    double posx, posy, t;
+    rang(posx, posy, 0., beam_width, rng);
+    pos = centre + vec{posx, posy, 2 * height};
+    dir = {0., 0., -1.};
+    bool flag = intersect_cone(pos, dir, t, centre, radius, height);
+    if (flag) {
+        pos = pos + t * dir;
+        vec normal = {2 * (pos.x - centre.x) / k, 2 * (pos.y - centre.y) / k, -2 * (pos.z - centre.z) + 2 * height};
+        normal = normal * (-1.);
+        normal = magnitude(normal);
+        reflect_refract(dir, normal, axicon_n, 1., flag, rng.slot(SLOT_SRC2));
+        t = (base_pos) / dir.z;
+        pos = pos + t * dir;
+        pos.z = B.radiusa + B.centre[2] + 2.220446049250313e-16; /* epsilon(1.) with -freal-4-real-8 */
+        if (B.ellipse) {
+            double rad1 = B.radiusa - B.thickness;
+            double rad2 = B.radiusb - B.thickness;
+            flag = intersect_ellipse(pos, dir, t, v3(B.centre), rad1, rad2);
+        } else {
+            flag = intersect_cylinder(pos, dir, t, v3(B.centre), B.radiusa - B.thickness);
+        }
+        if (!flag) return false;
+        pos = pos + t * dir;
+    }
+    double r = 0. + rng.slot(SLOT_SRC0) * ((L1.radius * L1.radius) - 0.);
+    double theta = rng.slot(SLOT_SRC1) * TWOPI;
+    posx = std::sqrt(r) * std::cos(theta);
+    posy = std::sqrt(r) * std::sin(theta);
+    vec lenspoint = {posx, posy, L1.fb};
+    double dx = lenspoint.x - pos.x, dy = lenspoint.y - pos.y, dz = lenspoint.z - pos.z;
+    double dist = std::sqrt(dx * dx + dy * dy + dz * dz);
+    dir = {(lenspoint.x - pos.x) / dist, (lenspoint.y - pos.y) / dist, (lenspoint.z - pos.z) / dist};
+    dir = magnitude(dir);
+    return true;
+}
+
 /* ---------------------------------------------------------------------------------------
  * optical elements, reference src/lens.f90
  * ------------------------------------------------------------------------------------- */
-inline vec v3(const double* p) { return {p[0], p[1], p[2]}; }
 
 /* bottle_forward_sub, src/lens.f90:230-350.  Returns 0 when the ray leaves the bottle. */
 inline int bottle_forward(const ort_bottle& B, vec centre, vec& pos, vec& dir, Draws& rng, int flags) {
@@ -614,20 +729,32 @@ inline RayOut trace_one(const ort_job& J, const ort_scene& S, int64_t ray, bool 
     o.xp = o.yp = INT32_MIN;
     int st = 0;
     vec bcentre = v3(S.bottle.centre);
-    if (!have_input) {
-        if (J.phase == ORT_PHASE_RING) {
-            source_ring(pos, dir, S.L2, S.r1, S.r2, S.bottle.radiusa, S.bottle.radiusb,
-                        S.bottle.ellipse != 0, bcentre.z, rng);
-        } else {
-            source_point(pos, dir, S.cos_theta_max, S.point_offset, rng);
-        }
-    }
     auto done = [&](int status) {
         o.pos = pos;
         o.dir = dir;
         o.status = status;
         return o;
     };
+    if (!have_input) { /* source dispatch of src/main.f90:95-101 and :132-142 */
+        if (J.phase == ORT_PHASE_RING) {
+            if (J.source_kind == ORT_SRC_ISORS) {
+                if (!source_isors(pos, dir, S.bottle, S.L2, S.isors_offset, S.ring_width, rng))
+                    return done(ORT_ST_SOURCE_MISS);
+            } else if (J.source_kind == ORT_SRC_CRS) {
+                if (!source_crs(pos, dir, S.cos_theta_max, S.bottle, S.spot_size, rng))
+                    return done(ORT_ST_SOURCE_MISS);
+            } else {
+                source_ring(pos, dir, S.L2, S.r1, S.r2, S.bottle.radiusa, S.bottle.radiusb,
+                            S.bottle.ellipse != 0, bcentre.z, rng);
+            }
+        } else {
+            if (J.source_kind == ORT_SRC_SPOT) {
+                source_spot(pos, dir, S.cos_theta_max, J.total_rays > 0 ? J.total_rays : J.nrays, ray + 1);
+            } else {
+                source_point(pos, dir, S.cos_theta_max, S.point_offset, rng);
+            }
+        }
+    }
     if (J.stop_after == ORT_STOP_SOURCE) return done(ORT_ST_STOPPED);
     if (J.phase == ORT_PHASE_POINT && J.use_bottle) { /* src/main.f90:145-155 */
         st = bottle_forward(S.bottle, bcentre, pos, dir, rng, J.flags);
@@ -780,7 +907,13 @@ int orc_load_bottle(const char* path, double wavelength, ort_bottle* o) {
  * and L3 are already loaded; applies the offset guard (:54-58).  alpha in degrees as read from
  * settings.params (converted at src/setupMod.f90:61). */
 int orc_derive_scene(ort_scene* S, double alpha_deg, double n_axicon, double ring_width,
-                     int isors_source, double isors_offset) {
+                     int isors_source, double isors_offset, double spot_size) {
+    { /* src/setupMod.f90:135-136, before the offset guard of main.f90 */
+        double offset = S->bottle.radiusa + S->bottle.centre[2];
+        S->spot_size = (spot_size * (S->L2.fb - offset)) / S->L2.fb;
+        S->isors_offset = isors_offset;
+        S->ring_width = ring_width;
+    }
     double alpha = alpha_deg * PI / 180.;
     double angle = std::atan(S->L2.radius / S->L2.fb);
     S->cos_theta_max = std::cos(angle);

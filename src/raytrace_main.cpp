@@ -41,10 +41,10 @@ int main(int argc, char** argv) {
                     " Deselecting tracking of packets\n ***************\n");
         st.use_tracker = 0;
     }
-    if (std::strcmp(st.source_type, "point") != 0) {
+    if (std::strcmp(st.source_type, "image") == 0) {
         std::fprintf(stderr,
-                     "raytrace: source type '%s' is not on the B200 path yet (ring + point loops only; "
-                     "see DESIGN.md, scope row 8(f))\n", st.source_type);
+                     "raytrace: source type 'image' is not on the B200 path yet (point, crs, isors and spot "
+                     "are; see DESIGN.md, scope row 8(f))\n");
         return 2;
     }
     int want = std::getenv("ORT_NUM_GPUS") ? std::atoi(std::getenv("ORT_NUM_GPUS")) : 0;

@@ -38,6 +38,23 @@ SCATTER_CASES = [
 ]
 
 
-def scene_for(orc, files, phase):
+# the other source types of settings.params: crs and isors change the ring
+# loop's emitter, spot the point loop's; isors also moves the point source to the bottle centre
+SOURCE_CASES = [
+    ("c1-crs-ring", C1, abi.PHASE_RING, dict(source="crs")),
+    ("c2-crs-ring", C2, abi.PHASE_RING, dict(source="crs")),
+    ("ellipse-crs-ring", ELL, abi.PHASE_RING, dict(source="crs")),
+    ("c1-isors-ring", C1, abi.PHASE_RING, dict(source="isors")),
+    ("c2-isors-ring", C2, abi.PHASE_RING, dict(source="isors")),
+    ("ellipse-isors-ring", ELL, abi.PHASE_RING, dict(source="isors")),
+    ("other-isors-point", OTHER, abi.PHASE_POINT, dict(source="isors")),
+    ("c1-spot-point", C1, abi.PHASE_POINT, dict(source="spot", total_rays=250_000)),
+    ("c2-spot-point-nobottle", C2, abi.PHASE_POINT, dict(source="spot", total_rays=1_000_000, use_bottle=False)),
+    ("c2-spot-ring", C2, abi.PHASE_RING, dict(source="spot")),
+]
+
+
+def scene_for(orc, files, phase, kw=None):
     lam = 843e-9 if phase == abi.PHASE_POINT else None
-    return orc.make_scene(*files, lens_wavelength=lam)
+    isors = bool(kw) and kw.get("source") == "isors"
+    return orc.make_scene(*files, lens_wavelength=lam, isors=isors)

@@ -27,8 +27,8 @@ NIMG = 200_000
 
 def main():
     rays, images = {}, {}
-    for cid, files, phase, kw in cases.RAY_CASES + cases.SCATTER_CASES:
-        scene = cases.scene_for(O, files, phase)
+    for cid, files, phase, kw in cases.RAY_CASES + cases.SCATTER_CASES + cases.SOURCE_CASES:
+        scene = cases.scene_for(O, files, phase, kw)
         job = abi.default_job(phase, **kw)
         r = O.trace_rays(job, scene, NRAYS)
         for k in ("pos", "dir", "status", "bin"):

@@ -38,7 +38,7 @@ def lib():
         L.orc_load_doublet.argtypes = [C.c_char_p, C.c_double, C.c_double, C.POINTER(abi.Doublet)]
         L.orc_load_bottle.argtypes = [C.c_char_p, C.c_double, C.POINTER(abi.Bottle)]
         L.orc_derive_scene.argtypes = [C.POINTER(abi.Scene), C.c_double, C.c_double, C.c_double,
-                                       C.c_int, C.c_double]
+                                       C.c_int, C.c_double, C.c_double]
         L.orc_uniforms.argtypes = [C.c_uint64, C.c_int32, C.c_int64, C.c_int32, C.c_int32, DP]
         L.orc_trace_rays.argtypes = [C.POINTER(abi.Job), C.POINTER(abi.Scene), C.c_int64,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -67,7 +67,7 @@ def _chk(rc, what):
 def make_scene(bottle="clearBottle-large.params", l2="planoConvex-f39.9mm.params",
                l3="achromaticDoublet-f50.0mm.params", *, wavelength=785e-9, lens_wavelength=None,
                alpha_deg=5.0, n_axicon=1.45, ring_width=0.5e-3, resdir=RES, isors=False,
-               isors_offset=1.5e-3):
+               isors_offset=1.5e-3, spot_size=1e-3):
     """Oracle's restatement of the scene set-up of reference src/setupMod.f90:113-119 +
     src/main.f90:51-70,81 (lens_wavelength=843e-9 gives the point-phase lenses, main.f90:113-117)."""
     L = lib()
@@ -80,7 +80,7 @@ def make_scene(bottle="clearBottle-large.params", l2="planoConvex-f39.9mm.params
     _chk(L.orc_load_doublet(os.path.join(resdir, l3).encode(), lw, off, C.byref(S.L3)),
          "load_doublet")
     _chk(L.orc_derive_scene(C.byref(S), alpha_deg, n_axicon, ring_width, 1 if isors else 0,
-                            isors_offset), "derive_scene")
+                            isors_offset, spot_size), "derive_scene")
     return S
 
 

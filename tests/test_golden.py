@@ -11,7 +11,7 @@ from tests import cases
 from tests.conftest import rel_err
 
 HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-ALL = cases.RAY_CASES + cases.SCATTER_CASES
+ALL = cases.RAY_CASES + cases.SCATTER_CASES + cases.SOURCE_CASES
 IDS = [c[0] for c in ALL]
 NRAYS, NIMG = 96, 200_000
 
@@ -37,7 +37,7 @@ def _check_rays(r, g, cid, tol):
 
 @pytest.mark.parametrize("cid,files,phase,kw", ALL, ids=IDS)
 def test_oracle_reproduces_golden(orc, gold, cid, files, phase, kw):
-    scene = cases.scene_for(orc, files, phase)
+    scene = cases.scene_for(orc, files, phase, kw)
     r = orc.trace_rays(abi.default_job(phase, **kw), scene, NRAYS)
     _check_rays(r, gold[0], cid, 1e-15)
     img, lost, hist = orc.trace(abi.default_job(phase, NIMG, **kw), scene)
@@ -54,7 +54,7 @@ def test_uniforms_golden(orc, gold):
 
 @pytest.mark.parametrize("cid,files,phase,kw", ALL, ids=IDS)
 def test_host_math_matches_golden(orc, harness, gold, cid, files, phase, kw):
-    scene = cases.scene_for(orc, files, phase)
+    scene = cases.scene_for(orc, files, phase, kw)
     r = harness(abi.default_job(phase, **kw), scene, NRAYS)
     _check_rays(r, gold[0], cid, 1e-6 if "scatter" in cid else 1e-9)
 
@@ -64,11 +64,11 @@ def test_host_math_matches_golden(orc, harness, gold, cid, files, phase, kw):
 def test_cuda_matches_golden(ort, gold, cid, files, phase, kw):
     """Does not touch the oracle: scenes come from the product's own readers."""
     res = os.path.join(os.path.dirname(HERE), "..", "res")
-    st = ort.make_settings(*files)
+    st = ort.make_settings(*files, source_type=kw.get("source", "point"))
     scene, _ = ort.build_scene(st, res, 843e-9 if phase == 2 else None)
     r = ort.trace_rays(abi.default_job(phase, **kw), scene, NRAYS)
     _check_rays(r, gold[0], cid, 1e-6 if "scatter" in cid else 1e-9)
-    img, lost, hist, _ = ort.trace(abi.default_job(phase, NIMG, **kw), scene)
+    img, lost, hist, _ = ort.trace(abi.default_job(phase, NIMG, **kw), scene, allow_trap=True)
     assert np.array_equal(img[0], _dense(gold[1], cid))
     assert np.array_equal(hist[0], gold[1]["%s/hist" % cid])
     assert np.array_equal(lost, gold[1]["%s/lost" % cid])

@@ -25,7 +25,8 @@ def test_uniforms_match_oracle(ort, orc):
 
 
 def _compare(ort, orc, files, phase, kw, n, tol, stop=0, first_ray=0):
-    scene = cases.scene_for(orc, files, phase)
+    scene = cases.scene_for(orc, files, phase, kw)
+    kw = dict(kw)
     job = abi.default_job(phase, stop_after=stop, first_ray=first_ray, **kw)
     a = orc.trace_rays(job, scene, n)
     b = ort.trace_rays(job, scene, n)
@@ -43,6 +44,28 @@ def test_rays_match_oracle(ort, orc, cid, files, phase, kw):
     ok = a["status"] == 0
     if ok.any():
         assert np.abs(np.linalg.norm(a["dir"][:, ok], axis=0) - 1).max() < 1e-12
+
+
+@pytest.mark.parametrize("cid,files,phase,kw", cases.SOURCE_CASES, ids=[c[0] for c in cases.SOURCE_CASES])
+def test_other_sources_match_oracle(ort, orc, cid, files, phase, kw):
+    """crs / isors / spot emitters: per-ray state after the source and at the detector, and the
+    megakernel's image + histogram (isors trips the reference's `error stop` on the ~2.8 % of rays
+    its axicon face reflects: counted as status 26, return code ORT_ETRACE)."""
+    e, a = _compare(ort, orc, files, phase, kw, 100_000, TOL, stop=1)
+    assert np.nanmax(e) < TOL
+    e, a = _compare(ort, orc, files, phase, kw, 100_000, TOL)
+    assert np.nanmax(e) < TOL
+    n = 400_003
+    scene = cases.scene_for(orc, files, phase, kw)
+    kw2 = dict(kw)
+    kw2.setdefault("total_rays", n)
+    job = abi.default_job(phase, n, **kw2)
+    img, lost, hist, _ = ort.trace(job, scene, allow_trap=True)
+    oimg, olost, ohist = orc.trace(job, scene)
+    assert np.array_equal(hist, ohist), list(zip(abi.STATUS_NAMES, hist[0], ohist[0]))
+    assert np.array_equal(img, oimg) and np.array_equal(lost, olost)
+    if kw.get("source") == "isors" and phase == 1:
+        assert 0.02 < hist[0, 26] / n < 0.04
 
 
 @pytest.mark.parametrize("stop", [1, 2, 3, 4])
@@ -108,7 +131,7 @@ def test_trace_image_bit_exact(ort, orc, cid, files, phase, kw):
     """The production megakernel (device-side sources, warp compaction, aggregated atomics):
     integer image, loss counter and per-status histogram identical to the oracle's."""
     n = 1_000_003  # not a multiple of 32 on purpose
-    scene = cases.scene_for(orc, files, phase)
+    scene = cases.scene_for(orc, files, phase, kw)
     job = abi.default_job(phase, n, **kw)
     img, lost, hist, tm = ort.trace(job, scene)
     oimg, olost, ohist = orc.trace(job, scene)
@@ -215,3 +238,33 @@ def test_fast_math_accuracy(ort):
     worst = ort.math_selftest(1 << 24)
     print("max ulp error:", worst)
     assert worst["rcp"] <= 2 and worst["div"] <= 2 and worst["sqrt"] <= 2 and worst["rsqrt"] <= 3, worst
+
+
+def test_ring_without_aim_plane_shortcut(ort, orc):
+    """A hand-built scene whose L2 is shifted 1 mm along z: the flat face no longer lies in the
+    ring source's aim plane, so stage 0 must run the general source + aperture arithmetic."""
+    scene = cases.scene_for(orc, cases.C1, 1)
+    scene.L2.centre[2] += 1e-3
+    n = 500_003
+    job = abi.default_job(1, n)
+    img, lost, hist, _ = ort.trace(job, scene)
+    oimg, olost, ohist = orc.trace(job, scene)
+    assert np.array_equal(hist, ohist) and np.array_equal(img, oimg) and np.array_equal(lost, olost)
+    a = orc.trace_rays(abi.default_job(1), scene, 100_000)
+    b = ort.trace_rays(abi.default_job(1), scene, 100_000)
+    assert np.array_equal(a["status"], b["status"]) and np.array_equal(a["bin"], b["bin"])
+    assert max(np.nanmax(rel_err(a["pos"], b["pos"])), np.nanmax(rel_err(a["dir"], b["dir"]))) < TOL
+
+
+def test_on_axis_ray_sees_zero_reflectance(ort, orc):
+    """SURVEY quirk 3 on the device: exactly normal incidence -> R = 0 -> never reflected."""
+    for bottle in (True, False):
+        scene = cases.scene_for(orc, cases.C2, 2)
+        job = abi.default_job(2, use_bottle=bottle, uniform_override=0.01)
+        p = np.zeros((3, 2))
+        d = np.array([[0.0, 1e-3], [0.0, 0.0], [1.0, np.sqrt(1 - 1e-6)]])
+        a = orc.trace_rays(job, scene, 2, p, d)
+        b = ort.trace_rays(job, scene, 2, p, d)
+        assert b["status"][0] == 0 and tuple(b["bin"][:, 0]) == (0, 0) and b["status"][1] != 0
+        assert np.array_equal(a["status"], b["status"]) and np.array_equal(a["bin"], b["bin"])
+        assert np.array_equal(b["dir"][:, 0], [0.0, 0.0, 1.0])

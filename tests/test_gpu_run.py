@@ -76,7 +76,11 @@ def test_cpp_raytrace_binary(orc, tmp_path):
     assert total.sum() == ring[0].sum() + point[0].sum()
     # unsupported source types stop with a message instead of silently running something else
     lines = (res / "job.params").read_text().splitlines()
-    lines[10] = "crs"
-    (res / "crs.params").write_text("\n".join(lines) + "\n")
-    p = subprocess.run(["./raytrace", "crs.params"], cwd=bindir, env=env, capture_output=True, text=True)
+    lines[10] = "image"
+    (res / "img.params").write_text("\n".join(lines) + "\n")
+    p = subprocess.run(["./raytrace", "img.params"], cwd=bindir, env=env, capture_output=True, text=True)
     assert p.returncode == 2 and "not on the B200 path yet" in p.stderr
+    # the shipped settings.params (crs source, 14-line bottle file, tracker on) runs as is
+    p = subprocess.run(["./raytrace", "settings.params"], cwd=bindir, env=env, capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    assert "Ring  transmitted:" in p.stdout and "Deselecting tracking" in p.stdout

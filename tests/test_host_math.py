@@ -12,10 +12,13 @@ from tests.conftest import rel_err
 TOL = 1e-9
 
 
-@pytest.mark.parametrize("cid,files,phase,kw", cases.RAY_CASES, ids=[c[0] for c in cases.RAY_CASES])
+_CASES = cases.RAY_CASES + cases.SOURCE_CASES
+
+
+@pytest.mark.parametrize("cid,files,phase,kw", _CASES, ids=[c[0] for c in _CASES])
 def test_reformulated_math_matches_oracle(orc, harness, cid, files, phase, kw):
     n = 100_000
-    scene = cases.scene_for(orc, files, phase)
+    scene = cases.scene_for(orc, files, phase, kw)
     job = abi.default_job(phase, **kw)
     a = orc.trace_rays(job, scene, n)
     b = harness(job, scene, n)
@@ -28,7 +31,7 @@ def test_reformulated_math_matches_oracle(orc, harness, cid, files, phase, kw):
 @pytest.mark.parametrize("cid,files,phase,kw", cases.SCATTER_CASES, ids=[c[0] for c in cases.SCATTER_CASES])
 def test_scatter_math_matches_oracle(orc, harness, cid, files, phase, kw):
     n = 100_000
-    scene = cases.scene_for(orc, files, phase)
+    scene = cases.scene_for(orc, files, phase, kw)
     job = abi.default_job(phase, **kw)
     a = orc.trace_rays(job, scene, n)
     b = harness(job, scene, n)
@@ -49,3 +52,19 @@ def test_stage_outputs(orc, harness, stop):
         assert np.array_equal(a["status"], b["status"])
         e = np.maximum(rel_err(a["pos"], b["pos"]), rel_err(a["dir"], b["dir"]))
         assert np.nanmax(e) < TOL
+
+
+def test_on_axis_ray_sees_zero_reflectance(orc, harness):
+    """at EXACTLY normal incidence the reference's fresnel() returns 0, so an
+    on-axis ray is never reflected -- even with a draw (0.01) far below the true 4 % reflectance."""
+    for phase, bottle in ((2, True), (2, False), (1, False)):
+        scene = cases.scene_for(orc, cases.C2, phase)
+        job = abi.default_job(2, use_bottle=bottle, uniform_override=0.01)
+        p = np.zeros((3, 2))
+        d = np.array([[0.0, 1e-3], [0.0, 0.0], [1.0, np.sqrt(1 - 1e-6)]])
+        a = orc.trace_rays(job, scene, 2, p, d)
+        b = harness(job, scene, 2, p, d)
+        assert a["status"][0] == 0 and tuple(a["bin"][:, 0]) == (0, 0)      # axial: sails through
+        assert a["status"][1] != 0                                           # 1 mrad off axis: reflected
+        assert np.array_equal(a["status"], b["status"]) and np.array_equal(a["bin"], b["bin"])
+        assert np.array_equal(a["dir"][:, 0], [0.0, 0.0, 1.0]) and np.array_equal(b["dir"][:, 0], [0.0, 0.0, 1.0])

@@ -243,7 +243,7 @@ def test_image_layout_x_fastest(orc):
 def test_pyref_agrees_with_oracle(orc, cid, files, phase, kw):
     """Independent pure-Python restatement vs the C++ oracle, ray by ray."""
     n = 1500
-    scene = cases.scene_for(orc, files, phase)
+    scene = cases.scene_for(orc, files, phase, kw)
     job = abi.default_job(phase, **kw)
     a = orc.trace_rays(job, scene, n)
     for i in range(n):
