@@ -25,6 +25,15 @@
 
 #include "ort_optics.cuh"
 
+/* `make DEBUG=1` (install.sh -d): own bounds checks on every queue slot and image bin -- the
+ * substitute for compute-sanitizer, which is closed on this GPU pool */
+#ifdef ORT_DEBUG
+#include <cassert>
+#define ORT_ASSERT(c) assert(c)
+#else
+#define ORT_ASSERT(c) ((void)0)
+#endif
+
 #ifndef ORT_TPB
 #define ORT_TPB 256
 #endif
@@ -61,6 +70,7 @@ __device__ __forceinline__ void ort_q_push(WarpQueue& q, int& n, bool alive, con
     unsigned m = __ballot_sync(ORT_FULL, alive);
     if (alive) {
         int p = n + __popc(m & ((1u << lane) - 1u));
+        ORT_ASSERT(p >= 0 && p < ORT_QCAP);
         q.px[p] = r.px; q.py[p] = r.py; q.pz[p] = r.pz;
         q.dx[p] = r.dx; q.dy[p] = r.dy; q.dz[p] = r.dz;
         q.id[p] = id;
@@ -74,6 +84,7 @@ __device__ __forceinline__ bool ort_q_pop(WarpQueue& q, int& n, OrtRay& r, uint3
     bool act = (int)lane < cnt;
     if (act) {
         int p = base + lane;
+        ORT_ASSERT(p >= 0 && p < ORT_QCAP);
         r.px = q.px[p]; r.py = q.py[p]; r.pz = q.pz[p];
         r.dx = q.dx[p]; r.dy = q.dy[p]; r.dz = q.dz[p];
         id = q.id[p];
@@ -103,6 +114,7 @@ __device__ __forceinline__ void ort_count(unsigned& mine, int st, unsigned lane)
 __device__ __forceinline__ void ort_bin(unsigned long long* img, bool binned, int xp, int yp, unsigned lane) {
     if (!__any_sync(ORT_FULL, binned)) return;
     unsigned key = binned ? (unsigned)((yp + ORT_IMG_HALF) * ORT_IMG_N + (xp + ORT_IMG_HALF)) : 0xffffffffu;
+    ORT_ASSERT(!binned || key < (unsigned)ORT_IMG_BINS);
     unsigned m = __match_any_sync(ORT_FULL, key);
     if (binned && (int)lane == __ffs(m) - 1) atomicAdd(img + key, (unsigned long long)__popc(m));
 }

@@ -84,3 +84,15 @@ def test_cpp_raytrace_binary(orc, tmp_path):
     p = subprocess.run(["./raytrace", "settings.params"], cwd=bindir, env=env, capture_output=True, text=True)
     assert p.returncode == 0, p.stderr
     assert "Ring  transmitted:" in p.stdout and "Deselecting tracking" in p.stdout
+
+
+def test_all_kernel_variants_bounds_checked():
+    """Every kernel variant once, through the assert-instrumented build (make DEBUG=1): the
+    project's own substitute for compute-sanitizer, which is closed on this GPU pool."""
+    dbg = os.path.join(ROOT, "opticalraytrace_b200", "libort_debug.so")
+    if not os.path.exists(dbg):
+        pytest.skip("libort_debug.so not built (make -C opticalraytrace_b200/csrc DEBUG=1)")
+    import sys
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sanitize_case.py")],
+                       env=dict(os.environ, ORT_LIB=dbg), capture_output=True, text=True)
+    assert p.returncode == 0 and "sanitize_case ok" in p.stdout, p.stdout + p.stderr
