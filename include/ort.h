@@ -237,6 +237,14 @@ int ort_trace_rays(const ort_job* job, const ort_scene* scene, int64_t n, const 
                    const double* dir_in, double* pos_out, double* dir_out, int32_t* status,
                    int32_t* bin_xy);
 
+/* The reference's ray tracker (src/stackMod.f90 + src/main.f90:103,107,144-160, read by
+ * debug-plot.py): for rays [first_ray, first_ray+nrays) of job->phase, append to `path` the
+ * positions each surviving ray visited (image plane first -- the stack is popped -- one
+ * "3(F10.7,1x)" line per position) followed by three blank lines; rays lost in a lens leave
+ * only the blank lines, rays lost in the bottle their source and bottle positions plus six.
+ * nrays <= 10000 like the reference (src/setupMod.f90:75). */
+int ort_write_tracks(const ort_job* job, const ort_scene* scene, const char* path);
+
 /* The uniforms a ray sees: out[i] = uniform of slot `first_slot+i` (testing the generator). */
 int ort_uniforms(uint64_t seed, int32_t phase, int64_t ray, int32_t first_slot, int32_t n,
                  double* out);

@@ -591,3 +591,66 @@ extern "C" int ort_math_selftest(int64_t n, uint64_t max_ulp[4]) {
     for (int i = 0; i < 4; ++i) max_ulp[i] = h[i];
     return ORT_OK;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * tracker files (reference src/stackMod.f90:38-52, src/main.f90:103-107,144-160,
+ * src/optics_system.f90:28-50)
+ * ---------------------------------------------------------------------------------------- */
+extern "C" int ort_write_tracks(const ort_job* job, const ort_scene* scene, const char* path) {
+    if (!job || !scene || !path) return ORT_EINVAL;
+    const int64_t n = job->nrays;
+    if (n > 10000) { /* src/setupMod.f90:75 */
+        ort_set_error("Too many photons for tracker use!");
+        return ORT_EINVAL;
+    }
+    if (n <= 0) return ORT_OK;
+    /* positions after the source, the bottle, L2, L3 and at the image plane: the same kernel
+     * stopped at five places (ort_job.stop_after) */
+    const int stops[5] = {ORT_STOP_SOURCE, ORT_STOP_BOTTLE, ORT_STOP_L2, ORT_STOP_L3, ORT_STOP_NONE};
+    std::vector<double> pos[5], dir((size_t)3 * n);
+    std::vector<int32_t> status[5], bins((size_t)2 * n);
+    for (int k = 0; k < 5; ++k) {
+        pos[k].resize((size_t)3 * n);
+        status[k].resize((size_t)n);
+        ort_job j = *job;
+        j.stop_after = stops[k];
+        int rc = ort_trace_rays(&j, scene, n, nullptr, nullptr, pos[k].data(), dir.data(), status[k].data(),
+                                bins.data());
+        if (rc && rc != ORT_ETRACE) return rc;
+    }
+    FILE* fh = fopen(path, "w");
+    if (!fh) {
+        ort_set_error("cannot write %s", path);
+        return ORT_EIO;
+    }
+    auto line = [&](int k, int64_t i) {
+        fprintf(fh, "%10.7f %10.7f %10.7f \n", pos[k][i], pos[k][n + i], pos[k][2 * n + i]);
+    };
+    auto blanks = [&]() { fputs("  \n  \n  \n", fh); };
+    const bool bottle = job->phase == ORT_PHASE_POINT && job->use_bottle;
+    for (int64_t i = 0; i < n; ++i) {
+        const int st = status[4][i];
+        const bool lost_bottle = (st >= 1 && st <= 8) || st == ORT_ST_TAUINT_MISS;
+        const bool lost_source = st == ORT_ST_SOURCE_MISS;
+        const bool lost_lens = st >= ORT_ST_L2_APERTURE && st <= ORT_ST_L3_IRIS_AFTER;
+        if (lost_source) { /* the reference aborts here */
+            blanks();
+        } else if (lost_bottle) { /* src/main.f90:150-155: write what was pushed, then write_empty */
+            line(4, i); /* where the ray stopped inside the bottle */
+            line(0, i);
+            blanks();
+            blanks();
+        } else if (lost_lens) { /* src/optics_system.f90:31-34,41-44: write_empty */
+            blanks();
+        } else { /* src/main.f90:107,160: pop everything */
+            line(4, i);
+            line(3, i);
+            line(2, i);
+            if (bottle) line(1, i);
+            line(0, i);
+            blanks();
+        }
+    }
+    fclose(fh);
+    return ORT_OK;
+}

@@ -18,7 +18,7 @@ _lib = None
 # every symbol include/ort.h declares (tests/test_abi.py checks the header against this list)
 EXPORTS = [
     "ort_init", "ort_init_rank", "ort_nccl_unique_id", "ort_finalize", "ort_last_error",
-    "ort_device_count", "ort_struct_sizes", "ort_trace", "ort_trace_rays", "ort_uniforms", "ort_measure_fp64_peak", "ort_math_selftest",
+    "ort_device_count", "ort_struct_sizes", "ort_trace", "ort_trace_rays", "ort_uniforms", "ort_measure_fp64_peak", "ort_math_selftest", "ort_write_tracks",
     "ort_load_plano", "ort_load_doublet", "ort_load_bottle", "ort_read_settings",
     "ort_build_scene", "ort_job_from_settings", "ort_output_basename", "ort_write_images",
     "ort_append_trans_stats",
@@ -53,6 +53,7 @@ def load():
     L.ort_uniforms.argtypes = [C.c_uint64, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]
     L.ort_measure_fp64_peak.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.ort_math_selftest.argtypes = [C.c_int64, C.POINTER(C.c_uint64)]
+    L.ort_write_tracks.argtypes = [C.POINTER(abi.Job), C.POINTER(abi.Scene), C.c_char_p]
     L.ort_load_plano.argtypes = [C.c_char_p, C.c_double, C.c_double, C.POINTER(abi.Plano)]
     L.ort_load_doublet.argtypes = [C.c_char_p, C.c_double, C.c_double, C.POINTER(abi.Doublet)]
     L.ort_load_bottle.argtypes = [C.c_char_p, C.c_double, C.POINTER(abi.Bottle)]
@@ -198,6 +199,11 @@ def trace_rays(job, scene, n, pos_in=None, dir_in=None):
                                 dir_out.ctypes.data, status.ctypes.data, bins.ctypes.data),
           allow=(abi.ORT_ETRACE,))
     return dict(pos=pos_out, dir=dir_out, status=status, bin=bins)
+
+
+def write_tracks(job, scene, path):
+    """ort_write_tracks: the reference's *-ringtrace.dat / *-pointtrace.dat"""
+    check(load().ort_write_tracks(C.byref(job), C.byref(scene), os.fsencode(path)))
 
 
 def uniforms(seed, phase, ray, first_slot, n):

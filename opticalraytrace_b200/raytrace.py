@@ -27,12 +27,14 @@ def run(settings_path, resdir, datadir=None, *, nphotons=None, write=True, verbo
         st.nphotons = nphotons
     if verbose:
         print(" Using %s settings." % os.path.basename(settings_path))
-    if st.use_tracker:
-        # the reference's OpenMP build does the same (src/setupMod.f90:65-73)
-        if verbose:
-            print(" ***************\n Cannot track packets on the GPU build!\n"
-                  " Deselecting tracking of packets\n ***************")
-        st.use_tracker = 0
+    if st.use_tracker:  # src/setupMod.f90:75-82
+        if st.nphotons > 10000:
+            raise lib.OrtError(abi.ORT_EINVAL, "Too many photons for tracker use!")
+        if st.make_images:
+            if verbose:
+                print(" ***************\n Cannot track packets and make images!\n"
+                      " Deselecting makeImages\n ***************")
+            st.make_images = 0
     src = st.source_type.decode()
     if src == "image":  # emit_image (src/sourceMod.f90:303-361) is the one emitter still missing
         raise lib.OrtError(abi.ORT_EINVAL, "source type 'image' is not on the B200 path yet")
@@ -55,6 +57,9 @@ def run(settings_path, resdir, datadir=None, *, nphotons=None, write=True, verbo
     if write and datadir is not None:
         folder = os.path.join(datadir, st.folder.decode())
         os.makedirs(folder, exist_ok=True)
+        if st.use_tracker:  # src/main.f90:72-74,121-124
+            lib.write_tracks(jr, scene_ring, os.path.join(folder, name + "-ringtrace.dat"))
+            lib.write_tracks(jp, scene_point, os.path.join(folder, name + "-pointtrace.dat"))
         lib.append_trans_stats(folder, st, scene_point, rcount, pcount)
         if st.make_images:
             lib.write_images(os.path.join(folder, name + "_image"), ring[0], point[0])

@@ -36,10 +36,16 @@ int main(int argc, char** argv) {
 
     ort_settings st;
     if (ort_read_settings((std::string(resdir) + "/" + arg).c_str(), &st)) return fail("settings");
-    if (st.use_tracker) { /* same rule as the reference's OpenMP build, src/setupMod.f90:65-73 */
-        std::printf(" ***************\n Cannot track packets on the GPU build!\n"
-                    " Deselecting tracking of packets\n ***************\n");
-        st.use_tracker = 0;
+    if (st.use_tracker) { /* src/setupMod.f90:75-82 */
+        if (st.nphotons > 10000) {
+            std::fprintf(stderr, "ERROR STOP Too many photons for tracker use!\n");
+            return 1;
+        }
+        if (st.make_images) {
+            std::printf(" ***************\n Cannot track packets and make images!\n"
+                        " Deselecting makeImages\n ***************\n");
+            st.make_images = 0;
+        }
     }
     if (std::strcmp(st.source_type, "image") == 0) {
         std::fprintf(stderr,
@@ -77,6 +83,12 @@ int main(int argc, char** argv) {
     std::string folder = std::string(datadir) + "/" + st.folder + "/";
     ::mkdir(datadir, 0777);
     ::mkdir(folder.c_str(), 0777);
+    if (st.use_tracker) { /* src/main.f90:72-74,121-124: <name>-ringtrace.dat / -pointtrace.dat */
+        ort_job_from_settings(&st, ORT_PHASE_RING, &job);
+        if (ort_write_tracks(&job, &ring_scene, (folder + name + "-ringtrace.dat").c_str())) return fail("ring tracks");
+        ort_job_from_settings(&st, ORT_PHASE_POINT, &job);
+        if (ort_write_tracks(&job, &point_scene, (folder + name + "-pointtrace.dat").c_str())) return fail("point tracks");
+    }
     if (ort_append_trans_stats(folder.c_str(), &st, &point_scene, rcount, pcount)) return fail("trans-stats");
     double n = (double)st.nphotons;
     std::printf("Ring  transmitted:  %8.2f%%\n", 100. * (1. - (rcount / n)));

@@ -83,7 +83,11 @@ def test_cpp_raytrace_binary(orc, tmp_path):
     # the shipped settings.params (crs source, 14-line bottle file, tracker on) runs as is
     p = subprocess.run(["./raytrace", "settings.params"], cwd=bindir, env=env, capture_output=True, text=True)
     assert p.returncode == 0, p.stderr
-    assert "Ring  transmitted:" in p.stdout and "Deselecting tracking" in p.stdout
+    assert "Ring  transmitted:" in p.stdout and "Deselecting makeImages" in p.stdout
+    out = tmp_path / "data" / "settings-testysors"
+    names = sorted(os.listdir(out))
+    assert [n.split("-")[-1] for n in names if "trace" in n] == ["pointtrace.dat", "ringtrace.dat"]
+    assert not any(n.endswith("_image-ring.dat") for n in names)   # tracker => no images
 
 
 def test_all_kernel_variants_bounds_checked():
@@ -96,3 +100,55 @@ def test_all_kernel_variants_bounds_checked():
     p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sanitize_case.py")],
                        env=dict(os.environ, ORT_LIB=dbg), capture_output=True, text=True)
     assert p.returncode == 0 and "sanitize_case ok" in p.stdout, p.stdout + p.stderr
+
+
+def _read_tracks(path):
+    """debug-plot.py's reader, condensed: blocks of position lines separated by blank lines."""
+    rays, cur, blanks = [], [], 0
+    for line in open(path):
+        if len(line) > 3:
+            cur.append([float(v) for v in line.split()])
+            blanks = 0
+        else:
+            if blanks == 0 and cur:
+                rays.append(cur)
+            cur = []
+            blanks += 1
+    return rays
+
+
+def test_tracker_files(ort, orc, tmp_path):
+    """reference src/stackMod.f90 + src/main.f90:103-107,144-160: popped stack (image plane first),
+    `3(F10.7,1x)` lines, three blank lines per ray; lens-lost rays leave only blanks."""
+    n = 500
+    for phase in (1, 2):
+        scene = cases.scene_for(orc, cases.C1, phase)
+        job = abi.default_job(phase, n)
+        path = str(tmp_path / ("p%d.dat" % phase))
+        ort.write_tracks(job, scene, path)
+        text = open(path).read().splitlines()
+        assert all(len(l) == 33 or l == "  " for l in text)
+        full = orc.trace_rays(job, scene, n)
+        st = full["status"]
+        survivors = np.flatnonzero((st == 0) | (st >= 21) & (st <= 23))
+        bottle_lost = np.flatnonzero((st >= 1) & (st <= 8))
+        rays = _read_tracks(path)
+        assert len(rays) == len(survivors) + len(bottle_lost)
+        k = 0
+        for i in range(n):
+            if i in survivors:
+                r = rays[k]; k += 1
+                assert len(r) == (5 if phase == 2 else 4)
+                assert np.allclose(r[0], full["pos"][:, i], atol=6e-8)            # image plane first
+                src = orc.trace_rays(abi.default_job(phase, stop_after=1, first_ray=i), scene, 1)
+                assert np.allclose(r[-1], src["pos"][:, 0], atol=6e-8)            # source last
+                zs = [p[2] for p in r]
+                assert zs == sorted(zs, reverse=True)
+            elif i in bottle_lost:
+                r = rays[k]; k += 1
+                assert len(r) == 2 and np.allclose(r[0], full["pos"][:, i], atol=6e-8)
+        blank = sum(1 for l in text if l == "  ")
+        assert blank == 3 * n + 3 * len(bottle_lost)
+    from opticalraytrace_b200.lib import OrtError
+    with pytest.raises(OrtError, match="Too many photons"):
+        ort.write_tracks(abi.default_job(1, 10001), scene, str(tmp_path / "x.dat"))
