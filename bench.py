@@ -209,6 +209,8 @@ def main():
     ap.add_argument("--flat", action="store_true", help="diagnostic: kernel without compaction")
     ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4],
                     help="BASELINE.json config (2 = the headline)")
+    ap.add_argument("--precision", type=int, default=64, choices=[64, 32],
+                    help="64 = the reference's arithmetic (headline); 32 = the fp32 variant (1e-5 parity)")
     ap.add_argument("--fix-ellipse", action="store_true",
                     help="config 4: opt-in outer-ellipse fix instead of the reference's half radii")
     args = ap.parse_args()
@@ -256,6 +258,7 @@ def main():
         job = lib.job_from_settings(st, ph)
         job.first_ray = (k * world + rank) * nr
         job.nrays = nr
+        job.precision = args.precision
         if args.flat:
             job.flags |= abi.FLAG_NO_COMPACTION
         if args.fix_ellipse:
@@ -307,7 +310,7 @@ def main():
             "metric": "rays/sec", "value": total_rays / dev_s, "unit": "rays/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_s / args.steps * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f%d" % args.precision, "data": "synthetic",
             "config": {"workload": workload_text(args.config, args.phase, args.flat, args.fix_ellipse),
                        "rays_per_gpu_per_step": n * nsc, "scenes": nsc,
                        "rays_per_step": n * nsc * world, "parallelism": "ray-range x%d" % world,

@@ -158,7 +158,9 @@ typedef struct {
     int32_t use_bottle;  /* src/setupMod.f90:63 (point phase only, src/main.f90:145) */
     int32_t iris_before; /* iris(1), src/setupMod.f90:103-108 */
     int32_t iris_after;  /* iris(2) */
-    int32_t precision;   /* 64 (fp64, the reference's arithmetic) */
+    int32_t precision;   /* 64: fp64, the reference's arithmetic (1e-9 parity);
+                            32: the fp32 variant (1e-5 parity, same draws, same decisions except
+                            within 2^-24 of a threshold) */
     int32_t flags;       /* ORT_FLAG_* */
     int32_t stop_after;  /* ORT_STOP_* (ort_trace_rays only) */
     int32_t source_kind; /* ORT_SRC_*: which of the reference's sources feeds the loop */

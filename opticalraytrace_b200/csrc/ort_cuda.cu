@@ -240,8 +240,8 @@ static int validate_job(const ort_job* job) {
         ort_set_error("job.phase must be 1 (ring) or 2 (point), got %d", job->phase);
         return ORT_EINVAL;
     }
-    if (job->precision != 64) {
-        ort_set_error("job.precision %d not supported (64 only)", job->precision);
+    if (job->precision != 64 && job->precision != 32) {
+        ort_set_error("job.precision %d not supported (64 or 32)", job->precision);
         return ORT_EINVAL;
     }
     if (job->nrays < 0 || job->first_ray < 0) {
@@ -266,37 +266,45 @@ static int validate_job(const ort_job* job) {
 /* ------------------------------------------------------------------------------------------
  * kernel dispatch
  * ---------------------------------------------------------------------------------------- */
-typedef void (*trace_kernel_t)(const DevScene, const DevJob, unsigned long long*, unsigned long long*);
-
-static trace_kernel_t pick_kernel(int phase, int bottle_mode, int src, bool flat) {
-    if (flat) { /* diagnostic kernel: default sources only */
-        if (phase == ORT_PHASE_RING) return ort_trace_flat_kernel<ORT_PHASE_RING, 0>;
+/* ------------------------------------------------------------------------------------------
+ * kernel dispatch: <loop, bottle kind, source kind, real type>
+ * ---------------------------------------------------------------------------------------- */
+template <typename R>
+struct Kernels {
+    typedef void (*trace_t)(const DevSceneT<R>, const DevJob, unsigned long long*, unsigned long long*);
+    static trace_t pick(int phase, int bottle_mode, int src, bool flat) {
+        if (flat) { /* diagnostic kernel: default sources only */
+            if (phase == ORT_PHASE_RING) return ort_trace_flat_kernel<ORT_PHASE_RING, 0, R>;
+            switch (bottle_mode) {
+                case 0: return ort_trace_flat_kernel<ORT_PHASE_POINT, 0, R>;
+                case 1: return ort_trace_flat_kernel<ORT_PHASE_POINT, 1, R>;
+                default: return ort_trace_flat_kernel<ORT_PHASE_POINT, 2, R>;
+            }
+        }
+        if (phase == ORT_PHASE_RING) {
+            switch (src) {
+                case ORT_SRC_CRS: return ort_trace_kernel<ORT_PHASE_RING, 0, ORT_SRC_CRS, R>;
+                case ORT_SRC_ISORS: return ort_trace_kernel<ORT_PHASE_RING, 0, ORT_SRC_ISORS, R>;
+                default: return ort_trace_kernel<ORT_PHASE_RING, 0, ORT_SRC_POINT, R>; /* point, spot: ring() */
+            }
+        }
+        const bool spot = src == ORT_SRC_SPOT; /* crs, isors: point() in the point loop */
         switch (bottle_mode) {
-            case 0: return ort_trace_flat_kernel<ORT_PHASE_POINT, 0>;
-            case 1: return ort_trace_flat_kernel<ORT_PHASE_POINT, 1>;
-            default: return ort_trace_flat_kernel<ORT_PHASE_POINT, 2>;
+            case 0: return spot ? ort_trace_kernel<ORT_PHASE_POINT, 0, ORT_SRC_SPOT, R> : ort_trace_kernel<ORT_PHASE_POINT, 0, ORT_SRC_POINT, R>;
+            case 1: return spot ? ort_trace_kernel<ORT_PHASE_POINT, 1, ORT_SRC_SPOT, R> : ort_trace_kernel<ORT_PHASE_POINT, 1, ORT_SRC_POINT, R>;
+            default: return spot ? ort_trace_kernel<ORT_PHASE_POINT, 2, ORT_SRC_SPOT, R> : ort_trace_kernel<ORT_PHASE_POINT, 2, ORT_SRC_POINT, R>;
         }
     }
-    if (phase == ORT_PHASE_RING) {
-        switch (src) {
-            case ORT_SRC_CRS: return ort_trace_kernel<ORT_PHASE_RING, 0, ORT_SRC_CRS>;
-            case ORT_SRC_ISORS: return ort_trace_kernel<ORT_PHASE_RING, 0, ORT_SRC_ISORS>;
-            default: return ort_trace_kernel<ORT_PHASE_RING, 0, ORT_SRC_POINT>; /* point, spot: ring() */
-        }
-    }
-    const bool spot = src == ORT_SRC_SPOT; /* crs, isors: point() in the point loop */
-    switch (bottle_mode) {
-        case 0: return spot ? ort_trace_kernel<ORT_PHASE_POINT, 0, ORT_SRC_SPOT> : ort_trace_kernel<ORT_PHASE_POINT, 0, ORT_SRC_POINT>;
-        case 1: return spot ? ort_trace_kernel<ORT_PHASE_POINT, 1, ORT_SRC_SPOT> : ort_trace_kernel<ORT_PHASE_POINT, 1, ORT_SRC_POINT>;
-        default: return spot ? ort_trace_kernel<ORT_PHASE_POINT, 2, ORT_SRC_SPOT> : ort_trace_kernel<ORT_PHASE_POINT, 2, ORT_SRC_POINT>;
-    }
-}
+};
+static inline void scene_as(const DevScene& s, DevSceneT<double>& d) { d = s; }
+static inline void scene_as(const DevScene& s, DevSceneT<float>& d) { ort_scene_to_float(s, d); }
 
 static const int64_t ORT_CHUNK = (int64_t)1 << 31; /* rays per scene per launch (ids are 32-bit) */
 
 /* enqueue the trace of rays [first, first+n) of every scene on device ctx; returns launches */
-static int enqueue_trace(DeviceCtx& c, const ort_job& job, const std::vector<DevScene>& ds, int64_t first,
-                         int64_t n, int64_t* launches) {
+template <typename R>
+static int enqueue_trace_t(DeviceCtx& c, const ort_job& job, const std::vector<DevScene>& ds, int64_t first,
+                           int64_t n, int64_t* launches) {
     const int nscenes = (int)ds.size();
     CK(cudaSetDevice(c.dev));
     size_t elems = (size_t)nscenes * (ORT_IMG_BINS + ORT_NSTATUS);
@@ -310,8 +318,8 @@ static int enqueue_trace(DeviceCtx& c, const ort_job& job, const std::vector<Dev
     for (auto& s : ds) any_scatter |= (s.scatter_b || s.scatter_c);
     int bottle_mode = (job.phase == ORT_PHASE_POINT && job.use_bottle) ? (any_scatter ? 2 : 1) : 0;
     bool flat = (job.flags & ORT_FLAG_NO_COMPACTION) != 0 && job.source_kind == ORT_SRC_POINT;
-    trace_kernel_t k = pick_kernel(job.phase, bottle_mode, job.source_kind, flat);
-    size_t smem = flat ? 0 : (size_t)ORT_WPB * sizeof(WarpShared);
+    typename Kernels<R>::trace_t k = Kernels<R>::pick(job.phase, bottle_mode, job.source_kind, flat);
+    size_t smem = flat ? 0 : (size_t)ORT_WPB * sizeof(WarpShared<R>);
     if (smem) CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, ORT_TPB, smem));
@@ -325,6 +333,8 @@ static int enqueue_trace(DeviceCtx& c, const ort_job& job, const std::vector<Dev
     /* one launch per scene and per <= 2^31-ray chunk, back to back on the stream; scene and job
      * travel as kernel parameters, so there is nothing to upload between launches */
     for (int sc = 0; sc < nscenes; ++sc) {
+        DevSceneT<R> dsr;
+        scene_as(ds[sc], dsr);
         for (int64_t off = 0; off < n; off += ORT_CHUNK) {
             int64_t m = n - off < ORT_CHUNK ? n - off : ORT_CHUNK;
             DevJob dj;
@@ -332,7 +342,7 @@ static int enqueue_trace(DeviceCtx& c, const ort_job& job, const std::vector<Dev
             int64_t batches = (m + 31) / 32;
             int64_t want = (batches + ORT_WPB - 1) / ORT_WPB;
             int gsz = (int)(want < grid ? (want > 0 ? want : 1) : grid);
-            k<<<gsz, ORT_TPB, smem, c.stream>>>(ds[sc], dj, d_img + (size_t)sc * ORT_IMG_BINS,
+            k<<<gsz, ORT_TPB, smem, c.stream>>>(dsr, dj, d_img + (size_t)sc * ORT_IMG_BINS,
                                                 d_cnt + (size_t)sc * ORT_NSTATUS);
             CK(cudaGetLastError());
             ++*launches;
@@ -340,6 +350,11 @@ static int enqueue_trace(DeviceCtx& c, const ort_job& job, const std::vector<Dev
     }
     CK(cudaEventRecord(c.ev_traced, c.stream));
     return ORT_OK;
+}
+static int enqueue_trace(DeviceCtx& c, const ort_job& job, const std::vector<DevScene>& ds, int64_t first,
+                         int64_t n, int64_t* launches) {
+    return job.precision == 32 ? enqueue_trace_t<float>(c, job, ds, first, n, launches)
+                               : enqueue_trace_t<double>(c, job, ds, first, n, launches);
 }
 
 extern "C" int ort_trace(const ort_job* job, const ort_scene* scenes, int nscenes, uint64_t* image,
@@ -490,8 +505,15 @@ extern "C" int ort_trace_rays(const ort_job* job, const ort_scene* scene, int64_
         CKB(cudaMalloc(&d_out, 2 * vb));
         CKB(cudaMalloc(&d_int, (size_t)3 * n * sizeof(int32_t)));
         int grid = (int)((n + ORT_TPB - 1) / ORT_TPB);
-        ort_rays_kernel<<<grid, ORT_TPB, 0, c.stream>>>(ds, dj, d_in, d_in ? d_in + 3 * n : nullptr, d_out,
-                                                        d_out + 3 * n, d_int, d_int + n, (long long)n);
+        if (job->precision == 32) {
+            DevSceneT<float> dsf;
+            ort_scene_to_float(ds, dsf);
+            ort_rays_kernel<float><<<grid, ORT_TPB, 0, c.stream>>>(dsf, dj, d_in, d_in ? d_in + 3 * n : nullptr, d_out,
+                                                                   d_out + 3 * n, d_int, d_int + n, (long long)n);
+        } else {
+            ort_rays_kernel<double><<<grid, ORT_TPB, 0, c.stream>>>(ds, dj, d_in, d_in ? d_in + 3 * n : nullptr, d_out,
+                                                                    d_out + 3 * n, d_int, d_int + n, (long long)n);
+        }
         CKB(cudaGetLastError());
         if (pos_out) CKB(cudaMemcpyAsync(pos_out, d_out, vb, cudaMemcpyDeviceToHost, c.stream));
         if (dir_out) CKB(cudaMemcpyAsync(dir_out, d_out + 3 * n, vb, cudaMemcpyDeviceToHost, c.stream));

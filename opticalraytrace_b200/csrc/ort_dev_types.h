@@ -18,63 +18,67 @@
                                travels as a __grid_constant__ kernel parameter (712 B) */
 
 /* One refracting interface n_a -> n_b */
-struct DevIface {
-    double na, nb;  /* refractive indices on the incoming / outgoing side */
-    double eta;     /* na / nb  (reference computes n1/n2 per call, src/surfaces.f90:279,352) */
-    double eta2;    /* eta * eta */
+template <typename R>
+struct DevIfaceT {
+    R na, nb;  /* refractive indices on the incoming / outgoing side */
+    R eta;     /* na / nb  (reference computes n1/n2 per call, src/surfaces.f90:279,352) */
+    R eta2;    /* eta * eta */
 };
 
-struct DevScene {
+template <typename R>
+struct DevSceneT {
     /* --- bottle (reference src/lens.f90:230-350) --- */
-    double bcx, bcy, bcz;         /* centre */
-    double b_in_r, b_in_r2;       /* inner cylinder radius Ra - th and its square */
-    double b_out_r, b_out_r2;     /* outer cylinder radius Ra */
-    double b_in_invr, b_out_invr; /* 1/radius: the radial normal of a clear cylindrical wall */
-    double b_in_ia2, b_in_ib2;    /* inner ellipse 1/semia^2 (z), 1/semib^2 (y) */
-    double b_out_ia2, b_out_ib2;  /* outer ellipse (reference: Ra/2, Rb/2; fixed: Ra, Rb) */
-    DevIface b_in;                /* contents -> glass */
-    DevIface b_out;               /* glass -> air (1.0) */
-    double mutot_c, inv_mutot_c, albedo_c; /* contents: mua+mus, 1/(mua+mus), mus/(mus+mua) */
-    double mutot_b, inv_mutot_b, albedo_b; /* wall */
+    R bcx, bcy, bcz;         /* centre */
+    R b_in_r, b_in_r2;       /* inner cylinder radius Ra - th and its square */
+    R b_out_r, b_out_r2;     /* outer cylinder radius Ra */
+    R b_in_invr, b_out_invr; /* 1/radius: the radial normal of a clear cylindrical wall */
+    R b_in_ia2, b_in_ib2;    /* inner ellipse 1/semia^2 (z), 1/semib^2 (y) */
+    R b_out_ia2, b_out_ib2;  /* outer ellipse (reference: Ra/2, Rb/2; fixed: Ra, Rb) */
+    DevIfaceT<R> b_in;                /* contents -> glass */
+    DevIfaceT<R> b_out;               /* glass -> air (1.0) */
+    R mutot_c, inv_mutot_c, albedo_c; /* contents: mua+mus, 1/(mua+mus), mus/(mus+mua) */
+    R mutot_b, inv_mutot_b, albedo_b; /* wall */
     /* --- sources (reference src/sourceMod.f90:12-47,250-300) --- */
-    double cos_theta_max, one_m_ctm, point_offset;
-    double r1, r2_m_r1;           /* annulus: r = r1 + u (r2 - r1) */
-    double ra2, ra_over_rb;       /* Ra^2, Ra/Rb */
-    double lens_r2;               /* (L2.radius + 10e-3)^2 */
-    double l2_fb;                 /* z of the aim disc */
+    R cos_theta_max, one_m_ctm, point_offset;
+    R r1, r2_m_r1;           /* annulus: r = r1 + u (r2 - r1) */
+    R ra2, ra_over_rb;       /* Ra^2, Ra/Rb */
+    R lens_r2;               /* (L2.radius + 10e-3)^2 */
+    R l2_fb;                 /* z of the aim disc */
     /* --- crs / isors sources (reference src/sourceMod.f90:50-89,162-247) --- */
-    double spot_size;             /* crs: sigma of the spot (already rescaled) */
-    double crs_r2;                /* crs: (Ra + thickness)^2, the cylinder the spot is projected on */
-    double isors_beam;            /* isors: beam width (sigma of the Gaussian on the axicon) */
-    double isors_base;            /* isors: (separation + beam) / tan(alpha (n_axicon - 1)) */
-    double isors_k, isors_h;      /* isors: axicon (radius/height)^2 and height */
-    double isors_z;               /* isors: Ra + bottle z + epsilon(1.) */
-    double isors_lens_r2;         /* isors: L2.radius^2 (aim disc) */
-    DevIface isors_axicon;        /* 1.4 -> 1.0 */
+    R spot_size;             /* crs: sigma of the spot (already rescaled) */
+    R crs_r2;                /* crs: (Ra + thickness)^2, the cylinder the spot is projected on */
+    R isors_beam;            /* isors: beam width (sigma of the Gaussian on the axicon) */
+    R isors_base;            /* isors: (separation + beam) / tan(alpha (n_axicon - 1)) */
+    R isors_k, isors_h;      /* isors: axicon (radius/height)^2 and height */
+    R isors_z;               /* isors: Ra + bottle z + epsilon(1.) */
+    R isors_lens_r2;         /* isors: L2.radius^2 (aim disc) */
+    DevIfaceT<R> isors_axicon;        /* 1.4 -> 1.0 */
     /* --- L2 plano-convex (reference src/lens.f90:425-481) --- */
-    double l2_cx, l2_cy, l2_cz;   /* sphere centre */
-    double l2_flat_z;             /* centre.z + R - thickness */
-    double l2_radius2;            /* aperture radius squared */
-    double l2_R2, l2_invR;        /* curve radius squared, 1/R */
-    double l2_fnx, l2_fny, l2_fnz;/* flat-face normal */
-    DevIface l2_in, l2_out;       /* n1 -> n2, n2 -> n1 */
+    R l2_cx, l2_cy, l2_cz;   /* sphere centre */
+    R l2_flat_z;             /* centre.z + R - thickness */
+    R l2_radius2;            /* aperture radius squared */
+    R l2_R2, l2_invR;        /* curve radius squared, 1/R */
+    R l2_fnx, l2_fny, l2_fnz;/* flat-face normal */
+    DevIfaceT<R> l2_in, l2_out;       /* n1 -> n2, n2 -> n1 */
     /* --- L3 achromatic doublet (reference src/lens.f90:531-645) --- */
-    double l3_c1x, l3_c1y, l3_c1z, l3_c2x, l3_c2y, l3_c2z, l3_c3x, l3_c3y, l3_c3z;
-    double l3_R1_2, l3_R2_2, l3_R3_2, l3_invR1, l3_invR2, l3_invR3;
-    double l3_radius2;            /* aperture */
-    double l3_iris_r2;            /* (radius * iris_radius)^2 */
-    double l3_iris1_z, l3_iris2_z;/* centre1.z - R1, centre3.z + R3 */
-    DevIface l3_s1, l3_s2, l3_s3; /* n1->n2, n2->n3, n3->n1 */
+    R l3_c1x, l3_c1y, l3_c1z, l3_c2x, l3_c2y, l3_c2z, l3_c3x, l3_c3y, l3_c3z;
+    R l3_R1_2, l3_R2_2, l3_R3_2, l3_invR1, l3_invR2, l3_invR3;
+    R l3_radius2;            /* aperture */
+    R l3_iris_r2;            /* (radius * iris_radius)^2 */
+    R l3_iris1_z, l3_iris2_z;/* centre1.z - R1, centre3.z + R3 */
+    DevIfaceT<R> l3_s1, l3_s2, l3_s3; /* n1->n2, n2->n3, n3->n1 */
     /* --- image plane (reference src/optics_system.f90:48-49, src/imageMod.f90:19-58) --- */
-    double img_z;                 /* img_plane + fibre_offset */
-    double inv_binwid;            /* 401 / diameter */
-    double binwid;                /* diameter / 401 */
-    double cos_na2;               /* cos(asin(0.22))^2 */
+    R img_z;                 /* img_plane + fibre_offset */
+    R inv_binwid;            /* 401 / diameter */
+    R binwid;                /* diameter / 401 */
+    R cos_na2;               /* cos(asin(0.22))^2 */
     int32_t ellipse, scatter_b, scatter_c;
     int32_t ring_shortcut;        /* L2's flat face lies in the ring source's aim plane z = fb (true for
                                      every lens the loaders build): the aperture test reduces to
                                      u * lens_r2 > radius^2 and is taken before anything else */
 };
+typedef DevIfaceT<double> DevIface;
+typedef DevSceneT<double> DevScene;
 
 struct DevJob {
     uint64_t seed;

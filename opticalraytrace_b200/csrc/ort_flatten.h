@@ -109,6 +109,18 @@ inline void ort_flatten_scene(const ort_scene& s, const ort_job& j, DevScene& d)
                        std::fabs(d.l2_flat_z - d.l2_fb) <= 4e-16 * std::fabs(d.l2_fb)) ? 1 : 0;
 }
 
+/* fp32 variant: every hoisted scalar is computed in double above and rounded once here.
+ * DevSceneT<R> is N reals followed by 4 int32, in the same order for every R. */
+inline void ort_scene_to_float(const DevScene& s, DevSceneT<float>& d) {
+    constexpr size_t N = (sizeof(DevScene) - 4 * sizeof(int32_t)) / sizeof(double);
+    static_assert(sizeof(DevScene) == N * sizeof(double) + 4 * sizeof(int32_t), "DevScene layout");
+    static_assert(sizeof(DevSceneT<float>) == N * sizeof(float) + 4 * sizeof(int32_t), "DevSceneT<float> layout");
+    const double* sp = reinterpret_cast<const double*>(&s);
+    float* dp = reinterpret_cast<float*>(&d);
+    for (size_t i = 0; i < N; ++i) dp[i] = (float)sp[i];
+    std::memcpy(dp + N, sp + N, 4 * sizeof(int32_t));
+}
+
 inline void ort_make_dev_job(const ort_job& j, int nscenes, int64_t first, int64_t n, DevJob& d) {
     memset(&d, 0, sizeof d);
     d.seed = j.seed;

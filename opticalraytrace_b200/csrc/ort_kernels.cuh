@@ -45,12 +45,14 @@
 #endif
 
 /* structure-of-arrays ray queue private to one warp */
+template <typename R>
 struct WarpQueue {
-    double px[ORT_QCAP], py[ORT_QCAP], pz[ORT_QCAP], dx[ORT_QCAP], dy[ORT_QCAP], dz[ORT_QCAP];
+    R px[ORT_QCAP], py[ORT_QCAP], pz[ORT_QCAP], dx[ORT_QCAP], dy[ORT_QCAP], dz[ORT_QCAP];
     uint32_t id[ORT_QCAP]; /* ray index relative to DevJob.first_ray */
 };
+template <typename R>
 struct WarpShared {
-    WarpQueue q[2];
+    WarpQueue<R> q[2];
 };
 
 __device__ __forceinline__ OrtRng ort_make_rng(const DevJob& J, uint32_t local_id) {
@@ -65,7 +67,8 @@ __device__ __forceinline__ OrtRng ort_make_rng(const DevJob& J, uint32_t local_i
     return g;
 }
 
-__device__ __forceinline__ void ort_q_push(WarpQueue& q, int& n, bool alive, const OrtRay& r,
+template <typename R>
+__device__ __forceinline__ void ort_q_push(WarpQueue<R>& q, int& n, bool alive, const OrtRayT<R>& r,
                                            uint32_t id, unsigned lane) {
     unsigned m = __ballot_sync(ORT_FULL, alive);
     if (alive) {
@@ -78,7 +81,8 @@ __device__ __forceinline__ void ort_q_push(WarpQueue& q, int& n, bool alive, con
     n += __popc(m);
     __syncwarp();
 }
-__device__ __forceinline__ bool ort_q_pop(WarpQueue& q, int& n, OrtRay& r, uint32_t& id, unsigned lane) {
+template <typename R>
+__device__ __forceinline__ bool ort_q_pop(WarpQueue<R>& q, int& n, OrtRayT<R>& r, uint32_t& id, unsigned lane) {
     int cnt = n < 32 ? n : 32;
     int base = n - cnt;
     bool act = (int)lane < cnt;
@@ -126,15 +130,15 @@ __device__ __forceinline__ void ort_bin(unsigned long long* img, bool binned, in
  * B: (ring shortcut: the rest of the source, then) through L2, up to and including the aperture
  *    test on L3's first surface.
  * C: the three refractions of L3, transfer to the image plane, acceptance + binning. */
-template <int PHASE, int BOTTLE, int SRC>
-__device__ __forceinline__ int ort_stage_a(const DevScene& S, const DevJob& J, const OrtRng& g, uint32_t id,
-                                           OrtRay& r) {
+template <int PHASE, int BOTTLE, int SRC, typename R>
+__device__ __forceinline__ int ort_stage_a(const DevSceneT<R>& S, const DevJob& J, const OrtRng& g, uint32_t id,
+                                           OrtRayT<R>& r) {
     if (PHASE == ORT_PHASE_RING && SRC == ORT_SRC_POINT && S.ring_shortcut) {
-        double u2, u3;
+        R u2, u3;
         ort_draw2(g, 1, &u2, &u3);
         r.px = u2;
         r.py = u3;
-        r.pz = r.dx = r.dy = r.dz = 0.0;
+        r.pz = r.dx = r.dy = r.dz = R(0.0);
         return ort_ring_aims_outside_aperture(S, u2) ? ORT_ST_L2_APERTURE : 0;
     }
     int es = ort_emit<PHASE, SRC>(S, J, g, J.first_ray + (long long)id, r);
@@ -150,10 +154,10 @@ __device__ __forceinline__ int ort_stage_a(const DevScene& S, const DevJob& J, c
     }
     return ort_l2_enter(S, r);
 }
-template <int PHASE, int SRC>
-__device__ __forceinline__ int ort_stage_b(const DevScene& S, const DevJob& J, const OrtRng& g, OrtRay& r) {
+template <int PHASE, int SRC, typename R>
+__device__ __forceinline__ int ort_stage_b(const DevSceneT<R>& S, const DevJob& J, const OrtRng& g, OrtRayT<R>& r) {
     if (PHASE == ORT_PHASE_RING && SRC == ORT_SRC_POINT && S.ring_shortcut) {
-        double u0, u1, u2 = r.px, u3 = r.py;
+        R u0, u1, u2 = r.px, u3 = r.py;
         ort_draw2(g, 0, &u0, &u1);
         ort_source_ring_u(S, u0, u1, u2, u3, r);
         int st0 = ort_l2_enter(S, r); /* same arithmetic as the general path; cannot fail except
@@ -164,7 +168,8 @@ __device__ __forceinline__ int ort_stage_b(const DevScene& S, const DevJob& J, c
     if (st) return st;
     return ort_l3_enter(S, J.iris_before != 0, r);
 }
-__device__ __forceinline__ int ort_stage_c(const DevScene& S, const DevJob& J, const OrtRng& g, OrtRay& r,
+template <typename R>
+__device__ __forceinline__ int ort_stage_c(const DevSceneT<R>& S, const DevJob& J, const OrtRng& g, OrtRayT<R>& r,
                                            int* xp, int* yp) {
     int st = ort_l3_body(S, g, J.iris_after != 0, r);
     if (st) return st;
@@ -185,12 +190,12 @@ __device__ __forceinline__ void ort_count_a(unsigned& mine, int st, unsigned lan
     else ORT_COUNT_A(mine, st, lane);
 }
 
-template <int PHASE, int BOTTLE, int SRC>
+template <int PHASE, int BOTTLE, int SRC, typename R>
 __global__ void __launch_bounds__(ORT_TPB, ORT_MIN_BLOCKS)
-ort_trace_kernel(const __grid_constant__ DevScene S, const __grid_constant__ DevJob J,
+ort_trace_kernel(const __grid_constant__ DevSceneT<R> S, const __grid_constant__ DevJob J,
                  unsigned long long* __restrict__ img, unsigned long long* __restrict__ counters) {
     extern __shared__ __align__(16) unsigned char ort_smem[];
-    WarpShared& ws = reinterpret_cast<WarpShared*>(ort_smem)[threadIdx.x >> 5];
+    WarpShared<R>& ws = reinterpret_cast<WarpShared<R>*>(ort_smem)[threadIdx.x >> 5];
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t nwarps = gridDim.x * ORT_WPB;
     const uint32_t gwarp = blockIdx.x * ORT_WPB + (threadIdx.x >> 5);
@@ -209,7 +214,7 @@ ort_trace_kernel(const __grid_constant__ DevScene S, const __grid_constant__ Dev
         else if (n1 > 0) stage = 1;
         else break;
 
-        OrtRay r;
+        OrtRayT<R> r;
         uint32_t id = 0;
         if (stage == 0) {
             id = b * 32u + lane;
@@ -247,9 +252,9 @@ ort_trace_kernel(const __grid_constant__ DevScene S, const __grid_constant__ Dev
 /* The same path, one thread per ray from source to detector, no compaction: every early exit
  * leaves its lane idle until the slowest lane of the warp is done.  Kept to measure what the
  * compaction buys (warp execution efficiency in ncu) and as a cross-check of the megakernel. */
-template <int PHASE, int BOTTLE>
+template <int PHASE, int BOTTLE, typename R>
 __global__ void __launch_bounds__(ORT_TPB, ORT_MIN_BLOCKS)
-ort_trace_flat_kernel(const __grid_constant__ DevScene S, const __grid_constant__ DevJob J,
+ort_trace_flat_kernel(const __grid_constant__ DevSceneT<R> S, const __grid_constant__ DevJob J,
                       unsigned long long* __restrict__ img, unsigned long long* __restrict__ counters) {
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t nwarps = gridDim.x * ORT_WPB;
@@ -262,7 +267,7 @@ ort_trace_flat_kernel(const __grid_constant__ DevScene S, const __grid_constant_
         int st = -1, xp = 0, yp = 0;
         if (id < nrays) {
             OrtRng g = ort_make_rng(J, id);
-            OrtRay r;
+            OrtRayT<R> r;
             st = ort_stage_a<PHASE, BOTTLE, ORT_SRC_POINT>(S, J, g, id, r);
             if (st == 0) st = ort_stage_b<PHASE, ORT_SRC_POINT>(S, J, g, r);
             if (st == 0) st = ort_stage_c(S, J, g, r, &xp, &yp);
@@ -275,19 +280,20 @@ ort_trace_flat_kernel(const __grid_constant__ DevScene S, const __grid_constant_
 }
 
 /* Explicit ray list; SoA in/out, see ort_trace_rays in include/ort.h */
+template <typename R>
 __global__ void __launch_bounds__(ORT_TPB)
-ort_rays_kernel(const __grid_constant__ DevScene S, const __grid_constant__ DevJob J,
+ort_rays_kernel(const __grid_constant__ DevSceneT<R> S, const __grid_constant__ DevJob J,
                 const double* __restrict__ pin, const double* __restrict__ din, double* __restrict__ pout,
                 double* __restrict__ dout, int32_t* __restrict__ status, int32_t* __restrict__ bin, long long n) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     OrtRng g = ort_make_rng(J, (uint32_t)i);
-    OrtRay r;
+    OrtRayT<R> r;
     int xp = INT32_MIN, yp = INT32_MIN, x = 0, y = 0;
     const bool have_input = pin != nullptr;
-    if (have_input) {
-        r.px = pin[i]; r.py = pin[n + i]; r.pz = pin[2 * n + i];
-        r.dx = din[i]; r.dy = din[n + i]; r.dz = din[2 * n + i];
+    if (have_input) { /* the ABI stays double; the fp32 variant rounds the start state once */
+        r.px = (R)pin[i]; r.py = (R)pin[n + i]; r.pz = (R)pin[2 * n + i];
+        r.dx = (R)din[i]; r.dy = (R)din[n + i]; r.dz = (R)din[2 * n + i];
     }
     int st = ort_full_path(S, J, g, have_input, r, &x, &y);
     if (st == ORT_ST_BINNED) { xp = x; yp = y; }

@@ -166,6 +166,143 @@ ORT_HD double ort_sqrt(double x) {
 }
 
 /* -------------------------------------------------------------------------------------------
+ * fp32 variant (ort_job.precision = 32, tolerance 1e-5): the same functions on float.  MUFU.RCP
+ * and MUFU.RSQ are ~1 ulp in fp32, so no refinement is needed.
+ * ----------------------------------------------------------------------------------------- */
+ORT_HD void ort_sincospi(float x, float* s, float* c) {
+#ifdef __CUDA_ARCH__
+    sincospif(x, s, c);
+#else
+    *s = sinf((float)ORT_PI * x);
+    *c = cosf((float)ORT_PI * x);
+#endif
+}
+ORT_HD void ort_sincos(float x, float* s, float* c) {
+#ifdef __CUDA_ARCH__
+    sincosf(x, s, c);
+#else
+    *s = sinf(x);
+    *c = cosf(x);
+#endif
+}
+/* MUFU seed (~1 ulp) + one Newton step: FP32 FMAs are nearly free next to everything else and
+ * keep the variant inside its 1e-5 budget through seven surfaces */
+ORT_HD float ort_rcp(float x) {
+#ifdef __CUDA_ARCH__
+    float y = __frcp_rn(x);
+    return y;
+#else
+    return 1.0f / x;
+#endif
+}
+ORT_HD float ort_div(float a, float b) {
+#ifdef __CUDA_ARCH__
+    float y = __fdividef(1.0f, b);
+    float q = a * y;
+    return fmaf(fmaf(-b, q, a), y, q);
+#else
+    return a / b;
+#endif
+}
+ORT_HD float ort_div_z(float a, float b) { return a / b; } /* IEEE: +-inf for b == 0 */
+ORT_HD float ort_rsqrt(float x) {
+#ifdef __CUDA_ARCH__
+    float y = rsqrtf(x);
+    return fmaf(y * fmaf(-x * y, y, 1.0f), 0.5f, y);
+#else
+    return 1.0f / sqrtf(x);
+#endif
+}
+ORT_HD float ort_sqrt(float x) {
+#ifdef __CUDA_ARCH__
+    float y = rsqrtf(x), g = x * y;
+    g = fmaf(fmaf(-g, g, x), 0.5f * y, g);
+    return (x == 0.0f) ? 0.0f : g;
+#else
+    return sqrtf(x);
+#endif
+}
+
+/* sign-bit tests on the high word: integer ALU work instead of a DSETP on the FP64 pipe.  Only
+ * used where a signed zero cannot occur (differences of distinct quantities). */
+ORT_HD bool ort_signbit(double x) {
+#ifdef __CUDA_ARCH__
+    return __double2hiint(x) < 0;
+#else
+    return signbit(x);
+#endif
+}
+ORT_HD bool ort_signbit(float x) { return signbit(x); }
+ORT_HD bool ort_either_negative(double x, double y) {
+#ifdef __CUDA_ARCH__
+    return (__double2hiint(x) | __double2hiint(y)) < 0;
+#else
+    return signbit(x) || signbit(y);
+#endif
+}
+ORT_HD bool ort_either_negative(float x, float y) { return signbit(x) || signbit(y); }
+ORT_HD bool ort_is_zero(double x) { /* +0 only */
+#ifdef __CUDA_ARCH__
+    return __double_as_longlong(x) == 0ll;
+#else
+    return x == 0.0 && !signbit(x);
+#endif
+}
+ORT_HD bool ort_is_zero(float x) { return x == 0.0f && !signbit(x); }
+ORT_HD bool ort_both_zero(double x, double y) { /* +-0 */
+#ifdef __CUDA_ARCH__
+    return ((__double_as_longlong(x) | __double_as_longlong(y)) << 1) == 0ll;
+#else
+    return x == 0.0 && y == 0.0;
+#endif
+}
+ORT_HD bool ort_both_zero(float x, float y) { return x == 0.0f && y == 0.0f; }
+
+/* uncontracted arithmetic for stokes (see there) */
+ORT_HD double ort_mul_rn(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+ORT_HD double ort_add_rn(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+ORT_HD double ort_sub_rn(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dsub_rn(a, b);
+#else
+    return a - b;
+#endif
+}
+ORT_HD float ort_mul_rn(float a, float b) {
+#ifdef __CUDA_ARCH__
+    return __fmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+ORT_HD float ort_add_rn(float a, float b) {
+#ifdef __CUDA_ARCH__
+    return __fadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+ORT_HD float ort_sub_rn(float a, float b) {
+#ifdef __CUDA_ARCH__
+    return __fsub_rn(a, b);
+#else
+    return a - b;
+#endif
+}
+
+/* -------------------------------------------------------------------------------------------
  * Counter-based uniforms -- replaces the reference's ran2() (src/random_mod.f90:39-46).
  * Philox4x32-10, counter = (ray_lo, ray_hi, phase, block), key = (seed_lo, seed_hi).
  * Block b yields draw slots 2b and 2b+1; u = (64 bits >> 11) * 2^-53 in [0,1).
@@ -196,90 +333,75 @@ ORT_HD void ort_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3
     o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
 }
 
-ORT_HD double ort_bits_to_uniform(uint32_t lo, uint32_t hi) {
+/* 64 random bits -> uniform in [0,1): 53 bits for double (like gfortran's random_number); the
+ * fp32 variant takes the top 24 of the SAME bits, so both variants make the same decisions
+ * except within 2^-24 of a threshold */
+template <typename R> ORT_HD R ort_bits_to_uniform(uint32_t lo, uint32_t hi);
+template <> ORT_HD double ort_bits_to_uniform<double>(uint32_t lo, uint32_t hi) {
     uint64_t bits = (((uint64_t)hi << 32) | lo) >> 11;
     return (double)bits * (1.0 / 9007199254740992.0);
 }
+template <> ORT_HD float ort_bits_to_uniform<float>(uint32_t lo, uint32_t hi) {
+    /* the 53-bit uniform of the fp64 variant, rounded to float: full relative precision for
+     * small draws (an annulus radius is sqrt(u)); never 1.0f */
+    uint64_t bits = (((uint64_t)hi << 32) | lo) >> 11;
+    float u = (float)bits * (1.0f / 9007199254740992.0f);
+    return fminf(u, 0.99999994f);
+}
 
 /* the two uniforms of Philox block `block`: slots 2*block and 2*block+1 */
-ORT_HD void ort_draw2(const OrtRng& g, uint32_t block, double* ua, double* ub) {
+template <typename R>
+ORT_HD void ort_draw2(const OrtRng& g, uint32_t block, R* ua, R* ub) {
     if (g.override_u >= 0.0) {
-        *ua = g.override_u;
-        *ub = g.override_u;
+        *ua = (R)g.override_u;
+        *ub = (R)g.override_u;
         return;
     }
     uint32_t w[4];
     ort_philox4x32_10(g.r0, g.r1, g.phase, block, g.k0, g.k1, w);
-    *ua = ort_bits_to_uniform(w[0], w[1]);
-    *ub = ort_bits_to_uniform(w[2], w[3]);
+    *ua = ort_bits_to_uniform<R>(w[0], w[1]);
+    *ub = ort_bits_to_uniform<R>(w[2], w[3]);
 }
 
 /* sequential draws for the scatter loops (slots 16, 17, ...) */
-struct OrtScatterRng {
+template <typename R>
+struct OrtScatterRngT {
     uint32_t next; /* next slot */
-    double spare;  /* odd-slot value of the last generated block */
+    R spare;       /* odd-slot value of the last generated block */
 };
-ORT_HD double ort_scatter_draw(const OrtRng& g, OrtScatterRng& s) {
-    if (g.override_u >= 0.0) return g.override_u;
+template <typename R>
+ORT_HD R ort_scatter_draw(const OrtRng& g, OrtScatterRngT<R>& s) {
+    if (g.override_u >= 0.0) return (R)g.override_u;
     uint32_t slot = s.next++;
     if (slot & 1u) return s.spare;
-    double a, b;
+    R a, b;
     ort_draw2(g, slot >> 1, &a, &b);
     s.spare = b;
     return a;
 }
 
-struct OrtRay {
-    double px, py, pz, dx, dy, dz;
+template <typename R>
+struct OrtRayT {
+    R px, py, pz, dx, dy, dz;
 };
+typedef OrtRayT<double> OrtRay;
 
 /* -------------------------------------------------------------------------------------------
  * Quadratic root selection -- reproduces solveQuadratic + the root picking shared by the
  * reference's intersect_* (src/surfaces.f90:227-260 and :74-87).  Half-b form:
- * a t^2 + 2 h t + c = 0.  `inv_aq_needed`: a != 1 (cylinder / ellipse).
+ * a t^2 + 2 h t + c = R(0.)  `inv_aq_needed`: a != 1 (cylinder / ellipse).
  * ----------------------------------------------------------------------------------------- */
-/* sign-bit tests on the high word: integer ALU work instead of a DSETP on the FP64 pipe.  Only
- * used where a signed zero cannot occur (differences of distinct quantities). */
-ORT_HD bool ort_signbit(double x) {
-#ifdef __CUDA_ARCH__
-    return __double2hiint(x) < 0;
-#else
-    return signbit(x);
-#endif
-}
-ORT_HD bool ort_either_negative(double x, double y) {
-#ifdef __CUDA_ARCH__
-    return (__double2hiint(x) | __double2hiint(y)) < 0;
-#else
-    return signbit(x) || signbit(y);
-#endif
-}
-ORT_HD bool ort_is_zero(double x) { /* +0 only */
-#ifdef __CUDA_ARCH__
-    return __double_as_longlong(x) == 0ll;
-#else
-    return x == 0.0 && !signbit(x);
-#endif
-}
-
-ORT_HD bool ort_both_zero(double x, double y) { /* +-0 */
-#ifdef __CUDA_ARCH__
-    return ((__double_as_longlong(x) | __double_as_longlong(y)) << 1) == 0ll;
-#else
-    return x == 0.0 && y == 0.0;
-#endif
-}
-
 /* Unit normal of a sphere at a point on it: (centre - pos) / R with 1/R hoisted.  A ray that runs
  * exactly along the axis must see EXACTLY (0,0,+-1): the reference normalises by the computed
  * length, gets |N.I| == 1 bit for bit, and its fresnel() then returns 0 -- the
  * on-axis rays of create_spot and of the known-answer tests depend on it. */
-ORT_HD void ort_sphere_normal(const OrtRay& r, double cx, double cy, double cz, double invR, double* nx,
-                              double* ny, double* nz) {
-    double vx = cx - r.px, vy = cy - r.py, vz = cz - r.pz;
+template <typename R>
+ORT_HD void ort_sphere_normal(const OrtRayT<R>& r, R cx, R cy, R cz, R invR, R* nx,
+                              R* ny, R* nz) {
+    R vx = cx - r.px, vy = cy - r.py, vz = cz - r.pz;
     *nx = vx * invR;
     *ny = vy * invR;
-    *nz = ort_both_zero(vx, vy) ? copysign(1.0, vz) : vz * invR;
+    *nz = ort_both_zero(vx, vy) ? copysign(R(1.0), vz) : vz * invR;
 }
 
 /* The reference sorts the two roots, takes the smaller unless it is negative, and misses when
@@ -287,59 +409,65 @@ ORT_HD void ort_sphere_normal(const OrtRay& r, double cx, double cy, double cz, 
  * outcome is decided by the signs of h and c alone, and only ONE quotient is ever needed:
  *   h > 0 : q < 0, so q/a < 0 and c/q has the sign of -c:  c > 0 -> miss, else t = c/q
  *   h <= 0: q >= 0:  c < 0 -> c/q < 0, t = q/a ;  c >= 0 -> both >= 0 and c/q is the smaller */
-ORT_HD bool ort_pick_root_unit(double h, double c, double* t) {
+template <typename R>
+ORT_HD bool ort_pick_root_unit(R h, R c, R* t) {
     /* a == 1 (unit direction): q/a = q */
-    double disc = fma(h, h, -c);
+    R disc = fma(h, h, -c);
     if (ort_signbit(disc)) return false;
-    double s = ort_sqrt(disc);
-    bool hpos = h > 0.0;
-    if (hpos && c > 0.0) return false;
-    double q = hpos ? -(h + s) : (s - h);
-    double x1 = ort_div(c, q);
-    double tt = (!hpos && c < 0.0) ? q : x1;
-    if (q == 0.0) tt = 0.0; /* h = c = 0: the ray starts on the surface, tangent */
+    R s = ort_sqrt(disc);
+    bool hpos = h > R(0.0);
+    if (hpos && c > R(0.0)) return false;
+    R q = hpos ? -(h + s) : (s - h);
+    R x1 = ort_div(c, q);
+    R tt = (!hpos && c < R(0.0)) ? q : x1;
+    if (q == R(0.0)) tt = R(0.0); /* h = c = 0: the ray starts on the surface, tangent */
     *t = tt;
     return true;
 }
-ORT_HD bool ort_pick_root(double a, double h, double c, double* t) {
-    double disc = fma(h, h, -a * c);
+template <typename R>
+ORT_HD bool ort_pick_root(R a, R h, R c, R* t) {
+    R disc = fma(h, h, -a * c);
     if (ort_signbit(disc)) return false;
-    double s = ort_sqrt(disc);
-    bool hpos = h > 0.0;
-    if (hpos && c > 0.0) return false;
-    double q = hpos ? -(h + s) : (s - h);
-    bool use_q = !hpos && c < 0.0;
-    double tt = ort_div(use_q ? q : c, use_q ? a : q);
-    if (!(tt >= 0.0)) return false; /* a = 0 (ray along the axis) or q = 0 */
+    R s = ort_sqrt(disc);
+    bool hpos = h > R(0.0);
+    if (hpos && c > R(0.0)) return false;
+    R q = hpos ? -(h + s) : (s - h);
+    bool use_q = !hpos && c < R(0.0);
+    R tt = ort_div(use_q ? q : c, use_q ? a : q);
+    if (!(tt >= R(0.0))) return false; /* a = 0 (ray along the axis) or q = 0 */
     *t = tt;
     return true;
 }
 
 /* intersect_sphere (src/surfaces.f90:52-89) for a unit direction */
-ORT_HD bool ort_hit_sphere(const OrtRay& r, double cx, double cy, double cz, double R2, double* t) {
-    double lx = r.px - cx, ly = r.py - cy, lz = r.pz - cz;
-    double h = fma(r.dx, lx, fma(r.dy, ly, r.dz * lz));
-    double c = fma(lx, lx, fma(ly, ly, fma(lz, lz, -R2)));
+template <typename R>
+ORT_HD bool ort_hit_sphere(const OrtRayT<R>& r, R cx, R cy, R cz, R R2, R* t) {
+    R lx = r.px - cx, ly = r.py - cy, lz = r.pz - cz;
+    R h = fma(r.dx, lx, fma(r.dy, ly, r.dz * lz));
+    R c = fma(lx, lx, fma(ly, ly, fma(lz, lz, -R2)));
     return ort_pick_root_unit(h, c, t);
 }
 /* intersect_cylinder (src/surfaces.f90:91-130): axis along x, only (y,z) enter */
-ORT_HD bool ort_hit_cylinder(const OrtRay& r, double cy, double cz, double R2, double* t) {
-    double ly = r.py - cy, lz = r.pz - cz;
-    double a = fma(r.dz, r.dz, r.dy * r.dy);
-    double h = fma(r.dz, lz, r.dy * ly);
-    double c = fma(lz, lz, fma(ly, ly, -R2));
+template <typename R>
+ORT_HD bool ort_hit_cylinder(const OrtRayT<R>& r, R cy, R cz, R R2, R* t) {
+    R ly = r.py - cy, lz = r.pz - cz;
+    R a = fma(r.dz, r.dz, r.dy * r.dy);
+    R h = fma(r.dz, lz, r.dy * ly);
+    R c = fma(lz, lz, fma(ly, ly, -R2));
     return ort_pick_root(a, h, c, t);
 }
 /* intersect_ellipse (src/surfaces.f90:133-176): ia2 = 1/semia^2 (z), ib2 = 1/semib^2 (y) */
-ORT_HD bool ort_hit_ellipse(const OrtRay& r, double cy, double cz, double ia2, double ib2, double* t) {
-    double ly = r.py - cy, lz = r.pz - cz;
-    double a = fma(ia2 * r.dz, r.dz, ib2 * r.dy * r.dy);
-    double h = fma(ia2 * r.dz, lz, ib2 * r.dy * ly);
-    double c = fma(ia2 * lz, lz, fma(ib2 * ly, ly, -1.0));
+template <typename R>
+ORT_HD bool ort_hit_ellipse(const OrtRayT<R>& r, R cy, R cz, R ia2, R ib2, R* t) {
+    R ly = r.py - cy, lz = r.pz - cz;
+    R a = fma(ia2 * r.dz, r.dz, ib2 * r.dy * r.dy);
+    R h = fma(ia2 * r.dz, lz, ib2 * r.dy * ly);
+    R c = fma(ia2 * lz, lz, fma(ib2 * ly, ly, -R(1.0)));
     return ort_pick_root(a, h, c, t);
 }
 
-ORT_HD void ort_advance(OrtRay& r, double t) {
+template <typename R>
+ORT_HD void ort_advance(OrtRayT<R>& r, R t) {
     r.px = fma(r.dx, t, r.px);
     r.py = fma(r.dy, t, r.py);
     r.pz = fma(r.dz, t, r.pz);
@@ -353,34 +481,35 @@ ORT_HD void ort_advance(OrtRay& r, double t) {
  *   its NaN guard turns that into 1);  R = 0 at exactly normal incidence (cos == 1);
  *   reflect when u <= R.
  * ----------------------------------------------------------------------------------------- */
-ORT_HD bool ort_interface(OrtRay& r, double nx, double ny, double nz, const DevIface& f, double u) {
-    double c = fma(nx, r.dx, fma(ny, r.dy, nz * r.dz)); /* N . I */
-    double costt = fabs(c);
-    double s2 = fma(-costt, costt, 1.0); /* sin^2(theta_i) */
-    double ct2 = fma(-f.eta2, s2, 1.0);  /* cos^2(theta_t) = 1 - eta^2 sin^2 */
-    double cost2 = ort_sqrt(fmax(ct2, 0.0));
+template <typename R>
+ORT_HD bool ort_interface(OrtRayT<R>& r, R nx, R ny, R nz, const DevIfaceT<R>& f, R u) {
+    R c = fma(nx, r.dx, fma(ny, r.dy, nz * r.dz)); /* N . I */
+    R costt = fabs(c);
+    R s2 = fma(-costt, costt, R(1.0)); /* sin^2(theta_i) */
+    R ct2 = fma(-f.eta2, s2, R(1.0));  /* cos^2(theta_t) = 1 - eta^2 sin^2 */
+    R cost2 = ort_sqrt(fmax(ct2, R(0.0)));
     /* Fresnel amplitudes in units of nb (the ratios do not change): A/B = r_s, C/D = r_p.
      * R = (A^2 D^2 + C^2 B^2) / (2 B^2 D^2); the draw is compared without forming the quotient:
-     *   u > R  <=>  2u B^2 D^2 > A^2 D^2 + C^2 B^2.
+     *   u > R  <=>  2u B^2 D^2 > A^2 D^2 + C^2 B^R(2.)
      * 0 <= R <= 1 by construction (|A| <= B, |C| <= D); a NaN fails the comparison and reflects,
      * which is what the reference's NaN guard (R = 1) does. */
-    double ec = f.eta * costt, e2 = f.eta * cost2;
-    double A = ec - cost2, B = ec + cost2, C = e2 - costt, D = e2 + costt;
-    double B2 = B * B, D2 = D * D;
-    double num = fma(A * A, D2, (C * C) * B2);
-    double lhs = (u + u) * (B2 * D2);
+    R ec = f.eta * costt, e2 = f.eta * cost2;
+    R A = ec - cost2, B = ec + cost2, C = e2 - costt, D = e2 + costt;
+    R B2 = B * B, D2 = D * D;
+    R num = fma(A * A, D2, (C * C) * B2);
+    R lhs = (u + u) * (B2 * D2);
     bool transmit = lhs > num;
     if (ort_either_negative(ct2, s2)) transmit = false; /* TIR, or |N.I| > 1 by rounding (reference: NaN -> R = 1) */
-    else if (ort_is_zero(s2)) transmit = u > 0.0;      /* exactly normal incidence: the reference returns R = 0 */
+    else if (ort_is_zero(s2)) transmit = u > R(0.0);      /* exactly normal incidence: the reference returns R = 0 */
     if (!transmit) { /* reflect, src/surfaces.f90:285-300 */
-        double k = -2.0 * c;
+        R k = -R(2.0) * c;
         r.dx = fma(k, nx, r.dx);
         r.dy = fma(k, ny, r.dy);
         r.dz = fma(k, nz, r.dz);
         return true;
     }
     /* refract, src/surfaces.f90:303-333: T = eta I + (eta c1 - c2) N', N' opposing I */
-    double k = (c < 0.0) ? A : -A; /* eta c1 - c2 */
+    R k = (c < R(0.0)) ? A : -A; /* eta c1 - c2 */
     r.dx = fma(f.eta, r.dx, k * nx);
     r.dy = fma(f.eta, r.dy, k * ny);
     r.dz = fma(f.eta, r.dz, k * nz);
@@ -391,33 +520,40 @@ ORT_HD bool ort_interface(OrtRay& r, double nx, double ny, double nz, const DevI
  * Sources (src/sourceMod.f90)
  * ----------------------------------------------------------------------------------------- */
 /* point, src/sourceMod.f90:12-47 */
-ORT_HD void ort_source_point(const DevScene& S, const OrtRng& g, OrtRay& r) {
-    double u0, u1, sp, cp;
+template <typename R>
+ORT_HD void ort_source_point(const DevSceneT<R>& S, const OrtRng& g, OrtRayT<R>& r) {
+    R u0, u1, sp, cp;
     ort_draw2(g, 0, &u0, &u1);
-    ort_sincospi(2.0 * u0, &sp, &cp);
-    double cost = fma(u1, S.cos_theta_max, 1.0 - u1);
-    double sint = ort_sqrt(fma(-cost, cost, 1.0));
+    ort_sincospi(R(2.0) * u0, &sp, &cp);
+    R cost = fma(u1, S.cos_theta_max, R(1.0) - u1);
+    R sint;
+    if (sizeof(R) == 4) { /* fp32: 1 - cost^2 cancels for small cones; (1-cost)(1+cost) does not */
+        sint = ort_sqrt((u1 * S.one_m_ctm) * (R(1.0) + cost));
+    } else {
+        sint = ort_sqrt(fma(-cost, cost, R(1.0)));
+    }
     r.dx = sint * cp;
     r.dy = sint * sp;
     r.dz = cost;
-    r.px = 0.0;
-    r.py = 0.0;
+    r.px = R(0.0);
+    r.py = R(0.0);
     r.pz = S.point_offset;
 }
 
 /* ring, src/sourceMod.f90:250-300; (u0,u1) place the ray on the annulus, (u2,u3) pick the aim
  * point on the disc of radius L2.radius + 10 mm in the plane z = L2.fb */
-ORT_HD void ort_source_ring_u(const DevScene& S, double u0, double u1, double u2, double u3, OrtRay& r) {
-    double s, c;
-    double rr = ort_sqrt(fma(u0, S.r2_m_r1, S.r1));
-    ort_sincospi(2.0 * u1, &s, &c);
-    double px = rr * c, py = rr * s;
-    double q = S.ellipse ? py * S.ra_over_rb : py;
-    double pz = S.bcz + ort_sqrt(fma(-q, q, S.ra2));
-    double rl = ort_sqrt(u2 * S.lens_r2);
-    ort_sincospi(2.0 * u3, &s, &c);
-    double ex = fma(rl, c, -px), ey = fma(rl, s, -py), ez = S.l2_fb - pz;
-    double inv = ort_rsqrt(fma(ex, ex, fma(ey, ey, ez * ez)));
+template <typename R>
+ORT_HD void ort_source_ring_u(const DevSceneT<R>& S, R u0, R u1, R u2, R u3, OrtRayT<R>& r) {
+    R s, c;
+    R rr = ort_sqrt(fma(u0, S.r2_m_r1, S.r1));
+    ort_sincospi(R(2.0) * u1, &s, &c);
+    R px = rr * c, py = rr * s;
+    R q = S.ellipse ? py * S.ra_over_rb : py;
+    R pz = S.bcz + ort_sqrt(fma(-q, q, S.ra2));
+    R rl = ort_sqrt(u2 * S.lens_r2);
+    ort_sincospi(R(2.0) * u3, &s, &c);
+    R ex = fma(rl, c, -px), ey = fma(rl, s, -py), ez = S.l2_fb - pz;
+    R inv = ort_rsqrt(fma(ex, ex, fma(ey, ey, ez * ez)));
     r.px = px;
     r.py = py;
     r.pz = pz;
@@ -425,49 +561,57 @@ ORT_HD void ort_source_ring_u(const DevScene& S, double u0, double u1, double u2
     r.dy = ey * inv;
     r.dz = ez * inv;
 }
-ORT_HD void ort_source_ring(const DevScene& S, const OrtRng& g, OrtRay& r) {
-    double u0, u1, u2, u3;
+template <typename R>
+ORT_HD void ort_source_ring(const DevSceneT<R>& S, const OrtRng& g, OrtRayT<R>& r) {
+    R u0, u1, u2, u3;
     ort_draw2(g, 0, &u0, &u1);
     ort_draw2(g, 1, &u2, &u3);
     ort_source_ring_u(S, u0, u1, u2, u3, r);
 }
-/* When L2's flat face lies in the aim plane (DevScene.ring_shortcut) the ray meets that face AT
+/* When L2's flat face lies in the aim plane (DevSceneT<R>.ring_shortcut) the ray meets that face AT
  * its aim point, so the aperture test of src/lens.f90:450-454 is a test on u2 alone: 69 % of the
  * ring rays of the shipped geometries end here, before any position, direction, sqrt or sincos
  * has been computed. */
-ORT_HD bool ort_ring_aims_outside_aperture(const DevScene& S, double u2) {
+template <typename R>
+ORT_HD bool ort_ring_aims_outside_aperture(const DevSceneT<R>& S, R u2) {
     return u2 * S.lens_r2 > S.l2_radius2;
 }
 
 /* ---- the other sources of settings.params ---------------------------- */
 /* rang, src/random_mod.f90:59-85: polar Box-Muller; its rejection loop takes the sequential
  * draws (slots 16, 17, ...) */
-ORT_HD void ort_rang(const OrtRng& g, OrtScatterRng& sr, double sigma, double* x, double* y) {
-    double a, b, s;
+template <typename R>
+ORT_HD void ort_rang(const OrtRng& g, OrtScatterRngT<R>& sr, R sigma, R* x, R* y) {
+    R a, b, s;
     do {
-        a = fma(ort_scatter_draw(g, sr), 2.0, -1.0);
-        b = fma(ort_scatter_draw(g, sr), 2.0, -1.0);
+        a = fma(ort_scatter_draw(g, sr), R(2.0), -R(1.0));
+        b = fma(ort_scatter_draw(g, sr), R(2.0), -R(1.0));
         s = fma(b, b, a * a);
-    } while (s >= 1.0 && g.override_u < 0.0);
-    double cst = sqrt(-2.0 * log(s) / s);
+    } while (s >= R(1.0) && g.override_u < R(0.0));
+    R cst = sqrt(-R(2.0) * log(s) / s);
     *x = sigma * (a * cst);
     *y = sigma * (b * cst);
 }
 
 /* point_on_bottle, src/sourceMod.f90:50-89 (crs, ring loop): a Gaussian spot projected along -z
  * onto the cylinder of radius Ra + thickness, emitting into the cone of point() */
-ORT_HD bool ort_source_crs(const DevScene& S, const OrtRng& g, OrtRay& r) {
-    OrtScatterRng sr;
+template <typename R>
+ORT_HD bool ort_source_crs(const DevSceneT<R>& S, const OrtRng& g, OrtRayT<R>& r) {
+    OrtScatterRngT<R> sr;
     sr.next = 16;
-    sr.spare = 0.0;
+    sr.spare = R(0.0);
     ort_source_point(S, g, r); /* same two draws, same direction formulas (:65-77) */
-    double dx = r.dx, dy = r.dy, dz = r.dz, x, y, t;
+    R dx = r.dx, dy = r.dy, dz = r.dz, x, y;
     ort_rang(g, sr, S.spot_size, &x, &y);
-    OrtRay probe = {x, y, 1.0, 0.0, 0.0, -1.0};
-    if (!ort_hit_cylinder(probe, S.bcy, S.bcz, S.crs_r2, &t)) return false;
+    /* the reference drops the point from z = 1 along -z onto the cylinder of radius Ra + thickness
+     * (intersect_cylinder, first root): z = cz + sqrt(R^2 - (y - cy)^2), formed directly so that
+     * the fp32 variant does not subtract two numbers close to 1 */
+    R qy = y - S.bcy;
+    R disc = fma(-qy, qy, S.crs_r2);
+    if (disc < R(0.0)) return false;
     r.px = x;
     r.py = y;
-    r.pz = 1.0 - t;
+    r.pz = S.bcz + ort_sqrt(disc);
     r.dx = dx;
     r.dy = dy;
     r.dz = dz;
@@ -476,57 +620,60 @@ ORT_HD bool ort_source_crs(const DevScene& S, const OrtRng& g, OrtRay& r) {
 
 /* create_spot, src/sourceMod.f90:122-159 (spot, point loop): deterministic angular grid;
  * n = 1-based loop index, nrays = nphotons */
-ORT_HD void ort_source_spot(const DevScene& S, long long nrays, long long n, OrtRay& r) {
-    double nrays_sqrt = sqrt((double)nrays);
-    double dphi = ORT_TWOPI / nrays_sqrt;
-    double dtheta = acos(S.cos_theta_max) / nrays_sqrt;
-    double phi = dphi * (double)(n % 10), theta = dtheta * (double)(n / 10);
-    double sp, cp, st_, ct;
+template <typename R>
+ORT_HD void ort_source_spot(const DevSceneT<R>& S, long long nrays, long long n, OrtRayT<R>& r) {
+    R nrays_sqrt = sqrt((R)nrays);
+    R dphi = R(ORT_TWOPI) / nrays_sqrt;
+    R dtheta = acos(S.cos_theta_max) / nrays_sqrt;
+    R phi = dphi * (R)(n % 10), theta = dtheta * (R)(n / 10);
+    R sp, cp, st_, ct;
     ort_sincos(phi, &sp, &cp);
     ort_sincos(theta, &st_, &ct);
-    double sint = sqrt(fma(-ct, ct, 1.0));
+    R sint = sqrt(fma(-ct, ct, R(1.0)));
     r.dx = sint * cp;
     r.dy = sint * sp;
     r.dz = ct;
-    r.px = r.py = r.pz = 0.0;
+    r.px = r.py = r.pz = R(0.0);
 }
 
 /* intersect_cone, src/surfaces.f90:179-224, for the axicon of iSORS */
-ORT_HD bool ort_hit_cone(const OrtRay& r, double k, double height, double* t) {
-    double lz = r.pz - height;
-    double a = fma(r.dx, r.dx, fma(r.dy, r.dy, -k * r.dz * r.dz));
-    double h = fma(r.dx, r.px, fma(r.dy, r.py, -k * r.dz * lz));
-    double c = fma(r.px, r.px, fma(r.py, r.py, -k * lz * lz));
+template <typename R>
+ORT_HD bool ort_hit_cone(const OrtRayT<R>& r, R k, R height, R* t) {
+    R lz = r.pz - height;
+    R a = fma(r.dx, r.dx, fma(r.dy, r.dy, -k * r.dz * r.dz));
+    R h = fma(r.dx, r.px, fma(r.dy, r.py, -k * r.dz * lz));
+    R c = fma(r.px, r.px, fma(r.py, r.py, -k * lz * lz));
     /* a < 0 here (steep ray), so the sign logic of ort_pick_root does not apply: both roots */
-    double disc = fma(h, h, -a * c);
-    if (disc < 0.0) return false;
-    double s = sqrt(disc);
-    double q = (h > 0.0) ? -(h + s) : (s - h);
-    double x0 = (disc == 0.0) ? -h / a : q / a, x1 = (disc == 0.0) ? x0 : c / q;
-    double t0 = fmin(x0, x1), t1 = fmax(x0, x1);
-    double tt = (t0 < 0.0) ? t1 : t0;
-    if (tt < 0.0) return false;
+    R disc = fma(h, h, -a * c);
+    if (disc < R(0.0)) return false;
+    R s = sqrt(disc);
+    R q = (h > R(0.0)) ? -(h + s) : (s - h);
+    R x0 = (disc == R(0.0)) ? -h / a : q / a, x1 = (disc == R(0.0)) ? x0 : c / q;
+    R t0 = fmin(x0, x1), t1 = fmax(x0, x1);
+    R tt = (t0 < R(0.0)) ? t1 : t0;
+    if (tt < R(0.0)) return false;
     *t = tt;
     return true;
 }
 
 /* iSORS(ring = .true.), src/sourceMod.f90:162-247 (isors, ring loop).  false = the reference's
- * `error stop "no intersection with bottle!"` (every ray the axicon face reflects, ~2.8 %). */
-ORT_HD bool ort_source_isors(const DevScene& S, const OrtRng& g, OrtRay& r) {
-    OrtScatterRng sr;
+ * `error stop "no intersection with bottle!"` (every ray the axicon face reflects, ~R(2.8) %). */
+template <typename R>
+ORT_HD bool ort_source_isors(const DevSceneT<R>& S, const OrtRng& g, OrtRayT<R>& r) {
+    OrtScatterRngT<R> sr;
     sr.next = 16;
-    sr.spare = 0.0;
-    double x, y, t, u_r, u_th, u_ax, unused;
+    sr.spare = R(0.0);
+    R x, y, t, u_r, u_th, u_ax, unused;
     ort_rang(g, sr, S.isors_beam, &x, &y);
-    r.px = x; r.py = y; r.pz = 2.0 * S.isors_h;
-    r.dx = 0.0; r.dy = 0.0; r.dz = -1.0;
+    r.px = x; r.py = y; r.pz = R(2.0) * S.isors_h;
+    r.dx = R(0.0); r.dy = R(0.0); r.dz = -R(1.0);
     ort_draw2(g, 0, &u_r, &u_th);
     ort_draw2(g, 1, &u_ax, &unused);
     if (ort_hit_cone(r, S.isors_k, S.isors_h, &t)) {
         ort_advance(r, t);
         /* gradient of the cone, inverted (upper nappe), normalised */
-        double nx = -(2.0 * r.px / S.isors_k), ny = -(2.0 * r.py / S.isors_k), nz = -(-2.0 * r.pz + 2.0 * S.isors_h);
-        double inv = 1.0 / sqrt(fma(nx, nx, fma(ny, ny, nz * nz)));
+        R nx = -(R(2.0) * r.px / S.isors_k), ny = -(R(2.0) * r.py / S.isors_k), nz = -(-R(2.0) * r.pz + R(2.0) * S.isors_h);
+        R inv = R(1.0) / sqrt(fma(nx, nx, fma(ny, ny, nz * nz)));
         (void)ort_interface(r, nx * inv, ny * inv, nz * inv, S.isors_axicon, u_ax); /* flag ignored */
         ort_advance(r, S.isors_base / r.dz);
         r.pz = S.isors_z;
@@ -535,10 +682,10 @@ ORT_HD bool ort_source_isors(const DevScene& S, const OrtRng& g, OrtRay& r) {
         if (!hit) return false;
         ort_advance(r, t);
     }
-    double rl = sqrt(u_r * S.isors_lens_r2), s, c;
-    ort_sincospi(2.0 * u_th, &s, &c);
-    double ex = fma(rl, c, -r.px), ey = fma(rl, s, -r.py), ez = S.l2_fb - r.pz;
-    double inv = 1.0 / sqrt(fma(ex, ex, fma(ey, ey, ez * ez)));
+    R rl = sqrt(u_r * S.isors_lens_r2), s, c;
+    ort_sincospi(R(2.0) * u_th, &s, &c);
+    R ex = fma(rl, c, -r.px), ey = fma(rl, s, -r.py), ez = S.l2_fb - r.pz;
+    R inv = R(1.0) / sqrt(fma(ex, ex, fma(ey, ey, ez * ez)));
     r.dx = ex * inv;
     r.dy = ey * inv;
     r.dz = ez * inv;
@@ -547,8 +694,8 @@ ORT_HD bool ort_source_isors(const DevScene& S, const OrtRng& g, OrtRay& r) {
 
 /* source dispatch of src/main.f90:95-101 (ring loop) and :132-142 (point loop); SRC is
  * ort_job.source_kind.  Returns 0 or ORT_ST_SOURCE_MISS. */
-template <int PHASE, int SRC>
-ORT_HD int ort_emit(const DevScene& S, const DevJob& J, const OrtRng& g, long long ray, OrtRay& r) {
+template <int PHASE, int SRC, typename R>
+ORT_HD int ort_emit(const DevSceneT<R>& S, const DevJob& J, const OrtRng& g, long long ray, OrtRayT<R>& r) {
     if (PHASE == ORT_PHASE_RING) {
         if (SRC == ORT_SRC_CRS) return ort_source_crs(S, g, r) ? 0 : ORT_ST_SOURCE_MISS;
         if (SRC == ORT_SRC_ISORS) return ort_source_isors(S, g, r) ? 0 : ORT_ST_SOURCE_MISS;
@@ -564,10 +711,11 @@ ORT_HD int ort_emit(const DevScene& S, const DevJob& J, const OrtRng& g, long lo
  * Scatter: tauint (src/surfaces.f90:13-50) and stokes (src/stokes.f90:7-166)
  * ----------------------------------------------------------------------------------------- */
 /* returns false where the reference would `error stop "no intersection"` */
-ORT_HD bool ort_tauint(const OrtRay& r, double mutot, double inv_mutot, double cy, double cz,
-                       double R2, double u, double* dist, bool* tflag) {
-    double tau = -log(u);
-    double d;
+template <typename R>
+ORT_HD bool ort_tauint(const OrtRayT<R>& r, R mutot, R inv_mutot, R cy, R cz,
+                       R R2, R u, R* dist, bool* tflag) {
+    R tau = -log(u);
+    R d;
     if (!ort_hit_cylinder(r, cy, cz, R2, &d)) return false;
     if (tau < d * mutot) {
         *dist = tau * inv_mutot;
@@ -583,78 +731,71 @@ ORT_HD bool ort_tauint(const OrtRay& r, double mutot, double inv_mutot, double c
  * difference of nearly equal quotients), so here -- and only here -- the arithmetic keeps the
  * reference's operation order and is protected from FMA contraction (ORT_MUL / ORT_ADD): any
  * other rounding is amplified by up to ~1/sin^2 of the deflection angle. */
-#ifdef __CUDA_ARCH__
-#define ORT_MUL(a, b) __dmul_rn((a), (b))
-#define ORT_ADD(a, b) __dadd_rn((a), (b))
-#define ORT_SUB(a, b) __dsub_rn((a), (b))
-#else
-#define ORT_MUL(a, b) ((a) * (b))
-#define ORT_ADD(a, b) ((a) + (b))
-#define ORT_SUB(a, b) ((a) - (b))
-#endif
-ORT_HD void ort_stokes(OrtRay& r, double hgg, const OrtRng& g, OrtScatterRng& sr) {
-    double cost = r.dz;
-    double sint = sqrt(ORT_SUB(1.0, ORT_MUL(cost, cost)));
-    double phi = atan2(r.dy, r.dx);
-    double sinp, cosp;
-    if (hgg == 0.0) { /* isotropic, src/stokes.f90:33-48 */
-        cost = ORT_SUB(ORT_MUL(2.0, ort_scatter_draw(g, sr)), 1.0);
-        sint = ORT_SUB(1.0, ORT_MUL(cost, cost));
-        sint = (sint <= 0.0) ? 0.0 : sqrt(sint);
-        ort_sincos(ORT_MUL(ORT_TWOPI, ort_scatter_draw(g, sr)), &sinp, &cosp);
+template <typename R>
+ORT_HD void ort_stokes(OrtRayT<R>& r, R hgg, const OrtRng& g, OrtScatterRngT<R>& sr) {
+    R cost = r.dz;
+    R sint = sqrt(ort_sub_rn(R(1.0), ort_mul_rn(cost, cost)));
+    R phi = atan2(r.dy, r.dx);
+    R sinp, cosp;
+    if (hgg == R(0.0)) { /* isotropic, src/stokes.f90:33-48 */
+        cost = ort_sub_rn(ort_mul_rn(R(2.0), ort_scatter_draw(g, sr)), R(1.0));
+        sint = ort_sub_rn(R(1.0), ort_mul_rn(cost, cost));
+        sint = (sint <= R(0.0)) ? R(0.0) : sqrt(sint);
+        ort_sincos(ort_mul_rn(R(ORT_TWOPI), ort_scatter_draw(g, sr)), &sinp, &cosp);
     } else { /* Henyey-Greenstein, src/stokes.f90:54-158 */
-        double g2 = ORT_MUL(hgg, hgg);
-        double costp = cost, sintp = sint;
-        double den = ORT_ADD(ORT_SUB(1.0, hgg), ORT_MUL(ORT_MUL(2.0, hgg), ort_scatter_draw(g, sr)));
-        double tq = ORT_SUB(1.0, g2) / den;
-        double bmu = ORT_SUB(ORT_ADD(1.0, g2), ORT_MUL(tq, tq)) / ORT_MUL(2.0, hgg);
-        double cosb2 = ORT_MUL(bmu, bmu);
-        if (fabs(bmu) > 1.0) {
-            bmu = (bmu > 1.0) ? 1.0 : -1.0;
-            cosb2 = 1.0;
+        R g2 = ort_mul_rn(hgg, hgg);
+        R costp = cost, sintp = sint;
+        R den = ort_add_rn(ort_sub_rn(R(1.0), hgg), ort_mul_rn(ort_mul_rn(R(2.0), hgg), ort_scatter_draw(g, sr)));
+        R tq = ort_sub_rn(R(1.0), g2) / den;
+        R bmu = ort_sub_rn(ort_add_rn(R(1.0), g2), ort_mul_rn(tq, tq)) / ort_mul_rn(R(2.0), hgg);
+        R cosb2 = ort_mul_rn(bmu, bmu);
+        if (fabs(bmu) > R(1.0)) {
+            bmu = (bmu > R(1.0)) ? R(1.0) : -R(1.0);
+            cosb2 = R(1.0);
         }
-        double sinbt = sqrt(ORT_SUB(1.0, cosb2));
-        double ri1 = ORT_MUL(ORT_TWOPI, ort_scatter_draw(g, sr));
+        R sinbt = sqrt(ort_sub_rn(R(1.0), cosb2));
+        R ri1 = ort_mul_rn(R(ORT_TWOPI), ort_scatter_draw(g, sr));
         /* the reference's two branches (ri1 > pi uses ri3 = 2pi - ri1 and adds acos; otherwise
          * subtracts) differ only in the sign applied to acos(cosdph) */
-        bool upper = ri1 > ORT_PI;
-        double ang = upper ? ORT_SUB(ORT_TWOPI, ri1) : ri1;
-        double sini, cosi;
+        bool upper = ri1 > R(ORT_PI);
+        R ang = upper ? ort_sub_rn(R(ORT_TWOPI), ri1) : ri1;
+        R sini, cosi;
         ort_sincos(ang, &sini, &cosi);
-        if (bmu == 1.0 || bmu == -1.0) return; /* goto 100: direction unchanged */
-        cost = ORT_ADD(ORT_MUL(costp, bmu), ORT_MUL(ORT_MUL(sintp, sinbt), cosi));
-        double sini2, cosi2 = 0.0;
-        if (fabs(cost) < 1.0) {
-            sint = fabs(sqrt(ORT_SUB(1.0, ORT_MUL(cost, cost))));
-            sini2 = ORT_MUL(sini, sintp) / sint;
-            double bott = ORT_MUL(sint, sinbt);
-            cosi2 = ORT_SUB(costp / bott, ORT_MUL(cost, bmu) / bott);
+        if (bmu == R(1.0) || bmu == -R(1.0)) return; /* goto 100: direction unchanged */
+        cost = ort_add_rn(ort_mul_rn(costp, bmu), ort_mul_rn(ort_mul_rn(sintp, sinbt), cosi));
+        R sini2, cosi2 = R(0.0);
+        if (fabs(cost) < R(1.0)) {
+            sint = fabs(sqrt(ort_sub_rn(R(1.0), ort_mul_rn(cost, cost))));
+            sini2 = ort_mul_rn(sini, sintp) / sint;
+            R bott = ort_mul_rn(sint, sinbt);
+            cosi2 = ort_sub_rn(costp / bott, ort_mul_rn(cost, bmu) / bott);
         } else {
-            sint = 0.0;
-            sini2 = 0.0;
-            if (cost >= 1.0) cosi2 = -1.0;
-            if (cost <= -1.0) cosi2 = 1.0;
+            sint = R(0.0);
+            sini2 = R(0.0);
+            if (cost >= R(1.0)) cosi2 = -R(1.0);
+            if (cost <= -R(1.0)) cosi2 = R(1.0);
         }
-        double cosdph = ORT_ADD(-ORT_MUL(cosi2, cosi), ORT_MUL(ORT_MUL(sini2, sini), bmu));
-        if (fabs(cosdph) > 1.0) cosdph = (cosdph > 1.0) ? 1.0 : -1.0;
-        double dph = acos(cosdph);
-        phi = upper ? ORT_ADD(phi, dph) : ORT_SUB(phi, dph);
-        if (phi > ORT_TWOPI) phi = ORT_SUB(phi, ORT_TWOPI);
-        if (phi < 0.0) phi = ORT_ADD(phi, ORT_TWOPI);
+        R cosdph = ort_add_rn(-ort_mul_rn(cosi2, cosi), ort_mul_rn(ort_mul_rn(sini2, sini), bmu));
+        if (fabs(cosdph) > R(1.0)) cosdph = (cosdph > R(1.0)) ? R(1.0) : -R(1.0);
+        R dph = acos(cosdph);
+        phi = upper ? ort_add_rn(phi, dph) : ort_sub_rn(phi, dph);
+        if (phi > R(ORT_TWOPI)) phi = ort_sub_rn(phi, R(ORT_TWOPI));
+        if (phi < R(0.0)) phi = ort_add_rn(phi, R(ORT_TWOPI));
         ort_sincos(phi, &sinp, &cosp);
     }
-    r.dx = ORT_MUL(sint, cosp);
-    r.dy = ORT_MUL(sint, sinp);
+    r.dx = ort_mul_rn(sint, cosp);
+    r.dy = ort_mul_rn(sint, sinp);
     r.dz = cost;
 }
 
 /* -------------------------------------------------------------------------------------------
- * glass_bottle%forward, src/lens.f90:230-350.  Returns 0 or the ort_status that ended the ray.
+ * glass_bottle%forward, src/lens.f90:230-R(350.)  Returns 0 or the ort_status that ended the ray.
  * ----------------------------------------------------------------------------------------- */
 /* one scatter loop (contents :262-282, wall :312-333); *t is the step still to be taken */
-ORT_HD int ort_scatter_loop(const DevScene& S, const OrtRng& g, OrtScatterRng& sr, OrtRay& r,
-                            double mutot, double inv_mutot, double albedo, double hgg, double Rlim,
-                            double Rlim2, int st_absorbed, int st_backward, double* t) {
+template <typename R>
+ORT_HD int ort_scatter_loop(const DevSceneT<R>& S, const OrtRng& g, OrtScatterRngT<R>& sr, OrtRayT<R>& r,
+                            R mutot, R inv_mutot, R albedo, R hgg, R Rlim,
+                            R Rlim2, int st_absorbed, int st_backward, R* t) {
     bool flag;
     if (!ort_tauint(r, mutot, inv_mutot, S.bcy, S.bcz, Rlim2, ort_scatter_draw(g, sr), t, &flag))
         return ORT_ST_TAUINT_MISS;
@@ -670,48 +811,48 @@ ORT_HD int ort_scatter_loop(const DevScene& S, const OrtRng& g, OrtScatterRng& s
         /* the reference's exit test uses (x,z) although the axis is x */
         if (sqrt(fma(r.px, r.px, r.pz * r.pz)) >= Rlim) break;
     }
-    if (r.dz < 0.0) return st_backward;
+    if (r.dz < R(0.0)) return st_backward;
     return 0;
 }
 
-template <bool SCATTER>
-ORT_HD int ort_bottle_forward(const DevScene& S, const OrtRng& g, OrtRay& r) {
-    double t, u_in, u_out;
-    OrtScatterRng sr;
+template <bool SCATTER, typename R>
+ORT_HD int ort_bottle_forward(const DevSceneT<R>& S, const OrtRng& g, OrtRayT<R>& r) {
+    R t, u_in, u_out;
+    OrtScatterRngT<R> sr;
     sr.next = 16;
-    sr.spare = 0.0;
+    sr.spare = R(0.0);
     bool hit = S.ellipse ? ort_hit_ellipse(r, S.bcy, S.bcz, S.b_in_ia2, S.b_in_ib2, &t)
                          : ort_hit_cylinder(r, S.bcy, S.bcz, S.b_in_r2, &t);
     if (!hit) return ORT_ST_BOTTLE_INNER_MISS;
     if (SCATTER && S.scatter_c) {
-        int st = ort_scatter_loop(S, g, sr, r, S.mutot_c, S.inv_mutot_c, S.albedo_c, 0.65, S.b_in_r,
+        int st = ort_scatter_loop(S, g, sr, r, S.mutot_c, S.inv_mutot_c, S.albedo_c, R(0.65), S.b_in_r,
                                   S.b_in_r2, ORT_ST_CONTENTS_ABSORBED, ORT_ST_CONTENTS_BACKWARD, &t);
         if (st) return st;
     }
     ort_advance(r, t);
     ort_draw2(g, 1, &u_in, &u_out);
     {   /* radial normal in the (y,z) plane, also for the ellipse (src/lens.f90:288-290) */
-        double ny = S.bcy - r.py, nz = S.bcz - r.pz;
+        R ny = S.bcy - r.py, nz = S.bcz - r.pz;
         /* on a clear cylindrical wall the hit point is on the cylinder: |(ny,nz)| = radius.  After
          * a scatter loop (quirk 4) or on an ellipse it is not, and the length is computed. */
-        double inv = (SCATTER || S.ellipse) ? ort_rsqrt(fma(ny, ny, nz * nz)) : S.b_in_invr;
-        double nzu = ort_both_zero(ny, 0.0) ? copysign(1.0, nz) : nz * inv; /* on-axis ray: exactly +-1 */
-        if (ort_interface(r, 0.0, ny * inv, nzu, S.b_in, u_in)) return ORT_ST_BOTTLE_INNER_REFLECT;
+        R inv = (SCATTER || S.ellipse) ? ort_rsqrt(fma(ny, ny, nz * nz)) : S.b_in_invr;
+        R nzu = ort_both_zero(ny, R(0.0)) ? copysign(R(1.0), nz) : nz * inv; /* on-axis ray: exactly +-1 */
+        if (ort_interface(r, R(0.0), ny * inv, nzu, S.b_in, u_in)) return ORT_ST_BOTTLE_INNER_REFLECT;
     }
     hit = S.ellipse ? ort_hit_ellipse(r, S.bcy, S.bcz, S.b_out_ia2, S.b_out_ib2, &t)
                     : ort_hit_cylinder(r, S.bcy, S.bcz, S.b_out_r2, &t);
     if (!hit) return ORT_ST_BOTTLE_OUTER_MISS;
     if (SCATTER && S.scatter_b) {
-        int st = ort_scatter_loop(S, g, sr, r, S.mutot_b, S.inv_mutot_b, S.albedo_b, 0.9, S.b_out_r,
+        int st = ort_scatter_loop(S, g, sr, r, S.mutot_b, S.inv_mutot_b, S.albedo_b, R(0.9), S.b_out_r,
                                   S.b_out_r2, ORT_ST_WALL_ABSORBED, ORT_ST_WALL_BACKWARD, &t);
         if (st) return st;
     }
     ort_advance(r, t);
     {
-        double ny = S.bcy - r.py, nz = S.bcz - r.pz;
-        double inv = (SCATTER || S.ellipse) ? ort_rsqrt(fma(ny, ny, nz * nz)) : S.b_out_invr;
-        double nzu = ort_both_zero(ny, 0.0) ? copysign(1.0, nz) : nz * inv;
-        if (ort_interface(r, 0.0, ny * inv, nzu, S.b_out, u_out)) return ORT_ST_BOTTLE_OUTER_REFLECT;
+        R ny = S.bcy - r.py, nz = S.bcz - r.pz;
+        R inv = (SCATTER || S.ellipse) ? ort_rsqrt(fma(ny, ny, nz * nz)) : S.b_out_invr;
+        R nzu = ort_both_zero(ny, R(0.0)) ? copysign(R(1.0), nz) : nz * inv;
+        if (ort_interface(r, R(0.0), ny * inv, nzu, S.b_out, u_out)) return ORT_ST_BOTTLE_OUTER_REFLECT;
     }
     return 0;
 }
@@ -719,20 +860,22 @@ ORT_HD int ort_bottle_forward(const DevScene& S, const OrtRng& g, OrtRay& r) {
 /* -------------------------------------------------------------------------------------------
  * plano_convex%forward, src/lens.f90:425-481, split at the aperture test
  * ----------------------------------------------------------------------------------------- */
-ORT_HD int ort_l2_enter(const DevScene& S, OrtRay& r) { /* :447-454 */
-    double d = ort_div_z(S.l2_flat_z - r.pz, r.dz);
+template <typename R>
+ORT_HD int ort_l2_enter(const DevSceneT<R>& S, OrtRayT<R>& r) { /* :447-454 */
+    R d = ort_div_z(S.l2_flat_z - r.pz, r.dz);
     ort_advance(r, d);
     if (fma(r.px, r.px, r.py * r.py) > S.l2_radius2) return ORT_ST_L2_APERTURE;
     return 0;
 }
-ORT_HD int ort_l2_body(const DevScene& S, const OrtRng& g, OrtRay& r) { /* :458-479 */
-    double u_flat, u_curved, t;
+template <typename R>
+ORT_HD int ort_l2_body(const DevSceneT<R>& S, const OrtRng& g, OrtRayT<R>& r) { /* :458-479 */
+    R u_flat, u_curved, t;
     ort_draw2(g, 2, &u_flat, &u_curved);
     /* a reflection at the flat face is computed but never tested */
     (void)ort_interface(r, S.l2_fnx, S.l2_fny, S.l2_fnz, S.l2_in, u_flat);
     if (!ort_hit_sphere(r, S.l2_cx, S.l2_cy, S.l2_cz, S.l2_R2, &t)) return ORT_ST_L2_SPHERE_MISS;
     ort_advance(r, t);
-    double nx, ny, nz;
+    R nx, ny, nz;
     ort_sphere_normal(r, S.l2_cx, S.l2_cy, S.l2_cz, S.l2_invR, &nx, &ny, &nz);
     if (ort_interface(r, nx, ny, nz, S.l2_out, u_curved)) return ORT_ST_L2_CURVED_REFLECT;
     return 0;
@@ -741,11 +884,12 @@ ORT_HD int ort_l2_body(const DevScene& S, const OrtRng& g, OrtRay& r) { /* :458-
 /* -------------------------------------------------------------------------------------------
  * achromatic_doublet%forward, src/lens.f90:531-645, split after the first-surface aperture test
  * ----------------------------------------------------------------------------------------- */
-ORT_HD int ort_l3_enter(const DevScene& S, bool iris_before, OrtRay& r) { /* :551-580 */
-    double t;
+template <typename R>
+ORT_HD int ort_l3_enter(const DevSceneT<R>& S, bool iris_before, OrtRayT<R>& r) { /* :551-580 */
+    R t;
     if (iris_before) {
         t = ort_div_z(S.l3_iris1_z - r.pz, r.dz);
-        double x = fma(r.dx, t, r.px), y = fma(r.dy, t, r.py);
+        R x = fma(r.dx, t, r.px), y = fma(r.dy, t, r.py);
         if (fma(x, x, y * y) > S.l3_iris_r2) { /* the reference leaves pos on the iris plane */
             r.px = x; r.py = y; r.pz = fma(r.dz, t, r.pz);
             return ORT_ST_L3_IRIS_BEFORE;
@@ -756,8 +900,9 @@ ORT_HD int ort_l3_enter(const DevScene& S, bool iris_before, OrtRay& r) { /* :55
     if (fma(r.px, r.px, r.py * r.py) > S.l3_radius2) return ORT_ST_L3_APERTURE;
     return 0;
 }
-ORT_HD int ort_l3_body(const DevScene& S, const OrtRng& g, bool iris_after, OrtRay& r) { /* :582-644 */
-    double u1, u2, u3, unused, t, nx, ny, nz;
+template <typename R>
+ORT_HD int ort_l3_body(const DevSceneT<R>& S, const OrtRng& g, bool iris_after, OrtRayT<R>& r) { /* :582-644 */
+    R u1, u2, u3, unused, t, nx, ny, nz;
     ort_draw2(g, 3, &u1, &u2);
     ort_sphere_normal(r, S.l3_c1x, S.l3_c1y, S.l3_c1z, S.l3_invR1, &nx, &ny, &nz);
     if (ort_interface(r, nx, ny, nz, S.l3_s1, u1)) return ORT_ST_L3_S1_REFLECT;
@@ -773,7 +918,7 @@ ORT_HD int ort_l3_body(const DevScene& S, const OrtRng& g, bool iris_after, OrtR
     if (ort_interface(r, nx, ny, nz, S.l3_s3, u3)) return ORT_ST_L3_S3_REFLECT;
     if (iris_after) {
         t = ort_div_z(S.l3_iris2_z - r.pz, r.dz);
-        double x = fma(r.dx, t, r.px), y = fma(r.dy, t, r.py);
+        R x = fma(r.dx, t, r.px), y = fma(r.dy, t, r.py);
         if (fma(x, x, y * y) > S.l3_iris_r2) {
             r.px = x; r.py = y; r.pz = fma(r.dz, t, r.pz);
             return ORT_ST_L3_IRIS_AFTER;
@@ -786,16 +931,17 @@ ORT_HD int ort_l3_body(const DevScene& S, const OrtRng& g, bool iris_after, OrtR
  * transfer to the image plane (src/optics_system.f90:48-49) + makeImage2D
  * (src/imageMod.f90:19-58).  Returns the status; *bin = (yp+200)*401 + (xp+200) when binned.
  * ----------------------------------------------------------------------------------------- */
-ORT_HD int ort_image(const DevScene& S, OrtRay& r, int* xp, int* yp) {
-    double d = ort_div_z(S.img_z - r.pz, r.dz);
+template <typename R>
+ORT_HD int ort_image(const DevSceneT<R>& S, OrtRayT<R>& r, int* xp, int* yp) {
+    R d = ort_div_z(S.img_z - r.pz, r.dz);
     ort_advance(r, d);
-    /* angle = acos(dz/|d|) > asin(0.22)  <=>  dz < cos_na |d|;  a NaN angle passes (reference) */
-    double dd = fma(r.dx, r.dx, fma(r.dy, r.dy, r.dz * r.dz));
-    if (r.dz <= 0.0 || r.dz * r.dz < S.cos_na2 * dd) return ORT_ST_NA_REJECT;
-    if (r.px > 1000.0 || r.py > 1000.0) return ORT_ST_FAR;
-    double fx = floor(r.px * S.inv_binwid), fy = floor(r.py * S.inv_binwid);
-    if (!(fabs(fx) < 2.0e9) || !(fabs(fy) < 2.0e9)) return ORT_ST_FAR;
-    if (fabs(fx) > 200.0 || fabs(fy) > 200.0) return ORT_ST_OFF_DETECTOR;
+    /* angle = acos(dz/|d|) > asin(R(0.22))  <=>  dz < cos_na |d|;  a NaN angle passes (reference) */
+    R dd = fma(r.dx, r.dx, fma(r.dy, r.dy, r.dz * r.dz));
+    if (r.dz <= R(0.0) || r.dz * r.dz < S.cos_na2 * dd) return ORT_ST_NA_REJECT;
+    if (r.px > R(1000.0) || r.py > R(1000.0)) return ORT_ST_FAR;
+    R fx = floor(r.px * S.inv_binwid), fy = floor(r.py * S.inv_binwid);
+    if (!(fabs(fx) < R(2.0e9)) || !(fabs(fy) < R(2.0e9))) return ORT_ST_FAR;
+    if (fabs(fx) > R(200.0) || fabs(fy) > R(200.0)) return ORT_ST_OFF_DETECTOR;
     *xp = (int)fx;
     *yp = (int)fy;
     return ORT_ST_BINNED;
@@ -806,7 +952,8 @@ ORT_HD int ort_image(const DevScene& S, OrtRay& r, int* xp, int* yp) {
  * :127-162 incl. telescope, src/optics_system.f90:6-52), with the explicit-ray conveniences of
  * ort_trace_rays: optional caller-supplied start state and ort_job.stop_after.
  * ----------------------------------------------------------------------------------------- */
-ORT_HD int ort_full_path(const DevScene& S, const DevJob& J, const OrtRng& g, bool have_input, OrtRay& r,
+template <typename R>
+ORT_HD int ort_full_path(const DevSceneT<R>& S, const DevJob& J, const OrtRng& g, bool have_input, OrtRayT<R>& r,
                          int* xp, int* yp) {
     const int stop = J.stop_after;
     int st;

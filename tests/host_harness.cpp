@@ -13,12 +13,9 @@
 #include "../opticalraytrace_b200/csrc/ort_flatten.h"
 #include "../opticalraytrace_b200/csrc/ort_optics.cuh"
 
-extern "C" int hh_trace_rays(const ort_job* job, const ort_scene* scene, int64_t n, const double* pin,
-                             const double* din, double* pout, double* dout, int32_t* status, int32_t* bin) {
-    DevScene S;
-    DevJob J;
-    ort_flatten_scene(*scene, *job, S);
-    ort_make_dev_job(*job, 1, job->first_ray, n, J);
+template <typename R>
+static void run_rays(const DevSceneT<R>& S, const DevJob& J, int64_t n, const double* pin, const double* din,
+                     double* pout, double* dout, int32_t* status, int32_t* bin) {
     const bool have = pin != nullptr;
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < n; ++i) {
@@ -28,10 +25,10 @@ extern "C" int hh_trace_rays(const ort_job* job, const ort_scene* scene, int64_t
         g.r0 = (uint32_t)ray; g.r1 = (uint32_t)(ray >> 32);
         g.phase = (uint32_t)J.phase;
         g.override_u = J.uniform_override;
-        OrtRay r = {0, 0, 0, 0, 0, 1};
+        OrtRayT<R> r = {0, 0, 0, 0, 0, 1};
         if (have) {
-            r.px = pin[i]; r.py = pin[n + i]; r.pz = pin[2 * n + i];
-            r.dx = din[i]; r.dy = din[n + i]; r.dz = din[2 * n + i];
+            r.px = (R)pin[i]; r.py = (R)pin[n + i]; r.pz = (R)pin[2 * n + i];
+            r.dx = (R)din[i]; r.dy = (R)din[n + i]; r.dz = (R)din[2 * n + i];
         }
         int x = 0, y = 0;
         int st = ort_full_path(S, J, g, have, r, &x, &y);
@@ -40,6 +37,21 @@ extern "C" int hh_trace_rays(const ort_job* job, const ort_scene* scene, int64_t
         status[i] = st;
         bin[i] = st == ORT_ST_BINNED ? x : INT32_MIN;
         bin[n + i] = st == ORT_ST_BINNED ? y : INT32_MIN;
+    }
+}
+
+extern "C" int hh_trace_rays(const ort_job* job, const ort_scene* scene, int64_t n, const double* pin,
+                             const double* din, double* pout, double* dout, int32_t* status, int32_t* bin) {
+    DevScene S;
+    DevJob J;
+    ort_flatten_scene(*scene, *job, S);
+    ort_make_dev_job(*job, 1, job->first_ray, n, J);
+    if (job->precision == 32) {
+        DevSceneT<float> Sf;
+        ort_scene_to_float(S, Sf);
+        run_rays<float>(Sf, J, n, pin, din, pout, dout, status, bin);
+    } else {
+        run_rays<double>(S, J, n, pin, din, pout, dout, status, bin);
     }
     return 0;
 }
