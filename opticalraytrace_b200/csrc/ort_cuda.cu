@@ -366,6 +366,10 @@ extern "C" int ort_trace(const ort_job* job, const ort_scene* scenes, int nscene
     }
     int rc = validate_job(job);
     if (rc) return rc;
+    if (job->uniform_override >= 0.0) {
+        ort_set_error("ort_trace: uniform_override is a known-answer-test device of ort_trace_rays only");
+        return ORT_EINVAL;
+    }
     if (!scenes || nscenes < 1 || nscenes > ORT_MAX_SCENES) {
         ort_set_error("ort_trace: nscenes must be 1..%d", ORT_MAX_SCENES);
         return ORT_EINVAL;

@@ -66,6 +66,13 @@ __device__ __forceinline__ OrtRng ort_make_rng(const DevJob& J, uint32_t local_i
     g.override_u = J.uniform_override;
     return g;
 }
+/* the trace kernels never use the test-only constant draw (ort_trace rejects it), so its
+ * branches fold away */
+__device__ __forceinline__ OrtRng ort_make_rng_prod(const DevJob& J, uint32_t local_id) {
+    OrtRng g = ort_make_rng(J, local_id);
+    g.override_u = -1.0;
+    return g;
+}
 
 template <typename R>
 __device__ __forceinline__ void ort_q_push(WarpQueue<R>& q, int& n, bool alive, const OrtRayT<R>& r,
@@ -98,19 +105,36 @@ __device__ __forceinline__ bool ort_q_pop(WarpQueue<R>& q, int& n, OrtRayT<R>& r
     return act;
 }
 
-/* Histogram of final ray statuses, kept in registers: lane s of the warp owns the counter of
- * status s.  A stage can only end a ray with a handful of statuses known at compile time, so
- * the update is one ballot + popc per candidate (no atomics, no match.any, no shared memory). */
+/* Histogram of final ray statuses.  Every warp keeps one counter per status it can produce, as
+ * plain (warp-uniform) registers: a stage adds popc(ballot(status == k)) -- vote, popc, add -- for
+ * the few statuses that end most of its rays; the rest share one cold path behind an any().  No
+ * atomics, no match.any, no shared memory; the counters reach memory once, at the end of the
+ * launch (lane k adds counter k). */
+struct OrtCounts {
+    unsigned c[ORT_NSTATUS];
+};
 template <int K>
-__device__ __forceinline__ void ort_count_one(unsigned& mine, int st, unsigned lane) {
-    unsigned c = __popc(__ballot_sync(ORT_FULL, st == K));
-    if (lane == (unsigned)K) mine += c;
+__device__ __forceinline__ void ort_count_one(OrtCounts& cnt, int st) {
+    cnt.c[K] += __popc(__ballot_sync(ORT_FULL, st == K));
 }
 template <int... KS>
-__device__ __forceinline__ void ort_count(unsigned& mine, int st, unsigned lane) {
-    if (__any_sync(ORT_FULL, st >= 0)) {
-        (ort_count_one<KS>(mine, st, lane), ...);
+__device__ __forceinline__ void ort_count(OrtCounts& cnt, int st) {
+    (ort_count_one<KS>(cnt, st), ...);
+}
+/* statuses outside the common list of a stage: cold */
+template <int... KS>
+__device__ __forceinline__ void ort_count_rare(OrtCounts& cnt, int st, bool is_rare) {
+    if (__any_sync(ORT_FULL, is_rare)) {
+        (ort_count_one<KS>(cnt, st), ...);
     }
+}
+__device__ __forceinline__ void ort_counts_flush(const OrtCounts& cnt, unsigned lane,
+                                                 unsigned long long* __restrict__ counters) {
+    unsigned mine = 0;
+#pragma unroll
+    for (int k = 0; k < ORT_NSTATUS; ++k)
+        if (lane == (unsigned)k) mine = cnt.c[k];
+    if (mine) atomicAdd(counters + lane, (unsigned long long)mine);
 }
 
 /* detector increment, reference src/imageMod.f90:55 (`!$omp atomic`): lanes that hit the same
@@ -176,18 +200,25 @@ __device__ __forceinline__ int ort_stage_c(const DevSceneT<R>& S, const DevJob& 
     return ort_image(S, r, xp, yp);
 }
 
-/* statuses a ray can end with, per stage */
-#define ORT_COUNT_A(mine, st, lane) ort_count<1, 2, 3, 4, 5, 6, 7, 8, 9, 24>(mine, st, lane)
-#define ORT_COUNT_A_RING(mine, st, lane) ort_count<9, 26>(mine, st, lane)
-#define ORT_COUNT_A_CLEAR(mine, st, lane) ort_count<1, 4, 5, 8, 9>(mine, st, lane)
-#define ORT_COUNT_B(mine, st, lane) ort_count<9, 10, 11, 12, 13, 14>(mine, st, lane)
-#define ORT_COUNT_C(mine, st, lane) ort_count<0, 15, 16, 17, 18, 19, 20, 21, 22, 23>(mine, st, lane)
-
-template <int PHASE, int BOTTLE>
-__device__ __forceinline__ void ort_count_a(unsigned& mine, int st, unsigned lane) {
-    if (PHASE == ORT_PHASE_RING || BOTTLE == 0) ORT_COUNT_A_RING(mine, st, lane);
-    else if (BOTTLE == 1) ORT_COUNT_A_CLEAR(mine, st, lane);
-    else ORT_COUNT_A(mine, st, lane);
+/* statuses a ray can end with, per stage: the common ones are counted unconditionally, the rest
+ * behind one any() */
+template <int PHASE, int BOTTLE, int SRC>
+__device__ __forceinline__ void ort_count_a(OrtCounts& cnt, int st) {
+    if (PHASE == ORT_PHASE_RING || BOTTLE == 0) {
+        ort_count<ORT_ST_L2_APERTURE>(cnt, st);
+        if (SRC != ORT_SRC_POINT) ort_count_rare<ORT_ST_SOURCE_MISS>(cnt, st, st == ORT_ST_SOURCE_MISS);
+    } else {
+        ort_count<ORT_ST_BOTTLE_INNER_REFLECT, ORT_ST_BOTTLE_OUTER_REFLECT, ORT_ST_L2_APERTURE>(cnt, st);
+        ort_count_rare<1, 2, 3, 5, 6, 7, 24>(cnt, st, st > 0 && st != 4 && st != 8 && st != 9);
+    }
+}
+__device__ __forceinline__ void ort_count_b(OrtCounts& cnt, int st) {
+    ort_count<ORT_ST_L2_CURVED_REFLECT, ORT_ST_L3_S1_MISS, ORT_ST_L3_APERTURE>(cnt, st);
+    ort_count_rare<ORT_ST_L2_APERTURE, ORT_ST_L2_SPHERE_MISS, ORT_ST_L3_IRIS_BEFORE>(cnt, st, st == 9 || st == 10 || st == 12);
+}
+__device__ __forceinline__ void ort_count_c(OrtCounts& cnt, int st) {
+    ort_count<ORT_ST_BINNED, ORT_ST_L3_S1_REFLECT, ORT_ST_L3_S3_REFLECT, ORT_ST_NA_REJECT>(cnt, st);
+    ort_count_rare<16, 17, 18, 20, 22, 23>(cnt, st, st == 16 || st == 17 || st == 18 || st == 20 || st >= 22);
 }
 
 template <int PHASE, int BOTTLE, int SRC, typename R>
@@ -202,7 +233,9 @@ ort_trace_kernel(const __grid_constant__ DevSceneT<R> S, const __grid_constant__
     const uint32_t nrays = (uint32_t)J.nrays;
     const uint32_t nbatches = (nrays + 31u) >> 5;
 
-    unsigned mine = 0; /* count of rays that ended with status == lane */
+    OrtCounts cnt;
+#pragma unroll
+    for (int k = 0; k < ORT_NSTATUS; ++k) cnt.c[k] = 0;
     int n1 = 0, n2 = 0;
     uint32_t b = gwarp;
     for (;;) {
@@ -221,32 +254,32 @@ ort_trace_kernel(const __grid_constant__ DevSceneT<R> S, const __grid_constant__
             b += nwarps;
             int st = -1;
             if (id < nrays) {
-                OrtRng g = ort_make_rng(J, id);
+                OrtRng g = ort_make_rng_prod(J, id);
                 st = ort_stage_a<PHASE, BOTTLE, SRC>(S, J, g, id, r);
             }
             ort_q_push(ws.q[0], n1, st == 0, r, id, lane);
-            ort_count_a<PHASE, BOTTLE>(mine, st == 0 ? -1 : st, lane);
+            ort_count_a<PHASE, BOTTLE, SRC>(cnt, st);
         } else if (stage == 1) {
             bool act = ort_q_pop(ws.q[0], n1, r, id, lane);
             int st = -1;
             if (act) {
-                OrtRng g = ort_make_rng(J, id);
+                OrtRng g = ort_make_rng_prod(J, id);
                 st = ort_stage_b<PHASE, SRC>(S, J, g, r);
             }
             ort_q_push(ws.q[1], n2, st == 0, r, id, lane);
-            ORT_COUNT_B(mine, st == 0 ? -1 : st, lane);
+            ort_count_b(cnt, st);
         } else {
             bool act = ort_q_pop(ws.q[1], n2, r, id, lane);
             int st = -1, xp = 0, yp = 0;
             if (act) {
-                OrtRng g = ort_make_rng(J, id);
+                OrtRng g = ort_make_rng_prod(J, id);
                 st = ort_stage_c(S, J, g, r, &xp, &yp);
             }
             ort_bin(img, st == ORT_ST_BINNED, xp, yp, lane);
-            ORT_COUNT_C(mine, st, lane);
+            ort_count_c(cnt, st);
         }
     }
-    if (mine) atomicAdd(counters + lane, (unsigned long long)mine);
+    ort_counts_flush(cnt, lane, counters);
 }
 
 /* The same path, one thread per ray from source to detector, no compaction: every early exit
@@ -261,22 +294,23 @@ ort_trace_flat_kernel(const __grid_constant__ DevSceneT<R> S, const __grid_const
     const uint32_t gwarp = blockIdx.x * ORT_WPB + (threadIdx.x >> 5);
     const uint32_t nrays = (uint32_t)J.nrays;
     const uint32_t nbatches = (nrays + 31u) >> 5;
-    unsigned mine = 0;
+    OrtCounts cnt;
+#pragma unroll
+    for (int k = 0; k < ORT_NSTATUS; ++k) cnt.c[k] = 0;
     for (uint32_t b = gwarp; b < nbatches; b += nwarps) {
         uint32_t id = b * 32u + lane;
         int st = -1, xp = 0, yp = 0;
         if (id < nrays) {
-            OrtRng g = ort_make_rng(J, id);
+            OrtRng g = ort_make_rng_prod(J, id);
             OrtRayT<R> r;
             st = ort_stage_a<PHASE, BOTTLE, ORT_SRC_POINT>(S, J, g, id, r);
             if (st == 0) st = ort_stage_b<PHASE, ORT_SRC_POINT>(S, J, g, r);
             if (st == 0) st = ort_stage_c(S, J, g, r, &xp, &yp);
         }
         ort_bin(img, st == ORT_ST_BINNED, xp, yp, lane);
-        ort_count<0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24>(
-            mine, st, lane);
+        ort_count<0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24>(cnt, st);
     }
-    if (mine) atomicAdd(counters + lane, (unsigned long long)mine);
+    ort_counts_flush(cnt, lane, counters);
 }
 
 /* Explicit ray list; SoA in/out, see ort_trace_rays in include/ort.h */

@@ -146,6 +146,22 @@ ORT_HD double ort_rsqrt(double x) {
 #endif
 }
 /* Goldschmidt: g -> sqrt(x), h -> 1/(2 sqrt(x)) */
+ORT_HD double ort_sqrt_nz(double x) { /* x > 0: no zero guard (0 would give NaN) */
+#ifdef __CUDA_ARCH__
+    double y = ort_mufu_rsq(x);
+    double g = x * y, h = 0.5 * y;
+#pragma unroll
+    for (int i = 0; i < ORT_NR - 1; ++i) {
+        double r = fma(-g, h, 0.5);
+        g = fma(g, r, g);
+        h = fma(h, r, h);
+    }
+    double d = fma(-g, g, x);
+    return fma(d, h, g);
+#else
+    return sqrt(x);
+#endif
+}
 ORT_HD double ort_sqrt(double x) {
 #ifdef __CUDA_ARCH__
     /* one Goldschmidt step, then the Newton correction of the root (also quadratic) */
@@ -211,6 +227,14 @@ ORT_HD float ort_rsqrt(float x) {
     return fmaf(y * fmaf(-x * y, y, 1.0f), 0.5f, y);
 #else
     return 1.0f / sqrtf(x);
+#endif
+}
+ORT_HD float ort_sqrt_nz(float x) { /* x > 0 */
+#ifdef __CUDA_ARCH__
+    float y = rsqrtf(x), g = x * y;
+    return fmaf(fmaf(-g, g, x), 0.5f * y, g);
+#else
+    return sqrtf(x);
 #endif
 }
 ORT_HD float ort_sqrt(float x) {
@@ -487,7 +511,7 @@ ORT_HD bool ort_interface(OrtRayT<R>& r, R nx, R ny, R nz, const DevIfaceT<R>& f
     R costt = fabs(c);
     R s2 = fma(-costt, costt, R(1.0)); /* sin^2(theta_i) */
     R ct2 = fma(-f.eta2, s2, R(1.0));  /* cos^2(theta_t) = 1 - eta^2 sin^2 */
-    R cost2 = ort_sqrt(fmax(ct2, R(0.0)));
+    R cost2 = ort_sqrt_nz(ct2); /* NaN under total internal reflection, where it is not used */
     /* Fresnel amplitudes in units of nb (the ratios do not change): A/B = r_s, C/D = r_p.
      * R = (A^2 D^2 + C^2 B^2) / (2 B^2 D^2); the draw is compared without forming the quotient:
      *   u > R  <=>  2u B^2 D^2 > A^2 D^2 + C^2 B^R(2.)
@@ -938,10 +962,12 @@ ORT_HD int ort_image(const DevSceneT<R>& S, OrtRayT<R>& r, int* xp, int* yp) {
     /* angle = acos(dz/|d|) > asin(R(0.22))  <=>  dz < cos_na |d|;  a NaN angle passes (reference) */
     R dd = fma(r.dx, r.dx, fma(r.dy, r.dy, r.dz * r.dz));
     if (r.dz <= R(0.0) || r.dz * r.dz < S.cos_na2 * dd) return ORT_ST_NA_REJECT;
-    if (r.px > R(1000.0) || r.py > R(1000.0)) return ORT_ST_FAR;
     R fx = floor(r.px * S.inv_binwid), fy = floor(r.py * S.inv_binwid);
-    if (!(fabs(fx) < R(2.0e9)) || !(fabs(fy) < R(2.0e9))) return ORT_ST_FAR;
-    if (fabs(fx) > R(200.0) || fabs(fy) > R(200.0)) return ORT_ST_OFF_DETECTOR;
+    if (!(fmax(fabs(fx), fabs(fy)) <= R(200.0))) { /* off the detector, far away, or not finite */
+        if (r.px > R(1000.0) || r.py > R(1000.0)) return ORT_ST_FAR;
+        if (!(fabs(fx) < R(2.0e9)) || !(fabs(fy) < R(2.0e9))) return ORT_ST_FAR;
+        return ORT_ST_OFF_DETECTOR;
+    }
     *xp = (int)fx;
     *yp = (int)fy;
     return ORT_ST_BINNED;
