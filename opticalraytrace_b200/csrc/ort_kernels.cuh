@@ -74,21 +74,25 @@ __device__ __forceinline__ OrtRng ort_make_rng_prod(const DevJob& J, uint32_t lo
     return g;
 }
 
-template <typename R>
+/* SLIM: the entry carries only (px, py) -- the ring loop's stage 0 hands on two uniforms */
+template <bool SLIM = false, typename R>
 __device__ __forceinline__ void ort_q_push(WarpQueue<R>& q, int& n, bool alive, const OrtRayT<R>& r,
                                            uint32_t id, unsigned lane) {
     unsigned m = __ballot_sync(ORT_FULL, alive);
     if (alive) {
         int p = n + __popc(m & ((1u << lane) - 1u));
         ORT_ASSERT(p >= 0 && p < ORT_QCAP);
-        q.px[p] = r.px; q.py[p] = r.py; q.pz[p] = r.pz;
-        q.dx[p] = r.dx; q.dy[p] = r.dy; q.dz[p] = r.dz;
+        q.px[p] = r.px; q.py[p] = r.py;
+        if (!SLIM) {
+            q.pz[p] = r.pz;
+            q.dx[p] = r.dx; q.dy[p] = r.dy; q.dz[p] = r.dz;
+        }
         q.id[p] = id;
     }
     n += __popc(m);
     __syncwarp();
 }
-template <typename R>
+template <bool SLIM = false, typename R>
 __device__ __forceinline__ bool ort_q_pop(WarpQueue<R>& q, int& n, OrtRayT<R>& r, uint32_t& id, unsigned lane) {
     int cnt = n < 32 ? n : 32;
     int base = n - cnt;
@@ -96,8 +100,11 @@ __device__ __forceinline__ bool ort_q_pop(WarpQueue<R>& q, int& n, OrtRayT<R>& r
     if (act) {
         int p = base + lane;
         ORT_ASSERT(p >= 0 && p < ORT_QCAP);
-        r.px = q.px[p]; r.py = q.py[p]; r.pz = q.pz[p];
-        r.dx = q.dx[p]; r.dy = q.dy[p]; r.dz = q.dz[p];
+        r.px = q.px[p]; r.py = q.py[p];
+        if (!SLIM) {
+            r.pz = q.pz[p];
+            r.dx = q.dx[p]; r.dy = q.dy[p]; r.dz = q.dz[p];
+        }
         id = q.id[p];
     }
     n = base;
@@ -238,6 +245,8 @@ ort_trace_kernel(const __grid_constant__ DevSceneT<R> S, const __grid_constant__
     for (int k = 0; k < ORT_NSTATUS; ++k) cnt.c[k] = 0;
     int n1 = 0, n2 = 0;
     uint32_t b = gwarp;
+    /* ring loop with the aim-plane shortcut: stage 0 hands on only (u2, u3) */
+    const bool slim = PHASE == ORT_PHASE_RING && SRC == ORT_SRC_POINT && S.ring_shortcut;
     for (;;) {
         int stage;
         if (n2 >= 32) stage = 2;
@@ -257,10 +266,11 @@ ort_trace_kernel(const __grid_constant__ DevSceneT<R> S, const __grid_constant__
                 OrtRng g = ort_make_rng_prod(J, id);
                 st = ort_stage_a<PHASE, BOTTLE, SRC>(S, J, g, id, r);
             }
-            ort_q_push(ws.q[0], n1, st == 0, r, id, lane);
+            if (slim) ort_q_push<true>(ws.q[0], n1, st == 0, r, id, lane);
+            else ort_q_push(ws.q[0], n1, st == 0, r, id, lane);
             ort_count_a<PHASE, BOTTLE, SRC>(cnt, st);
         } else if (stage == 1) {
-            bool act = ort_q_pop(ws.q[0], n1, r, id, lane);
+            bool act = slim ? ort_q_pop<true>(ws.q[0], n1, r, id, lane) : ort_q_pop(ws.q[0], n1, r, id, lane);
             int st = -1;
             if (act) {
                 OrtRng g = ort_make_rng_prod(J, id);

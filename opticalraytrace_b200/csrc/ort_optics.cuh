@@ -41,9 +41,39 @@
 /* -------------------------------------------------------------------------------------------
  * small wrappers over device intrinsics (host versions only serve the test harness)
  * ----------------------------------------------------------------------------------------- */
+/* sin(pi x), cos(pi x) for x in [0, 2) -- all the sources ever ask for (x = 2u).  The library
+ * sincospi spends ~75 instructions on arbitrary arguments; here: q = nearest half-integer count,
+ * r = x - q/2 in [-1/4, 1/4] (exact), Taylor polynomials of sin(pi r), cos(pi r) in r^2
+ * (truncation < 5e-17), quadrant fix-up.  <= 2 ulp, like the library. */
 ORT_HD void ort_sincospi(double x, double* s, double* c) {
 #ifdef __CUDA_ARCH__
-    sincospi(x, s, c);
+    const double q = rint(x + x);
+    const double r = fma(q, -0.5, x);
+    const double t = r * r;
+    double ps = 7.95205400147551261e-07;
+    ps = fma(ps, t, -2.19153534478302173e-05);
+    ps = fma(ps, t, 4.66302805767612554e-04);
+    ps = fma(ps, t, -7.37043094571435044e-03);
+    ps = fma(ps, t, 8.21458866111282326e-02);
+    ps = fma(ps, t, -5.99264529320792105e-01);
+    ps = fma(ps, t, 2.55016403987734552e+00);
+    ps = fma(ps, t, -5.16771278004997026e+00);
+    ps = fma(ps, t, 3.14159265358979312e+00);
+    ps *= r;
+    double pc = -1.38789524622137714e-07;
+    pc = fma(pc, t, 4.30306958703294729e-06);
+    pc = fma(pc, t, -1.04638104924845705e-04);
+    pc = fma(pc, t, 1.92957430940392314e-03);
+    pc = fma(pc, t, -2.58068913900140612e-02);
+    pc = fma(pc, t, 2.35330630358893206e-01);
+    pc = fma(pc, t, -1.33526276885458950e+00);
+    pc = fma(pc, t, 4.05871212641676848e+00);
+    pc = fma(pc, t, -4.93480220054467900e+00);
+    pc = fma(pc, t, 1.0);
+    const int k = (int)q; /* 0..4 */
+    const double a = (k & 1) ? pc : ps, b = (k & 1) ? ps : pc; /* odd quadrant: swap */
+    *s = (k & 2) ? -a : a;
+    *c = ((k + 1) & 2) ? -b : b;
 #else
     *s = sin(ORT_PI * x);
     *c = cos(ORT_PI * x);
