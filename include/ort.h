@@ -64,11 +64,14 @@ extern "C" {
  *   CRS           point_on_bottle()  :50                   point()
  *   ISORS         iSORS(ring=.true.) :162                  point(offset = bottle centre z)
  *   SPOT          ring()                                   create_spot()      :122
- *   (image: emit_image() in the point loop -- not on the B200 path yet) */
+ *   IMAGE         ring()                                   emit_image()       :303 (needs
+ *                                                          ort_set_image_source first) */
 #define ORT_SRC_POINT 0
 #define ORT_SRC_CRS 1
 #define ORT_SRC_ISORS 2
 #define ORT_SRC_SPOT 3
+#define ORT_SRC_IMAGE 4
+#define ORT_SRCIMG_N 512 /* the image source is 512 x 512, src/sourceMod.f90:372 */
 
 /* ort_job.stop_after (explicit-ray entry point only): where pos_out/dir_out are sampled */
 #define ORT_STOP_NONE 0   /* full path, sampled at the image plane */
@@ -246,6 +249,19 @@ int ort_trace_rays(const ort_job* job, const ort_scene* scene, int64_t n, const 
  * only the blank lines, rays lost in the bottle their source and bottle positions plus six.
  * nrays <= 10000 like the reference (src/setupMod.f90:75). */
 int ort_write_tracks(const ort_job* job, const ort_scene* scene, const char* path);
+
+/* Image source (source_type "image", reference src/sourceMod.f90:303-408).
+ * ort_load_image_source = init_emit_image (:363-408): reads the 512x512 fp64 intensity file
+ * bpm.py writes, and turns it into a per-pixel ray budget for `nphotons` rays (fractional parts
+ * rounded up with probability = fraction; the draws come from the counter-based generator,
+ * stream 3).  budget[(j-1)*512 + (i-1)] = imgin(i,j), the Fortran memory order, which is also
+ * the order emit_image scans (:313-321).
+ * ort_set_image_source hands a budget to the library (copied to every device); the point loop of
+ * a job with source_kind = ORT_SRC_IMAGE then emits ray k from the pixel the reference's scan
+ * would have reached after k rays.  Rays beyond the total budget end with ORT_ST_SOURCE_MISS
+ * (the reference re-uses stale state for them). */
+int ort_load_image_source(const char* path, int64_t nphotons, uint64_t seed, int32_t* budget);
+int ort_set_image_source(const int32_t* budget);
 
 /* The uniforms a ray sees: out[i] = uniform of slot `first_slot+i` (testing the generator). */
 int ort_uniforms(uint64_t seed, int32_t phase, int64_t ray, int32_t first_slot, int32_t n,

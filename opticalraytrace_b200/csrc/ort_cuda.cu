@@ -109,12 +109,14 @@ struct DeviceCtx {
     unsigned long long* d_buf = nullptr; /* [nscenes*BINS image][nscenes*NSTATUS counters] */
     size_t d_elems = 0;
     ncclComm_t comm = nullptr;
+    long long* d_image_cdf = nullptr; /* image source: prefix sums of the ray budget */
 };
 struct LibState {
     bool ready = false;
     bool rank_mode = false;
     int rank = 0, nranks = 1;
     std::vector<DeviceCtx> devs;
+    std::vector<long long> image_cdf; /* host copy, re-uploaded when devices are (re)opened */
     unsigned long long* h_pinned = nullptr;
     size_t h_elems = 0;
 };
@@ -146,13 +148,17 @@ extern "C" int ort_finalize(void) {
         cudaSetDevice(c.dev);
         if (c.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c.comm);
         if (c.d_buf) cudaFree(c.d_buf);
+        if (c.d_image_cdf) cudaFree(c.d_image_cdf);
         if (c.ev_start) cudaEventDestroy(c.ev_start);
         if (c.ev_traced) cudaEventDestroy(c.ev_traced);
         if (c.ev_reduced) cudaEventDestroy(c.ev_reduced);
         if (c.stream) cudaStreamDestroy(c.stream);
     }
     if (g.h_pinned) cudaFreeHost(g.h_pinned);
+    std::vector<long long> keep;
+    keep.swap(g.image_cdf); /* the image source outlives re-initialisation */
     g = LibState();
+    g.image_cdf.swap(keep);
     return ORT_OK;
 }
 
@@ -252,7 +258,7 @@ static int validate_job(const ort_job* job) {
         ort_set_error("image_diameter must be > 0");
         return ORT_EINVAL;
     }
-    if (job->source_kind < ORT_SRC_POINT || job->source_kind > ORT_SRC_SPOT) {
+    if (job->source_kind < ORT_SRC_POINT || job->source_kind > ORT_SRC_IMAGE) {
         ort_set_error("job.source_kind %d unknown", job->source_kind);
         return ORT_EINVAL;
     }
@@ -266,6 +272,39 @@ static int validate_job(const ort_job* job) {
 /* ------------------------------------------------------------------------------------------
  * kernel dispatch
  * ---------------------------------------------------------------------------------------- */
+/* image source: the host keeps the prefix sums; each device gets a copy on first use */
+static int ensure_image_source(DeviceCtx& c) {
+    if (g.image_cdf.empty()) {
+        ort_set_error("source_kind = image needs ort_set_image_source() first");
+        return ORT_EINVAL;
+    }
+    if (c.d_image_cdf) return ORT_OK;
+    CK(cudaSetDevice(c.dev));
+    CK(cudaMalloc(&c.d_image_cdf, g.image_cdf.size() * sizeof(long long)));
+    CK(cudaMemcpy(c.d_image_cdf, g.image_cdf.data(), g.image_cdf.size() * sizeof(long long), cudaMemcpyHostToDevice));
+    return ORT_OK;
+}
+
+extern "C" int ort_set_image_source(const int32_t* budget) {
+    for (auto& c : g.devs) {
+        if (c.d_image_cdf) {
+            cudaSetDevice(c.dev);
+            cudaFree(c.d_image_cdf);
+            c.d_image_cdf = nullptr;
+        }
+    }
+    g.image_cdf.clear();
+    if (!budget) return ORT_OK;
+    const size_t n = (size_t)ORT_SRCIMG_N * ORT_SRCIMG_N;
+    g.image_cdf.resize(n);
+    long long acc = 0;
+    for (size_t k = 0; k < n; ++k) {
+        acc += budget[k] > 0 ? budget[k] : 0;
+        g.image_cdf[k] = acc;
+    }
+    return ORT_OK;
+}
+
 /* ------------------------------------------------------------------------------------------
  * kernel dispatch: <loop, bottle kind, source kind, real type>
  * ---------------------------------------------------------------------------------------- */
@@ -286,6 +325,13 @@ struct Kernels {
                 case ORT_SRC_CRS: return ort_trace_kernel<ORT_PHASE_RING, 0, ORT_SRC_CRS, R>;
                 case ORT_SRC_ISORS: return ort_trace_kernel<ORT_PHASE_RING, 0, ORT_SRC_ISORS, R>;
                 default: return ort_trace_kernel<ORT_PHASE_RING, 0, ORT_SRC_POINT, R>; /* point, spot: ring() */
+            }
+        }
+        if (src == ORT_SRC_IMAGE) {
+            switch (bottle_mode) {
+                case 0: return ort_trace_kernel<ORT_PHASE_POINT, 0, ORT_SRC_IMAGE, R>;
+                case 1: return ort_trace_kernel<ORT_PHASE_POINT, 1, ORT_SRC_IMAGE, R>;
+                default: return ort_trace_kernel<ORT_PHASE_POINT, 2, ORT_SRC_IMAGE, R>;
             }
         }
         const bool spot = src == ORT_SRC_SPOT; /* crs, isors: point() in the point loop */
@@ -339,6 +385,7 @@ static int enqueue_trace_t(DeviceCtx& c, const ort_job& job, const std::vector<D
             int64_t m = n - off < ORT_CHUNK ? n - off : ORT_CHUNK;
             DevJob dj;
             ort_make_dev_job(job, nscenes, first + off, m, dj);
+            dj.image_cdf = c.d_image_cdf;
             int64_t batches = (m + 31) / 32;
             int64_t want = (batches + ORT_WPB - 1) / ORT_WPB;
             int gsz = (int)(want < grid ? (want > 0 ? want : 1) : grid);
@@ -378,6 +425,12 @@ extern "C" int ort_trace(const ort_job* job, const ort_scene* scenes, int nscene
     for (int i = 0; i < nscenes; ++i) ort_flatten_scene(scenes[i], *job, ds[i]);
 
     const int G = (int)g.devs.size();
+    if (job->source_kind == ORT_SRC_IMAGE && job->phase == ORT_PHASE_POINT) {
+        for (int d = 0; d < G; ++d) {
+            rc = ensure_image_source(g.devs[d]);
+            if (rc) return rc;
+        }
+    }
     const size_t elems = (size_t)nscenes * (ORT_IMG_BINS + ORT_NSTATUS);
     int64_t launches = 0;
     /* contiguous ray-index ranges per device; uniforms depend only on the ray
@@ -487,6 +540,11 @@ extern "C" int ort_trace_rays(const ort_job* job, const ort_scene* scene, int64_
     ort_flatten_scene(*scene, *job, ds);
     DevJob dj;
     ort_make_dev_job(*job, 1, job->first_ray, n, dj);
+    if (job->source_kind == ORT_SRC_IMAGE && job->phase == ORT_PHASE_POINT && !pos_in) {
+        rc = ensure_image_source(c);
+        if (rc) return rc;
+    }
+    dj.image_cdf = c.d_image_cdf;
     double *d_in = nullptr, *d_out = nullptr;
     int32_t* d_int = nullptr;
     size_t vb = (size_t)3 * n * sizeof(double);

@@ -88,6 +88,8 @@ struct DevJob {
     int32_t phase, use_bottle, iris_before, iris_after;
     int32_t nscenes, stop_after, flags, source_kind;
     int64_t total_rays;  /* nphotons of the whole job (create_spot) */
+    const long long* image_cdf; /* image source: inclusive prefix sums of the 512x512 ray budget in
+                                   emit_image's scan order (device memory), or NULL */
 };
 
 #endif

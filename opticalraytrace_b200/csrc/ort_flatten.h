@@ -136,6 +136,7 @@ inline void ort_make_dev_job(const ort_job& j, int nscenes, int64_t first, int64
     d.flags = j.flags;
     d.source_kind = j.source_kind;
     d.total_rays = j.total_rays > 0 ? j.total_rays : j.nrays;
+    d.image_cdf = nullptr; /* the launcher fills in its device copy */
 }
 
 

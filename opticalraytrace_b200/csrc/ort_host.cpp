@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "ort_internal.h"
+#include "ort_optics.cuh" /* host build of the counter-based generator (init_emit_image's draws) */
 
 namespace {
 
@@ -381,11 +382,49 @@ int ort_job_from_settings(const ort_settings* st, int32_t phase, ort_job* out) {
     if (std::strcmp(st->source_type, "crs") == 0) out->source_kind = ORT_SRC_CRS;
     else if (std::strcmp(st->source_type, "isors") == 0) out->source_kind = ORT_SRC_ISORS;
     else if (std::strcmp(st->source_type, "spot") == 0) out->source_kind = ORT_SRC_SPOT;
-    else out->source_kind = ORT_SRC_POINT; /* "image": not on this path, callers must check */
+    else if (std::strcmp(st->source_type, "image") == 0) out->source_kind = ORT_SRC_IMAGE;
+    else out->source_kind = ORT_SRC_POINT;
     out->total_rays = st->nphotons;
     out->seed = 123456789ull; /* src/main.f90:79 */
     out->first_ray = 0;
     out->nrays = st->nphotons;
+    return ORT_OK;
+}
+
+/* init_emit_image, src/sourceMod.f90:363-408 */
+int ort_load_image_source(const char* path, int64_t nphotons, uint64_t seed, int32_t* budget) {
+    if (!path || !budget || nphotons < 0) return ORT_EINVAL;
+    const int N = ORT_SRCIMG_N;
+    std::vector<double> f((size_t)N * N);
+    FILE* fh = std::fopen(path, "rb");
+    if (!fh) {
+        ort_set_error("cannot open image source %s", path);
+        return ORT_EIO;
+    }
+    size_t got = std::fread(f.data(), sizeof(double), f.size(), fh);
+    std::fclose(fh);
+    if (got != f.size()) {
+        ort_set_error("%s: expected %d x %d float64 values", path, N, N);
+        return ORT_EPARSE;
+    }
+    /* the file is read column-major and transposed: imgout(i,j) = f[(i-1)*N + (j-1)];
+     * sum() walks the transposed array in its memory order (j outer, i inner) */
+    double tot = 0.0;
+    for (int j = 0; j < N; ++j)
+        for (int i = 0; i < N; ++i) tot += f[(size_t)i * N + j];
+    OrtRng g;
+    g.k0 = (uint32_t)seed; g.k1 = (uint32_t)(seed >> 32);
+    g.r1 = 0; g.phase = 3; g.override_u = -1.0;
+    for (int i = 0; i < N; ++i) {
+        for (int j = 0; j < N; ++j) {
+            double share = ((double)nphotons * f[(size_t)i * N + j]) / tot;
+            long long whole = (long long)share;
+            double frac = share - (double)whole, u, unused;
+            g.r0 = (uint32_t)(i * N + j);
+            ort_draw2(g, 0, &u, &unused);
+            budget[(size_t)j * N + i] = (int32_t)((u < frac && frac > 0) ? whole + 1 : whole);
+        }
+    }
     return ORT_OK;
 }
 

@@ -216,7 +216,7 @@ __device__ __forceinline__ void ort_count_a(OrtCounts& cnt, int st) {
         if (SRC != ORT_SRC_POINT) ort_count_rare<ORT_ST_SOURCE_MISS>(cnt, st, st == ORT_ST_SOURCE_MISS);
     } else {
         ort_count<ORT_ST_BOTTLE_INNER_REFLECT, ORT_ST_BOTTLE_OUTER_REFLECT, ORT_ST_L2_APERTURE>(cnt, st);
-        ort_count_rare<1, 2, 3, 5, 6, 7, 24>(cnt, st, st > 0 && st != 4 && st != 8 && st != 9);
+        ort_count_rare<1, 2, 3, 5, 6, 7, 24, 26>(cnt, st, st > 0 && st != 4 && st != 8 && st != 9);
     }
 }
 __device__ __forceinline__ void ort_count_b(OrtCounts& cnt, int st) {

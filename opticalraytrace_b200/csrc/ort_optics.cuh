@@ -746,6 +746,40 @@ ORT_HD bool ort_source_isors(const DevSceneT<R>& S, const OrtRng& g, OrtRayT<R>&
     return true;
 }
 
+/* emit_image + emit, src/sourceMod.f90:303-361 (image source, point loop): ray k leaves the pixel
+ * the reference's budget scan reaches after k rays (binary search in the prefix sums), from a
+ * uniform point inside it, aimed at a uniform point of L2's aperture disc.
+ * Slots: x 0, y 1, aim radius 10, aim angle 11. */
+template <typename R>
+ORT_HD bool ort_source_image(const DevSceneT<R>& S, const DevJob& J, const OrtRng& g, long long k, OrtRayT<R>& r) {
+    const long long npix = (long long)ORT_SRCIMG_N * ORT_SRCIMG_N;
+    const long long* cdf = J.image_cdf;
+    if (cdf == nullptr || k >= cdf[npix - 1]) return false;
+    long long lo = 0, hi = npix - 1;
+    while (lo < hi) {
+        long long mid = (lo + hi) >> 1;
+        if (cdf[mid] > k) hi = mid;
+        else lo = mid + 1;
+    }
+    const R dx = R(5000e-6 / 512.);
+    const R fj = (R)(lo % ORT_SRCIMG_N), fi = (R)(lo / ORT_SRCIMG_N); /* zero-based pixel */
+    R u0, u1, u2, u3, s, c;
+    ort_draw2(g, 0, &u0, &u1);
+    ort_draw2(g, 5, &u2, &u3);
+    R ax = fj * dx, bx = (fj + R(1.0)) * dx, ay = fi * dx, by = (fi + R(1.0)) * dx;
+    r.px = fma(u0, bx - ax, ax) - R(2500e-6);
+    r.py = fma(u1, by - ay, ay) - R(2500e-6);
+    r.pz = R(0.0);
+    R rl = ort_sqrt(u2 * S.isors_lens_r2); /* L2.radius^2 */
+    ort_sincospi(R(2.0) * u3, &s, &c);
+    R ex = fma(rl, c, -r.px), ey = fma(rl, s, -r.py), ez = S.l2_fb - r.pz;
+    R inv = ort_rsqrt(fma(ex, ex, fma(ey, ey, ez * ez)));
+    r.dx = ex * inv;
+    r.dy = ey * inv;
+    r.dz = ez * inv;
+    return true;
+}
+
 /* source dispatch of src/main.f90:95-101 (ring loop) and :132-142 (point loop); SRC is
  * ort_job.source_kind.  Returns 0 or ORT_ST_SOURCE_MISS. */
 template <int PHASE, int SRC, typename R>
@@ -755,6 +789,7 @@ ORT_HD int ort_emit(const DevSceneT<R>& S, const DevJob& J, const OrtRng& g, lon
         if (SRC == ORT_SRC_ISORS) return ort_source_isors(S, g, r) ? 0 : ORT_ST_SOURCE_MISS;
         ort_source_ring(S, g, r);
     } else {
+        if (SRC == ORT_SRC_IMAGE) return ort_source_image(S, J, g, ray, r) ? 0 : ORT_ST_SOURCE_MISS;
         if (SRC == ORT_SRC_SPOT) ort_source_spot(S, J.total_rays, ray + 1, r);
         else ort_source_point(S, g, r);
     }
@@ -1022,7 +1057,8 @@ ORT_HD int ort_full_path(const DevSceneT<R>& S, const DevJob& J, const OrtRng& g
                                                 : ort_emit<ORT_PHASE_RING, ORT_SRC_POINT>(S, J, g, ray, r);
         } else {
             es = J.source_kind == ORT_SRC_SPOT ? ort_emit<ORT_PHASE_POINT, ORT_SRC_SPOT>(S, J, g, ray, r)
-                                               : ort_emit<ORT_PHASE_POINT, ORT_SRC_POINT>(S, J, g, ray, r);
+               : J.source_kind == ORT_SRC_IMAGE ? ort_emit<ORT_PHASE_POINT, ORT_SRC_IMAGE>(S, J, g, ray, r)
+                                                : ort_emit<ORT_PHASE_POINT, ORT_SRC_POINT>(S, J, g, ray, r);
         }
         if (es) return es;
     }

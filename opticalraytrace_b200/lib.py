@@ -19,6 +19,7 @@ _lib = None
 EXPORTS = [
     "ort_init", "ort_init_rank", "ort_nccl_unique_id", "ort_finalize", "ort_last_error",
     "ort_device_count", "ort_struct_sizes", "ort_trace", "ort_trace_rays", "ort_uniforms", "ort_measure_fp64_peak", "ort_math_selftest", "ort_write_tracks",
+    "ort_load_image_source", "ort_set_image_source",
     "ort_load_plano", "ort_load_doublet", "ort_load_bottle", "ort_read_settings",
     "ort_build_scene", "ort_job_from_settings", "ort_output_basename", "ort_write_images",
     "ort_append_trans_stats",
@@ -54,6 +55,8 @@ def load():
     L.ort_measure_fp64_peak.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.ort_math_selftest.argtypes = [C.c_int64, C.POINTER(C.c_uint64)]
     L.ort_write_tracks.argtypes = [C.POINTER(abi.Job), C.POINTER(abi.Scene), C.c_char_p]
+    L.ort_load_image_source.argtypes = [C.c_char_p, C.c_int64, C.c_uint64, C.c_void_p]
+    L.ort_set_image_source.argtypes = [C.c_void_p]
     L.ort_load_plano.argtypes = [C.c_char_p, C.c_double, C.c_double, C.POINTER(abi.Plano)]
     L.ort_load_doublet.argtypes = [C.c_char_p, C.c_double, C.c_double, C.POINTER(abi.Doublet)]
     L.ort_load_bottle.argtypes = [C.c_char_p, C.c_double, C.POINTER(abi.Bottle)]
@@ -199,6 +202,21 @@ def trace_rays(job, scene, n, pos_in=None, dir_in=None):
                                 dir_out.ctypes.data, status.ctypes.data, bins.ctypes.data),
           allow=(abi.ORT_ETRACE,))
     return dict(pos=pos_out, dir=dir_out, status=status, bin=bins)
+
+
+def load_image_source(path, nphotons, seed=123456789):
+    """ort_load_image_source (init_emit_image) -> int32[512*512] ray budget, Fortran memory order"""
+    budget = np.zeros(abi.SRCIMG_N * abi.SRCIMG_N, dtype=np.int32)
+    check(load().ort_load_image_source(os.fsencode(path), int(nphotons), seed, budget.ctypes.data))
+    return budget
+
+
+def set_image_source(budget):
+    if budget is None:
+        return check(load().ort_set_image_source(None))
+    b = np.ascontiguousarray(budget, dtype=np.int32)
+    assert b.size == abi.SRCIMG_N * abi.SRCIMG_N
+    return check(load().ort_set_image_source(b.ctypes.data))
 
 
 def write_tracks(job, scene, path):

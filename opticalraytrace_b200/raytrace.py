@@ -36,8 +36,8 @@ def run(settings_path, resdir, datadir=None, *, nphotons=None, write=True, verbo
                       " Deselecting makeImages\n ***************")
             st.make_images = 0
     src = st.source_type.decode()
-    if src == "image":  # emit_image (src/sourceMod.f90:303-361) is the one emitter still missing
-        raise lib.OrtError(abi.ORT_EINVAL, "source type 'image' is not on the B200 path yet")
+    if src == "image":  # init_emit_image, src/setupMod.f90:120-121
+        lib.set_image_source(lib.load_image_source(os.path.join(resdir, st.image_file.decode()), st.nphotons))
     scene_ring, pre_guard = lib.build_scene(st, resdir, st.wavelength)
     scene_point, _ = lib.build_scene(st, resdir, 843e-9)
     if verbose and scene_ring.bottle.centre[2] != pre_guard:

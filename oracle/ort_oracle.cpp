@@ -483,6 +483,37 @@ inline void source_spot(vec& pos, vec& dir, double cosThetaMax, int64_t nrays, i
     pos = {0., 0., 0.};
 }
 
+/* emit_image + emit, src/sourceMod.f90:303-361.  `cdf` = inclusive prefix sums of the budget in
+ * the order emit_image scans it (second index outer, first index inner = memory order);
+ * ray k goes to the first pixel whose prefix sum exceeds k.  Slots: x 0, y 1, aim r 10, aim theta 11. */
+inline bool source_image(vec& pos, vec& dir, const ort_plano& lens, const int64_t* cdf, int64_t k, Draws& rng) {
+    const int64_t npix = (int64_t)ORT_SRCIMG_N * ORT_SRCIMG_N;
+    if (!cdf || k >= cdf[npix - 1]) return false;
+    int64_t lo = 0, hi = npix - 1;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) / 2;
+        if (cdf[mid] > k) hi = mid; else lo = mid + 1;
+    }
+    int64_t j = lo % ORT_SRCIMG_N + 1; /* first index of img(j,i): passed to emit as its `i` */
+    int64_t i = lo / ORT_SRCIMG_N + 1; /* second index: emit's `j` */
+    double dx = 5000e-6 / 512.;
+    double ax = (j - 1.) * dx, bx = j * dx, ay = (i - 1.) * dx, by = i * dx;
+    double x = (ax + rng.slot(0) * (bx - ax)) - 2500e-6;
+    double y = (ay + rng.slot(1) * (by - ay)) - 2500e-6;
+    pos = {x, y, 0.0};
+    double r = 0. + rng.slot(10) * ((lens.radius * lens.radius) - 0.);
+    double theta = rng.slot(11) * TWOPI;
+    double posx = std::sqrt(r) * std::cos(theta);
+    double posy = std::sqrt(r) * std::sin(theta);
+    vec lenspoint = {posx, posy, lens.fb};
+    double ex = lenspoint.x - pos.x, ey = lenspoint.y - pos.y, ez = lenspoint.z - pos.z;
+    double dist = std::sqrt(ex * ex + ey * ey + ez * ez);
+    dir = {(lenspoint.x - pos.x) / dist, (lenspoint.y - pos.y) / dist, (lenspoint.z - pos.z) / dist};
+    dir = magnitude(dir);
+    return true;
+}
+std::vector<int64_t> g_image_cdf; /* set by orc_set_image_source */
+
 /* iSORS with ring = .true., src/sourceMod.f90:162-247.  Returns false at the reference's
  * `error stop "no intersection with bottle!"`. */
 inline bool source_isors(vec& pos, vec& dir, const ort_bottle& B, const ort_plano& L1, double seperation,
@@ -748,7 +779,10 @@ inline RayOut trace_one(const ort_job& J, const ort_scene& S, int64_t ray, bool 
                             S.bottle.ellipse != 0, bcentre.z, rng);
             }
         } else {
-            if (J.source_kind == ORT_SRC_SPOT) {
+            if (J.source_kind == ORT_SRC_IMAGE) {
+                if (!source_image(pos, dir, S.L2, g_image_cdf.empty() ? nullptr : g_image_cdf.data(), ray, rng))
+                    return done(ORT_ST_SOURCE_MISS);
+            } else if (J.source_kind == ORT_SRC_SPOT) {
                 source_spot(pos, dir, S.cos_theta_max, J.total_rays > 0 ? J.total_rays : J.nrays, ray + 1);
             } else {
                 source_point(pos, dir, S.cos_theta_max, S.point_offset, rng);
@@ -932,6 +966,47 @@ int orc_derive_scene(ort_scene* S, double alpha_deg, double n_axicon, double rin
     S->r1 = r1 * r1;
     S->img_plane = 2. * (S->L2.fb + S->L3.fb) + S->L2.thickness + S->L3.thickness;
     S->point_offset = isors_source ? S->bottle.centre[2] : 0.0;
+    return 0;
+}
+
+/* init_emit_image, src/sourceMod.f90:363-408 (serial build: nphotonsLocal = nphotons).
+ * budget[(j-1)*512 + (i-1)] = imgin(i,j).  The rounding draw of pixel (i,j) is slot 0 of ray
+ * (i-1)*512 + (j-1) of stream 3 (the reference draws them in that loop order, before init_rng). */
+int orc_load_image_source(const char* path, int64_t nphotons, uint64_t seed, int32_t* budget) {
+    const int N = ORT_SRCIMG_N;
+    std::vector<double> f((size_t)N * N);
+    FILE* fh = std::fopen(path, "rb");
+    if (!fh) return ORT_EIO;
+    size_t got = std::fread(f.data(), sizeof(double), f.size(), fh);
+    std::fclose(fh);
+    if (got != f.size()) return ORT_EPARSE;
+    /* imgout(a,b) = f[(b-1)*N + (a-1)]; after the transpose imgout(i,j) = f[(i-1)*N + (j-1)] */
+    double tot = 0.;
+    for (int b = 1; b <= N; ++b)         /* sum() runs over the array in memory order */
+        for (int a = 1; a <= N; ++a) tot += f[(size_t)(a - 1) * N + (b - 1)];
+    for (int i = 1; i <= N; ++i) {
+        for (int j = 1; j <= N; ++j) {
+            double v = f[(size_t)(i - 1) * N + (j - 1)];
+            double tmp = ((double)nphotons * v) / tot;
+            double diff = tmp - (double)(int64_t)tmp;
+            Draws rng(seed, 3, (uint64_t)((i - 1) * N + (j - 1)), -1.0);
+            int32_t n = (int32_t)(int64_t)tmp;
+            if (rng.slot(0) < diff && diff > 0) n += 1;
+            budget[(size_t)(j - 1) * N + (i - 1)] = n;
+        }
+    }
+    return 0;
+}
+int orc_set_image_source(const int32_t* budget) {
+    g_image_cdf.clear();
+    if (!budget) return 0;
+    const size_t n = (size_t)ORT_SRCIMG_N * ORT_SRCIMG_N;
+    g_image_cdf.resize(n);
+    int64_t acc = 0;
+    for (size_t k = 0; k < n; ++k) {
+        acc += budget[k] > 0 ? budget[k] : 0;
+        g_image_cdf[k] = acc;
+    }
     return 0;
 }
 

@@ -47,11 +47,12 @@ int main(int argc, char** argv) {
             st.make_images = 0;
         }
     }
-    if (std::strcmp(st.source_type, "image") == 0) {
-        std::fprintf(stderr,
-                     "raytrace: source type 'image' is not on the B200 path yet (point, crs, isors and spot "
-                     "are; see DESIGN.md, scope row 8(f))\n");
-        return 2;
+    if (std::strcmp(st.source_type, "image") == 0) { /* init_emit_image, src/setupMod.f90:120-121 */
+        std::vector<int32_t> budget((size_t)ORT_SRCIMG_N * ORT_SRCIMG_N);
+        if (ort_load_image_source((std::string(resdir) + "/" + st.image_file).c_str(), st.nphotons, 123456789ull,
+                                  budget.data()))
+            return fail("image source");
+        ort_set_image_source(budget.data());
     }
     int want = std::getenv("ORT_NUM_GPUS") ? std::atoi(std::getenv("ORT_NUM_GPUS")) : 0;
     int ngpu = ort_init(want);

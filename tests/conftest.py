@@ -33,6 +33,15 @@ def harness():
     H = C.CDLL(os.path.join(ROOT, "tests", "libhost_harness.so"))
     H.hh_trace_rays.argtypes = [C.POINTER(abi.Job), C.POINTER(abi.Scene), C.c_int64] + [C.c_void_p] * 6
 
+    H.hh_set_image_source.argtypes = [C.c_void_p]
+
+    def set_image_source(budget):
+        if budget is None:
+            H.hh_set_image_source(None)
+        else:
+            b = np.ascontiguousarray(budget, dtype=np.int32)
+            H.hh_set_image_source(b.ctypes.data)
+
     def run(job, scene, n, pos_in=None, dir_in=None):
         po, do = np.zeros((3, n)), np.zeros((3, n))
         st, b = np.zeros(n, np.int32), np.zeros((2, n), np.int32)
@@ -44,6 +53,7 @@ def harness():
         H.hh_trace_rays(C.byref(job), C.byref(scene), n, pi, di, po.ctypes.data, do.ctypes.data,
                         st.ctypes.data, b.ctypes.data)
         return dict(pos=po, dir=do, status=st, bin=b)
+    run.set_image_source = set_image_source
     return run
 
 

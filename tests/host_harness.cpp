@@ -9,6 +9,7 @@
  */
 #include <cstdint>
 #include <cstring>
+#include <vector>
 
 #include "../opticalraytrace_b200/csrc/ort_flatten.h"
 #include "../opticalraytrace_b200/csrc/ort_optics.cuh"
@@ -40,12 +41,25 @@ static void run_rays(const DevSceneT<R>& S, const DevJob& J, int64_t n, const do
     }
 }
 
+static std::vector<long long> g_cdf;
+extern "C" int hh_set_image_source(const int32_t* budget) {
+    g_cdf.clear();
+    if (!budget) return 0;
+    long long acc = 0;
+    for (size_t k = 0; k < (size_t)ORT_SRCIMG_N * ORT_SRCIMG_N; ++k) {
+        acc += budget[k] > 0 ? budget[k] : 0;
+        g_cdf.push_back(acc);
+    }
+    return 0;
+}
+
 extern "C" int hh_trace_rays(const ort_job* job, const ort_scene* scene, int64_t n, const double* pin,
                              const double* din, double* pout, double* dout, int32_t* status, int32_t* bin) {
     DevScene S;
     DevJob J;
     ort_flatten_scene(*scene, *job, S);
     ort_make_dev_job(*job, 1, job->first_ray, n, J);
+    J.image_cdf = g_cdf.empty() ? nullptr : g_cdf.data();
     if (job->precision == 32) {
         DevSceneT<float> Sf;
         ort_scene_to_float(S, Sf);

@@ -55,6 +55,8 @@ def lib():
         for name in ("orc_intersect_sphere", "orc_intersect_cylinder"):
             getattr(L, name).argtypes = [DP, DP, DP, C.c_double, DP]
         L.orc_intersect_ellipse.argtypes = [DP, DP, DP, C.c_double, C.c_double, DP]
+        L.orc_load_image_source.argtypes = [C.c_char_p, C.c_int64, C.c_uint64, C.c_void_p]
+        L.orc_set_image_source.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -120,6 +122,21 @@ def trace(job, scenes, nthreads=0):
     _chk(lib().orc_trace(C.byref(job), arr, ns, image.ctypes.data, lost.ctypes.data,
                          hist.ctypes.data, nthreads), "trace")
     return image, lost, hist
+
+
+def load_image_source(path, nphotons, seed=123456789):
+    budget = np.zeros(512 * 512, dtype=np.int32)
+    _chk(lib().orc_load_image_source(os.fsencode(path), int(nphotons), seed, budget.ctypes.data),
+         "load_image_source")
+    return budget
+
+
+def set_image_source(budget):
+    if budget is None:
+        lib().orc_set_image_source(None)
+    else:
+        b = np.ascontiguousarray(budget, dtype=np.int32)
+        lib().orc_set_image_source(b.ctypes.data)
 
 
 def v3(a):
