@@ -88,6 +88,8 @@ struct DevJob {
     int32_t phase, use_bottle, iris_before, iris_after;
     int32_t nscenes, stop_after, flags, source_kind;
     int64_t total_rays;  /* nphotons of the whole job (create_spot) */
+    uint32_t round_keys[20];    /* Philox key schedule seed + r * (W0, W1), r = 0..9: launch constants,
+                                   so the rounds read them straight from the constant bank */
     const long long* image_cdf; /* image source: inclusive prefix sums of the 512x512 ray budget in
                                    emit_image's scan order (device memory), or NULL */
 };

@@ -137,6 +137,10 @@ inline void ort_make_dev_job(const ort_job& j, int nscenes, int64_t first, int64
     d.source_kind = j.source_kind;
     d.total_rays = j.total_rays > 0 ? j.total_rays : j.nrays;
     d.image_cdf = nullptr; /* the launcher fills in its device copy */
+    for (int r = 0; r < 10; ++r) {
+        d.round_keys[2 * r] = (uint32_t)j.seed + (uint32_t)r * 0x9E3779B9u;
+        d.round_keys[2 * r + 1] = (uint32_t)(j.seed >> 32) + (uint32_t)r * 0xBB67AE85u;
+    }
 }
 
 

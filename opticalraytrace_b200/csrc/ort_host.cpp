@@ -414,6 +414,7 @@ int ort_load_image_source(const char* path, int64_t nphotons, uint64_t seed, int
         for (int i = 0; i < N; ++i) tot += f[(size_t)i * N + j];
     OrtRng g;
     g.k0 = (uint32_t)seed; g.k1 = (uint32_t)(seed >> 32);
+    g.rk = nullptr;
     g.r1 = 0; g.phase = 3; g.override_u = -1.0;
     for (int i = 0; i < N; ++i) {
         for (int j = 0; j < N; ++j) {

@@ -60,6 +60,7 @@ __device__ __forceinline__ OrtRng ort_make_rng(const DevJob& J, uint32_t local_i
     unsigned long long ray = (unsigned long long)J.first_ray + local_id;
     g.k0 = (uint32_t)J.seed;
     g.k1 = (uint32_t)(J.seed >> 32);
+    g.rk = J.round_keys;
     g.r0 = (uint32_t)ray;
     g.r1 = (uint32_t)(ray >> 32);
     g.phase = (uint32_t)J.phase;
@@ -354,6 +355,7 @@ __global__ void ort_uniforms_kernel(uint64_t seed, int32_t phase, int64_t ray, i
     if (i >= n) return;
     OrtRng g;
     g.k0 = (uint32_t)seed; g.k1 = (uint32_t)(seed >> 32);
+    g.rk = nullptr;
     g.r0 = (uint32_t)(uint64_t)ray; g.r1 = (uint32_t)((uint64_t)ray >> 32);
     g.phase = (uint32_t)phase;
     g.override_u = -1.0;
@@ -395,7 +397,7 @@ __global__ void ort_math_selftest_kernel(long long n, unsigned long long* __rest
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     OrtRng g;
-    g.k0 = 0x5eedu; g.k1 = 0; g.r0 = (uint32_t)i; g.r1 = (uint32_t)(i >> 32); g.phase = 7; g.override_u = -1.0;
+    g.k0 = 0x5eedu; g.k1 = 0; g.rk = nullptr; g.r0 = (uint32_t)i; g.r1 = (uint32_t)(i >> 32); g.phase = 7; g.override_u = -1.0;
     double u0, u1, u2, u3;
     ort_draw2(g, 0, &u0, &u1);
     ort_draw2(g, 1, &u2, &u3);

@@ -368,19 +368,21 @@ ORT_HD float ort_sub_rn(float a, float b) {
  * ----------------------------------------------------------------------------------------- */
 struct OrtRng {
     uint32_t k0, k1;   /* seed */
+    const uint32_t* rk; /* optional precomputed key schedule (DevJob.round_keys), or NULL */
     uint32_t r0, r1;   /* ray index */
     uint32_t phase;
     double override_u; /* >= 0: every draw returns this */
 };
 
 ORT_HD void ort_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
-                              uint32_t k1, uint32_t* o) {
+                              uint32_t k1, uint32_t* o, const uint32_t* rk = nullptr) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         uint32_t hi0 = ort_mulhi(M0, c0), lo0 = M0 * c0;
         uint32_t hi1 = ort_mulhi(M1, c2), lo1 = M1 * c2;
-        uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        uint32_t ka = rk ? rk[2 * r] : k0, kb = rk ? rk[2 * r + 1] : k1;
+        uint32_t n0 = hi1 ^ c1 ^ ka, n2 = hi0 ^ c3 ^ kb;
         c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
         k0 += W0; k1 += W1;
     }
@@ -412,7 +414,7 @@ ORT_HD void ort_draw2(const OrtRng& g, uint32_t block, R* ua, R* ub) {
         return;
     }
     uint32_t w[4];
-    ort_philox4x32_10(g.r0, g.r1, g.phase, block, g.k0, g.k1, w);
+    ort_philox4x32_10(g.r0, g.r1, g.phase, block, g.k0, g.k1, w, g.rk);
     *ua = ort_bits_to_uniform<R>(w[0], w[1]);
     *ub = ort_bits_to_uniform<R>(w[2], w[3]);
 }

@@ -23,6 +23,7 @@ static void run_rays(const DevSceneT<R>& S, const DevJob& J, int64_t n, const do
         OrtRng g;
         uint64_t ray = (uint64_t)J.first_ray + (uint64_t)i;
         g.k0 = (uint32_t)J.seed; g.k1 = (uint32_t)(J.seed >> 32);
+        g.rk = J.round_keys;
         g.r0 = (uint32_t)ray; g.r1 = (uint32_t)(ray >> 32);
         g.phase = (uint32_t)J.phase;
         g.override_u = J.uniform_override;
