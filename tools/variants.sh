@@ -1,10 +1,6 @@
 #!/bin/bash
-# tuning helper (GPU box): selftest + short bench for each experimental build variants_tmp_*.so
+# tuning helper (GPU box): short bench for each experimental build variants_tmp_*.so
 for so in variants_tmp_*.so; do
-  ORT_LIB=$PWD/$so python -c "
-import sys; sys.path.insert(0,'.')
-from opticalraytrace_b200 import lib
-lib.init(1); print('$so', 'max ulp', lib.math_selftest(1<<26)); lib.finalize()"
   for ph in ring point; do
     ORT_LIB=$PWD/$so python bench.py --phase $ph --rays 2147483648 --steps 3 --no-cpu 2>&1 | tail -1 | python -c "
 import sys, json
