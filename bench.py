@@ -107,6 +107,23 @@ def flops_by_status(phase, use_bottle=True, iris_before=False, iris_after=False)
     return f
 
 
+def ncu_traffic(phase_name):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one trace-kernel launch, from the committed
+    ncu --set full summary (profiles/r01_<loop>_full.txt); None when absent."""
+    path = os.path.join(ROOT, "profiles", "r01_%s_full.txt" % phase_name)
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    total, seen = 0.0, False
+    try:
+        for line in open(path):
+            f = line.split()
+            if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                total += float(f[1]) * unit.get(f[2], 1.0)
+                seen = True
+    except OSError:
+        return None
+    return total if seen else None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -324,7 +341,11 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "alu_fp64", "achieved": achieved, "peak": peak_tf * world,
                          "unit": "TFLOP/s", "frac": achieved / (peak_tf * world) if peak_tf else None,
-                         "traffic": None,
+                         "traffic": ncu_traffic(args.phase) if (args.config == 2 and args.precision == 64
+                                                                and not args.flat) else None,
+                         "traffic_note": "DRAM bytes of one ncu-profiled launch of 2^27 rays "
+                                         "(profiles/r01_<loop>_full.txt): the loops have no per-ray memory "
+                                         "traffic, the image stays in L2",
                          "peak_source": "DFMA micro-kernel measured in this run on rank 0 at %.0f MHz, "
                                         "x n_gpus (MEASURED_PEAKS.json holds no FP64 figure)" % peak_mhz,
                          "flops_per_launched_ray": flops / (total_rays)},
