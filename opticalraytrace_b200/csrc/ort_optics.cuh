@@ -1,21 +1,25 @@
 /*
- * ort_optics.cuh -- per-ray optics of the trace loop, written for one-thread-per-ray fp64 on
- * sm_100a.  Each function names the reference routine whose result it reproduces (to 1e-9
- * relative; see DESIGN.md "numerics" for why the two need not be bit-identical).
+ * ort_optics.cuh -- per-ray optics of the trace loop, one thread per ray, templated on the real
+ * type R (double = the reference's arithmetic, 1e-9 parity; float = the fp32 variant, 1e-5).
+ * Each function names the reference routine whose result it reproduces; DESIGN.md section 3.3
+ * explains why the two need not be bit-identical.
  *
- * This is not a transliteration of the Fortran.  What changed and why (fp64 div / sqrt / sincos
- * are 15-70 instruction sequences on the FP64 pipe, FMAs are 1):
- *   - quadratics are solved in half-b form with ONE division (c/q) for unit directions and one
- *     reciprocal for the cylinder/ellipse (q/a and c/q share 1/(a*q));
- *   - Fresnel + Snell are fused: the reference's fresnel() and refract() each take
- *     sqrt(1 - eta^2 sin^2), here it is taken once, and the two squared amplitude ratios share
- *     one division; sin(theta_i) is never formed (the TIR test is done on eta^2 sin^2);
- *   - surface normals on spheres are (centre - pos) * (1/R) with 1/R hoisted to the host
- *     (the point is on the sphere by construction), no sqrt + 3 divisions;
- *   - aperture / iris tests compare squared radii; the fibre-NA test compares
- *     dz^2 >= cos^2(asin 0.22) |d|^2 instead of acos() > asin();
- *   - sin/cos of 2*pi*u use sincospi (no range-reduction slow path);
- *   - every launch-invariant scalar comes pre-computed in DevScene.
+ * This is not a transliteration of the Fortran.  Measured on this chip (tools/microbench): a
+ * DFMA with three distinct register operands issues every 3 cycles per scheduler, fp64 div and
+ * sqrt are 6-9 dependent FP64 instructions, and two thirds of what the loops execute is NOT
+ * floating point -- so the code below minimises instructions of every kind:
+ *   - quadratics in half-b form; the root the reference picks by sorting follows from the signs
+ *     of h and c, so only ONE quotient is formed (c/q or q/a);
+ *   - Fresnel + Snell fused: one sqrt, amplitudes in units of n_b, the draw compared as
+ *     2u B^2 D^2 > A^2 D^2 + C^2 B^2 (no division), eta c1 - c2 shared with the refraction;
+ *   - sphere normals are (centre - pos) * (1/R), clear-cylinder normals * (1/R), 1/R hoisted;
+ *   - aperture / iris tests on squared radii; the fibre-NA test as dz^2 >= cos^2(asin .22) |d|^2;
+ *   - rcp / div / sqrt from the MUFU seed + one refinement + residual correction, without the
+ *     compiler's range checks and slow-path calls (0 ulp off the correctly rounded operators over
+ *     1.3e8 device samples, ort_math_selftest); sincospi restricted to [0, 2);
+ *   - sign / zero tests on the integer pipe where a signed zero cannot occur;
+ *   - every launch-invariant scalar comes pre-computed in DevScene (kernel-parameter constant
+ *     bank), the Philox key schedule in DevJob.
  *
  * The header is also compiled for the host by tests/host_harness (test-only) so the
  * reformulated arithmetic can be checked against the oracle without a GPU; the product never
@@ -445,7 +449,7 @@ typedef OrtRayT<double> OrtRay;
 /* -------------------------------------------------------------------------------------------
  * Quadratic root selection -- reproduces solveQuadratic + the root picking shared by the
  * reference's intersect_* (src/surfaces.f90:227-260 and :74-87).  Half-b form:
- * a t^2 + 2 h t + c = R(0.)  `inv_aq_needed`: a != 1 (cylinder / ellipse).
+ * a t^2 + 2 h t + c = 0 (a = 1 for the spheres: unit directions).
  * ----------------------------------------------------------------------------------------- */
 /* Unit normal of a sphere at a point on it: (centre - pos) / R with 1/R hoisted.  A ray that runs
  * exactly along the axis must see EXACTLY (0,0,+-1): the reference normalises by the computed
@@ -546,7 +550,7 @@ ORT_HD bool ort_interface(OrtRayT<R>& r, R nx, R ny, R nz, const DevIfaceT<R>& f
     R cost2 = ort_sqrt_nz(ct2); /* NaN under total internal reflection, where it is not used */
     /* Fresnel amplitudes in units of nb (the ratios do not change): A/B = r_s, C/D = r_p.
      * R = (A^2 D^2 + C^2 B^2) / (2 B^2 D^2); the draw is compared without forming the quotient:
-     *   u > R  <=>  2u B^2 D^2 > A^2 D^2 + C^2 B^R(2.)
+     *   u > R  <=>  2u B^2 D^2 > A^2 D^2 + C^2 B^2.
      * 0 <= R <= 1 by construction (|A| <= B, |C| <= D); a NaN fails the comparison and reflects,
      * which is what the reference's NaN guard (R = 1) does. */
     R ec = f.eta * costt, e2 = f.eta * cost2;
@@ -713,7 +717,7 @@ ORT_HD bool ort_hit_cone(const OrtRayT<R>& r, R k, R height, R* t) {
 }
 
 /* iSORS(ring = .true.), src/sourceMod.f90:162-247 (isors, ring loop).  false = the reference's
- * `error stop "no intersection with bottle!"` (every ray the axicon face reflects, ~R(2.8) %). */
+ * `error stop "no intersection with bottle!"` (every ray the axicon face reflects, ~2.8 %). */
 template <typename R>
 ORT_HD bool ort_source_isors(const DevSceneT<R>& S, const OrtRng& g, OrtRayT<R>& r) {
     OrtScatterRngT<R> sr;
@@ -880,7 +884,7 @@ ORT_HD void ort_stokes(OrtRayT<R>& r, R hgg, const OrtRng& g, OrtScatterRngT<R>&
 }
 
 /* -------------------------------------------------------------------------------------------
- * glass_bottle%forward, src/lens.f90:230-R(350.)  Returns 0 or the ort_status that ended the ray.
+ * glass_bottle%forward, src/lens.f90:230-350.  Returns 0 or the ort_status that ended the ray.
  * ----------------------------------------------------------------------------------------- */
 /* one scatter loop (contents :262-282, wall :312-333); *t is the step still to be taken */
 template <typename R>
@@ -1026,7 +1030,7 @@ template <typename R>
 ORT_HD int ort_image(const DevSceneT<R>& S, OrtRayT<R>& r, int* xp, int* yp) {
     R d = ort_div_z(S.img_z - r.pz, r.dz);
     ort_advance(r, d);
-    /* angle = acos(dz/|d|) > asin(R(0.22))  <=>  dz < cos_na |d|;  a NaN angle passes (reference) */
+    /* angle = acos(dz/|d|) > asin(0.22)  <=>  dz < cos_na |d|;  a NaN angle passes (reference) */
     R dd = fma(r.dx, r.dx, fma(r.dy, r.dy, r.dz * r.dz));
     if (r.dz <= R(0.0) || r.dz * r.dz < S.cos_na2 * dd) return ORT_ST_NA_REJECT;
     R fx = floor(r.px * S.inv_binwid), fy = floor(r.py * S.inv_binwid);
