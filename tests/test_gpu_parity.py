@@ -268,3 +268,24 @@ def test_on_axis_ray_sees_zero_reflectance(ort, orc):
         assert b["status"][0] == 0 and tuple(b["bin"][:, 0]) == (0, 0) and b["status"][1] != 0
         assert np.array_equal(a["status"], b["status"]) and np.array_equal(a["bin"], b["bin"])
         assert np.array_equal(b["dir"][:, 0], [0.0, 0.0, 1.0])
+
+
+def test_more_rays_than_one_launch_holds(ort, orc):
+    """Ray ids inside a launch are 32-bit offsets, so ort_trace splits jobs into launches of at
+    most 2^31 rays: a job of 2^32 + 5 rays (three launches) must account for every ray once and
+    equal the sum of its parts, also far out in the ray-index space (1e11-ray jobs, config 5)."""
+    scene = cases.scene_for(orc, cases.C2, 1)
+    n = (1 << 32) + 5
+    first = 10 ** 11
+    img, lost, hist, tm = ort.trace(abi.default_job(1, n, first_ray=first), scene)
+    assert tm.kernel_launches == 3 and int(hist.sum()) == n and int(img.sum()) == int(hist[0, 0])
+    acc_img, acc_hist = np.zeros_like(img), np.zeros_like(hist)
+    for lo, cnt in ((0, 1 << 31), (1 << 31, 1 << 31), (1 << 32, 5)):
+        part = ort.trace(abi.default_job(1, cnt, first_ray=first + lo), scene)
+        acc_img += part[0]
+        acc_hist += part[2]
+    assert np.array_equal(acc_img, img) and np.array_equal(acc_hist, hist)
+    # the tail of the index space matches the oracle ray by ray
+    a = orc.trace_rays(abi.default_job(1, first_ray=first + (1 << 32) - 1000), scene, 1005)
+    b = ort.trace_rays(abi.default_job(1, first_ray=first + (1 << 32) - 1000), scene, 1005)
+    assert np.array_equal(a["status"], b["status"]) and np.array_equal(a["bin"], b["bin"])
