@@ -291,7 +291,7 @@ def main():
         sampler.start()
     barrier()
     t0 = time.perf_counter()
-    dev_s, red_s, launches, h2d, d2h = 0.0, 0.0, 0, 0, 0
+    dev_s, red_s, launches, h2d, d2h, d2h_s = 0.0, 0.0, 0, 0, 0, 0.0
     hist = np.zeros(32, dtype=np.int64)
     for k in range(args.steps):
         _, _, h, tm = step(args.warmup + k)
@@ -299,6 +299,7 @@ def main():
         red_s += tm.reduce_seconds
         launches += tm.kernel_launches
         h2d, d2h = tm.h2d_bytes, tm.d2h_bytes
+        d2h_s += tm.d2h_seconds
         if rank == 0:
             hist += h.sum(axis=0)
     barrier()
@@ -338,6 +339,10 @@ def main():
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
             "reduce_ms_per_step": red_s / args.steps * 1e3,
+            # there is no flush kernel (hits go to the L2-resident image with RED): the only image
+            # traffic is this device-to-host read-back of image + histogram on rank 0
+            "image_readback": {"bytes_per_step": int(d2h), "ms_per_step": d2h_s / args.steps * 1e3,
+                               "GB/s": (d2h * args.steps / d2h_s * 1e-9) if d2h_s > 0 else None},
             "clocks": clocks,
             "roofline": {"bound": "alu_fp64", "achieved": achieved, "peak": peak_tf * world,
                          "unit": "TFLOP/s", "frac": achieved / (peak_tf * world) if peak_tf else None,

@@ -54,7 +54,7 @@ module ort_interface
     end type ort_job
 
     type, bind(C) :: ort_timing
-        real(c_double)     :: trace_seconds, reduce_seconds, wall_seconds
+        real(c_double)     :: trace_seconds, reduce_seconds, wall_seconds, d2h_seconds
         integer(c_int64_t) :: kernel_launches, h2d_bytes, d2h_bytes
     end type ort_timing
 

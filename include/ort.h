@@ -185,6 +185,7 @@ typedef struct {
     double trace_seconds;  /* CUDA-event time: image clear + trace kernels, max over devices */
     double reduce_seconds; /* CUDA-event time of the NCCL image reduce (0 on one GPU) */
     double wall_seconds;   /* host wall clock of the whole call incl. H2D/D2H */
+    double d2h_seconds;    /* CUDA-event time of the image + histogram read-back on device 0 */
     int64_t kernel_launches;
     int64_t h2d_bytes, d2h_bytes;
 } ort_timing;

@@ -79,7 +79,8 @@ class Job(C.Structure):
 
 class Timing(C.Structure):
     _fields_ = [("trace_seconds", C.c_double), ("reduce_seconds", C.c_double),
-                ("wall_seconds", C.c_double), ("kernel_launches", C.c_int64),
+                ("wall_seconds", C.c_double), ("d2h_seconds", C.c_double),
+                ("kernel_launches", C.c_int64),
                 ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
 
 

@@ -105,7 +105,7 @@ struct DeviceCtx {
     int dev = -1;
     int num_sms = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev_start = nullptr, ev_traced = nullptr, ev_reduced = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_traced = nullptr, ev_reduced = nullptr, ev_copied = nullptr;
     unsigned long long* d_buf = nullptr; /* [nscenes*BINS image][nscenes*NSTATUS counters] */
     size_t d_elems = 0;
     ncclComm_t comm = nullptr;
@@ -139,6 +139,7 @@ static int ctx_open(DeviceCtx& c, int dev) {
     CK(cudaEventCreate(&c.ev_start));
     CK(cudaEventCreate(&c.ev_traced));
     CK(cudaEventCreate(&c.ev_reduced));
+    CK(cudaEventCreate(&c.ev_copied));
     return ORT_OK;
 }
 
@@ -152,6 +153,7 @@ extern "C" int ort_finalize(void) {
         if (c.ev_start) cudaEventDestroy(c.ev_start);
         if (c.ev_traced) cudaEventDestroy(c.ev_traced);
         if (c.ev_reduced) cudaEventDestroy(c.ev_reduced);
+        if (c.ev_copied) cudaEventDestroy(c.ev_copied);
         if (c.stream) cudaStreamDestroy(c.stream);
     }
     if (g.h_pinned) cudaFreeHost(g.h_pinned);
@@ -478,6 +480,7 @@ extern "C" int ort_trace(const ort_job* job, const ort_scene* scenes, int nscene
     CK(cudaMemcpyAsync(g.h_pinned + img_elems, c0.d_buf + img_elems, (size_t)nscenes * ORT_NSTATUS * 8,
                        cudaMemcpyDeviceToHost, c0.stream));
     d2h += (size_t)nscenes * ORT_NSTATUS * 8;
+    CK(cudaEventRecord(c0.ev_copied, c0.stream));
     for (int d = 0; d < G; ++d) {
         CK(cudaSetDevice(g.devs[d].dev));
         CK(cudaStreamSynchronize(g.devs[d].stream));
@@ -506,6 +509,12 @@ extern "C" int ort_trace(const ort_job* job, const ort_scene* scenes, int nscene
         }
         timing->trace_seconds = tmax * 1e-3;
         timing->reduce_seconds = reduced ? rmax * 1e-3 : 0.0;
+        {
+            float cms = 0.f;
+            CK(cudaSetDevice(c0.dev));
+            CK(cudaEventElapsedTime(&cms, c0.ev_reduced, c0.ev_copied));
+            timing->d2h_seconds = cms * 1e-3;
+        }
         timing->kernel_launches = launches;
         /* scene + job of every launch travel host -> device as kernel parameters */
         timing->h2d_bytes = (int64_t)(launches * (int64_t)(sizeof(DevScene) + sizeof(DevJob)));
