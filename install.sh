@@ -1,89 +1,56 @@
 #!/bin/bash
-# Build and run the B200 ray tracer -- same interface as the reference's install.sh
-# (reference install.sh:85-102): builds in src/, moves the binary to bin/, runs it from bin/.
-
-function showhelp
-{
-  echo 'Usage: ./install.sh [option] [option]...'
-  echo 'Compile and run raytrace (B200 build).'
-  echo
-  echo '   -h, --help            Shows this dialog.'
-  echo '   -n, --threads         Number of GPUs that share the ray loops (the reference: OpenMP'
-  echo '                         threads).  1 = a single device; default 32 = all visible devices.'
-  echo '   -f, --file            Settings file in res/ (default settings.params).'
-  echo '   -d, --debug           Device debug build (-G) of the CUDA library.'
-  echo '   -m, --make            Compile only, with warnings enabled.'
-}
-
-function makebuild
-{
-  if [ "$debug" = 1 ]; then
-    make clean && make debug
-  elif [ "$make" = 1 ]; then
-    make clean && make build
-  else
-    if [ "$NUM_THREADS" = 1 ]; then
-      make clean && make
-    else
-      make clean && make mp
-    fi
-  fi
-}
-
-function createdirs
-{
-  if [ ! -d "build" ]; then mkdir "build"; fi
-  cd build; ndirec="$(pwd)"; cd ..
-  if [ ! -d "bin" ]; then mkdir "bin"; fi
-  cd bin; bdirc="$(pwd)"; cd ..
-  if [ ! -d "data" ]; then mkdir "data"; fi
-  cd src
-}
-
-function run
-{
-  for i in *; do
-    if [ "${i}" != "${i%.o}" ]; then mv "${i}" "$ndirec"; fi
-  done
-  if [ "$make" = "1" ]; then exit 0; fi
-  mv raytrace "$bdirc" && echo " " && echo "*****Install complete*****" && echo " "
-  cd ../bin
-  ./raytrace $file
-}
-
-#defaults
-NUM_THREADS=32
-debug=0
-help=0
-make=0
-file="settings.params"
+# Launcher of the B200 ray tracer.  Same command line as the reference's install.sh
+# (flags -n/-f/-d/-m/-h, reference install.sh:85-102) and the same directory choreography:
+# compile in src/, park objects in build/, put the program in bin/ and start it FROM bin/ so
+# that it finds ../res/<settings> and writes ../data/<folder>/.
+#
+#   -n, --threads N   the reference: OpenMP threads.  Here: how many GPUs share the two ray
+#                     loops (1 = one device, the default 32 = every visible device).
+#   -f, --file FILE   settings file inside res/ (default settings.params)
+#   -d, --debug       link against the assert-instrumented CUDA library (make DEBUG=1)
+#   -m, --make        compile only (with -pedantic), do not run
+#   -h, --help        this text
 set -e
-cd "$(dirname "$0")"
+here="$(cd "$(dirname "$0")" && pwd)"
 
-createdirs
+usage() {
+  sed -n '2,14p' "$0" | sed 's/^# \{0,1\}//'
+}
 
-while [ "$1" != "" ]; do
-    case $1 in
-        -n | --threads )        NUM_THREADS=$2
-                                ;;
-        -h | --help )           showhelp
-                                exit
-                                ;;
-        -m | --make )           make=1
-                                makebuild
-                                exit
-                                ;;
-        -d | --debug )          debug=1
-                                ;;
-        -f | --file )           file=$2
-                                ;;
-    esac
-    shift
+gpus=32
+settings="settings.params"
+mode=release
+while [ $# -gt 0 ]; do
+  case "$1" in
+    -n|--threads) gpus="$2"; shift ;;
+    -f|--file)    settings="$2"; shift ;;
+    -d|--debug)   mode=debug ;;
+    -m|--make)    mode=compile-only ;;
+    -h|--help)    usage; exit 0 ;;
+    *)            echo "install.sh: unknown option $1" >&2; usage >&2; exit 64 ;;
+  esac
+  shift
 done
 
-makebuild
-# the reference exports OMP_NUM_THREADS here; the GPU build caps the device count instead
-if [ "$NUM_THREADS" != "32" ]; then
-  export ORT_NUM_GPUS=$NUM_THREADS
+mkdir -p "$here/build" "$here/bin" "$here/data"
+
+# --- compile (the GPU count is a run-time matter: one build serves every -n) ---------------
+case "$mode" in
+  debug)        target=debug ;;
+  compile-only) target=build ;;
+  *)            if [ "$gpus" = 1 ]; then target=all; else target=mp; fi ;;
+esac
+make -C "$here/src" clean
+make -C "$here/src" "$target"
+find "$here/src" -maxdepth 1 -name '*.o' -exec mv {} "$here/build/" \;
+[ "$mode" = compile-only ] && exit 0
+
+mv "$here/src/raytrace" "$here/bin/raytrace"
+printf '\n*****Install complete*****\n\n'
+
+# --- run, from bin/ like the reference -------------------------------------------------------
+if [ "$gpus" != 32 ]; then
+  export ORT_NUM_GPUS="$gpus"      # the reference exports OMP_NUM_THREADS here
 fi
-run
+cd "$here/bin"
+exec ./raytrace "$settings"
