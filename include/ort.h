@@ -56,6 +56,13 @@ extern "C" {
 #define ORT_FLAG_NO_REDUCE 2         /* rank mode: leave per-rank images un-reduced */
 #define ORT_FLAG_NO_COMPACTION 4     /* diagnostic: one-thread-per-ray kernel without the
                                         warp-level live-ray compaction */
+#define ORT_FLAG_NO_FILTER 8         /* ring loop: do not use the single-precision culling filter
+                                        (every ray past L2's aperture is traced in fp64; results are
+                                        the same either way) */
+#define ORT_FLAG_VERIFY_FILTER 16    /* ring loop, diagnostic: run the filter AND fp64 on every ray;
+                                        status_hist[ORT_FILTER_SLOT_CALLED] = rays the filter called,
+                                        status_hist[ORT_FILTER_SLOT_WRONG] = calls that disagree with
+                                        fp64 (0 expected); image and the other counters as usual */
 
 /* ort_job.source_kind = settings.params source_type.  Which routine emits, per loop
  * (reference src/main.f90:95-101 and :132-142):
@@ -112,6 +119,8 @@ enum ort_status {
                                         with bottle!"`; crs: spot point beside the bottle */
 };
 #define ORT_NSTATUS 32
+#define ORT_FILTER_SLOT_CALLED 30 /* only with ORT_FLAG_VERIFY_FILTER */
+#define ORT_FILTER_SLOT_WRONG 31
 /* statuses 1..20 and 24 are what the reference adds to rcount / pcount
  * (src/optics_system.f90:32,42 and src/main.f90:150-151); 26 is an abort there */
 #define ORT_STATUS_IS_LOST(s) (((s) >= 1 && (s) <= 20) || (s) == 24 || (s) == 26)

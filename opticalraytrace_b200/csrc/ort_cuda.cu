@@ -349,6 +349,42 @@ static inline void scene_as(const DevScene& s, DevSceneT<float>& d) { ort_scene_
 
 static const int64_t ORT_CHUNK = (int64_t)1 << 31; /* rays per scene per launch (ids are 32-bit) */
 
+/* The ring loop's four-stage kernel with the fp32 culling filter (ort_kernels.cuh): fp64 jobs with
+ * the default ring source on scenes whose L2 flat face lies in the aim plane. */
+template <typename R>
+static bool ring_filter_applies(const ort_job& job, const DevScene& s, bool flat) {
+    return sizeof(R) == sizeof(double) && !flat && job.phase == ORT_PHASE_RING && s.ring_shortcut &&
+           (job.source_kind == ORT_SRC_POINT || job.source_kind == ORT_SRC_SPOT) &&
+           !(job.flags & ORT_FLAG_NO_FILTER);
+}
+static int enqueue_ring_filter(DeviceCtx& c, const ort_job& job, const DevScene& s, int nscenes, int64_t first,
+                               int64_t n, unsigned long long* d_img, unsigned long long* d_cnt, int64_t* launches) {
+    typedef void (*kern_t)(const DevSceneT<double>, const DevSceneT<float>, const DevJob, unsigned long long*,
+                           unsigned long long*);
+    kern_t k = (job.flags & ORT_FLAG_VERIFY_FILTER) ? ort_trace_ring_filter_kernel<true>
+                                                    : ort_trace_ring_filter_kernel<false>;
+    size_t smem = (size_t)ORT_WPB * sizeof(RingFilterShared);
+    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, ORT_TPB, smem));
+    if (occ < 1) occ = 1;
+    int grid = c.num_sms * occ;
+    DevSceneT<float> sf;
+    ort_scene_to_float(s, sf);
+    for (int64_t off = 0; off < n; off += ORT_CHUNK) {
+        int64_t m = n - off < ORT_CHUNK ? n - off : ORT_CHUNK;
+        DevJob dj;
+        ort_make_dev_job(job, nscenes, first + off, m, dj);
+        int64_t batches = (m + 31) / 32;
+        int64_t want = (batches + ORT_WPB - 1) / ORT_WPB;
+        int gsz = (int)(want < grid ? (want > 0 ? want : 1) : grid);
+        k<<<gsz, ORT_TPB, smem, c.stream>>>(s, sf, dj, d_img, d_cnt);
+        CK(cudaGetLastError());
+        ++*launches;
+    }
+    return ORT_OK;
+}
+
 /* enqueue the trace of rays [first, first+n) of every scene on device ctx; returns launches */
 template <typename R>
 static int enqueue_trace_t(DeviceCtx& c, const ort_job& job, const std::vector<DevScene>& ds, int64_t first,
@@ -383,6 +419,12 @@ static int enqueue_trace_t(DeviceCtx& c, const ort_job& job, const std::vector<D
     for (int sc = 0; sc < nscenes; ++sc) {
         DevSceneT<R> dsr;
         scene_as(ds[sc], dsr);
+        if (ring_filter_applies<R>(job, ds[sc], flat)) {
+            int rc = enqueue_ring_filter(c, job, ds[sc], nscenes, first, n, d_img + (size_t)sc * ORT_IMG_BINS,
+                                         d_cnt + (size_t)sc * ORT_NSTATUS, launches);
+            if (rc != ORT_OK) return rc;
+            continue;
+        }
         for (int64_t off = 0; off < n; off += ORT_CHUNK) {
             int64_t m = n - off < ORT_CHUNK ? n - off : ORT_CHUNK;
             DevJob dj;

@@ -293,6 +293,135 @@ ort_trace_kernel(const __grid_constant__ DevSceneT<R> S, const __grid_constant__
     ort_counts_flush(cnt, lane, counters);
 }
 
+/* ---- ring loop with the fp32 culling filter (ort_ring_filter) ------------------------------
+ * Four stages: A draws the aim point and drops the rays aimed outside L2's aperture; F runs the
+ * single-precision filter on the survivors and counts the rays it can call; B is the ordinary fp64
+ * stage for the few the filter hands on (the ones that reach L3, and the near-calls); C as before.
+ * Used when the scene has ring_shortcut, precision is 64 and ORT_FLAG_NO_FILTER is not set; the
+ * results are identical to ort_trace_kernel's.
+ * VERIFY (ORT_FLAG_VERIFY_FILTER): F passes every ray on and B compares the filter's verdict with
+ * what fp64 finds: counters[ORT_FILTER_SLOT_CALLED] = rays the filter called,
+ * counters[ORT_FILTER_SLOT_WRONG] = calls that disagree with fp64 (must stay 0). */
+struct SlimQueue {
+    double a[ORT_QCAP], b[ORT_QCAP];
+    uint32_t id[ORT_QCAP];
+};
+struct RingFilterShared {
+    SlimQueue q0, q1;
+    WarpQueue<double> q2;
+};
+__device__ __forceinline__ void ort_slim_push(SlimQueue& q, int& n, bool alive, double a, double b, uint32_t id,
+                                              unsigned lane) {
+    unsigned m = __ballot_sync(ORT_FULL, alive);
+    if (alive) {
+        int p = n + __popc(m & ((1u << lane) - 1u));
+        ORT_ASSERT(p >= 0 && p < ORT_QCAP);
+        q.a[p] = a;
+        q.b[p] = b;
+        q.id[p] = id;
+    }
+    n += __popc(m);
+    __syncwarp();
+}
+__device__ __forceinline__ bool ort_slim_pop(SlimQueue& q, int& n, double& a, double& b, uint32_t& id, unsigned lane) {
+    int cnt = n < 32 ? n : 32;
+    int base = n - cnt;
+    bool act = (int)lane < cnt;
+    if (act) {
+        int p = base + lane;
+        ORT_ASSERT(p >= 0 && p < ORT_QCAP);
+        a = q.a[p];
+        b = q.b[p];
+        id = q.id[p];
+    }
+    n = base;
+    __syncwarp();
+    return act;
+}
+
+template <bool VERIFY>
+__global__ void __launch_bounds__(ORT_TPB, ORT_MIN_BLOCKS)
+ort_trace_ring_filter_kernel(const __grid_constant__ DevSceneT<double> S, const __grid_constant__ DevSceneT<float> F,
+                             const __grid_constant__ DevJob J, unsigned long long* __restrict__ img,
+                             unsigned long long* __restrict__ counters) {
+    extern __shared__ __align__(16) unsigned char ort_smem[];
+    RingFilterShared& ws = reinterpret_cast<RingFilterShared*>(ort_smem)[threadIdx.x >> 5];
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t nwarps = gridDim.x * ORT_WPB;
+    const uint32_t gwarp = blockIdx.x * ORT_WPB + (threadIdx.x >> 5);
+    const uint32_t nrays = (uint32_t)J.nrays;
+    const uint32_t nbatches = (nrays + 31u) >> 5;
+
+    OrtCounts cnt;
+#pragma unroll
+    for (int k = 0; k < ORT_NSTATUS; ++k) cnt.c[k] = 0;
+    int n0 = 0, n1 = 0, n2 = 0;
+    uint32_t b = gwarp;
+    for (;;) {
+        int stage;
+        if (n2 >= 32) stage = 3;
+        else if (n1 >= 32) stage = 2;
+        else if (n0 >= 32) stage = 1;
+        else if (b < nbatches) stage = 0;
+        else if (n0 > 0) stage = 1; /* drain from the top so the later stages run full */
+        else if (n1 > 0) stage = 2;
+        else if (n2 > 0) stage = 3;
+        else break;
+
+        uint32_t id = 0;
+        if (stage == 0) {
+            id = b * 32u + lane;
+            b += nwarps;
+            int st = -1;
+            double u2 = 0.0, u3 = 0.0;
+            if (id < nrays) {
+                OrtRng g = ort_make_rng_prod(J, id);
+                ort_draw2(g, 1, &u2, &u3);
+                st = ort_ring_aims_outside_aperture(S, u2) ? ORT_ST_L2_APERTURE : 0;
+            }
+            ort_slim_push(ws.q0, n0, st == 0, u2, u3, id, lane);
+            ort_count<ORT_ST_L2_APERTURE>(cnt, st);
+        } else if (stage == 1) {
+            double u2 = 0.0, u3 = 0.0;
+            bool act = ort_slim_pop(ws.q0, n0, u2, u3, id, lane);
+            int st = -1;
+            if (act) {
+                OrtRng g = ort_make_rng_prod(J, id);
+                st = VERIFY ? 0 : ort_ring_filter(F, J, g, (float)u2, (float)u3);
+            }
+            ort_slim_push(ws.q1, n1, st == 0, u2, u3, id, lane);
+            ort_count_b(cnt, st);
+        } else if (stage == 2) {
+            OrtRayT<double> r;
+            bool act = ort_slim_pop(ws.q1, n1, r.px, r.py, id, lane);
+            int st = -1;
+            if (act) {
+                OrtRng g = ort_make_rng_prod(J, id);
+                int verdict = VERIFY ? ort_ring_filter(F, J, g, (float)r.px, (float)r.py) : 0;
+                r.pz = r.dx = r.dy = r.dz = 0.0;
+                st = ort_stage_b<ORT_PHASE_RING, ORT_SRC_POINT>(S, J, g, r);
+                if (VERIFY) {
+                    cnt.c[ORT_FILTER_SLOT_CALLED] += __popc(__ballot_sync(__activemask(), verdict > 0));
+                    cnt.c[ORT_FILTER_SLOT_WRONG] += __popc(__ballot_sync(__activemask(), verdict > 0 && verdict != st));
+                }
+            }
+            ort_q_push(ws.q2, n2, st == 0, r, id, lane);
+            ort_count_b(cnt, st);
+        } else {
+            OrtRayT<double> r;
+            bool act = ort_q_pop(ws.q2, n2, r, id, lane);
+            int st = -1, xp = 0, yp = 0;
+            if (act) {
+                OrtRng g = ort_make_rng_prod(J, id);
+                st = ort_stage_c(S, J, g, r, &xp, &yp);
+            }
+            ort_bin(img, st == ORT_ST_BINNED, xp, yp, lane);
+            ort_count_c(cnt, st);
+        }
+    }
+    ort_counts_flush(cnt, lane, counters);
+}
+
 /* The same path, one thread per ray from source to detector, no compaction: every early exit
  * leaves its lane idle until the slowest lane of the warp is done.  Kept to measure what the
  * compaction buys (warp execution efficiency in ncu) and as a cross-check of the megakernel. */

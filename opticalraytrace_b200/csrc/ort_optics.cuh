@@ -1045,6 +1045,191 @@ ORT_HD int ort_image(const DevSceneT<R>& S, OrtRayT<R>& r, int* xp, int* yp) {
 }
 
 /* -------------------------------------------------------------------------------------------
+ * Single-precision culling filter for the ring loop (no counterpart in the reference).
+ *
+ * 99.5 % of the ring rays that pass L2's aperture still end between L2's curved face and L3's first
+ * surface (total reflection in L2, or no intersection with L3's first sphere), i.e. they only add
+ * one to a status counter.  WHICH counter is a chain of sign decisions -- discriminants, aperture
+ * radii, the Fresnel draw -- and a decision is safe in single precision whenever its operands are
+ * further apart than single precision can blur.  The filter walks source -> L2 -> L3 first
+ * surface in fp32 (one issue slot per FFMA instead of a multi-cycle DFMA, one MUFU per
+ * rcp/rsqrt/sin/cos) and returns
+ *     s > 0 : every decision up to the ray's end had a relative margin > ORT_FILTER_TOL and the ray
+ *             ends with status s -- exactly what the fp64 path would count;
+ *     0     : the ray survives to L3, or some decision was too close to call -> the caller runs
+ *             the ordinary fp64 stage on it (ort_stage_b), which alone moves rays forward.
+ * Measured (tools/filter_margin.py, host build, 1e7 rays past L2's aperture over shipped and
+ * randomised geometries): with NO margin at all fp32 misjudges 2 rays in 1e7, i.e. its error is
+ * ~1e-7 of the compared quantities (the divisions by near-zero discriminants that could amplify it
+ * are exactly the near-calls that are handed back); the margin used is 5e-4, more than three
+ * orders of magnitude above that, and costs ~1 % of the rays an unnecessary fp64 pass.
+ * ORT_FLAG_VERIFY_FILTER runs both paths on every ray and counts disagreements
+ * (tests/test_ring_filter.py), ORT_FLAG_NO_FILTER switches the filter off.
+ * ----------------------------------------------------------------------------------------- */
+#ifndef ORT_FILTER_TOL
+#define ORT_FILTER_TOL 5e-4f
+#endif
+
+ORT_HD float ortf_rcp(float x) {
+#ifdef __CUDA_ARCH__
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#else
+    return 1.0f / x;
+#endif
+}
+ORT_HD float ortf_rsqrt(float x) {
+#ifdef __CUDA_ARCH__
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#else
+    return 1.0f / sqrtf(x);
+#endif
+}
+ORT_HD float ortf_sqrt(float x) {
+#ifdef __CUDA_ARCH__
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#else
+    return sqrtf(x);
+#endif
+}
+/* sin, cos of 2 pi u, u in [0,1): the argument is folded to [-pi, pi] first, where the MUFU
+ * approximations are good to ~5e-7 absolute */
+ORT_HD void ortf_sincos_turn(float u, float* s, float* c) {
+    float a = (u - (u >= 0.5f ? 1.0f : 0.0f)) * 6.2831853071795865f;
+#ifdef __CUDA_ARCH__
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(*s) : "f"(a));
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(*c) : "f"(a));
+#else
+    *s = sinf(a);
+    *c = cosf(a);
+#endif
+}
+/* the top 24 bits of the 53-bit uniform (the fp64 path's u differs by < 2^-24) */
+ORT_HD float ortf_uniform(uint32_t hi) {
+    return (float)(hi >> 8) * 5.9604644775390625e-8f;
+}
+
+/* sphere intersection with margins: 1 hit (t set), 0 miss, -1 too close to call */
+ORT_HD int ortf_hit_sphere(const OrtRayT<float>& r, float cx, float cy, float cz, float R2, float* t) {
+    float lx = r.px - cx, ly = r.py - cy, lz = r.pz - cz;
+    float h = fmaf(r.dx, lx, fmaf(r.dy, ly, r.dz * lz));
+    float l2 = fmaf(lx, lx, fmaf(ly, ly, lz * lz));
+    float c = l2 - R2;
+    float disc = fmaf(h, h, -c);
+    float tol = ORT_FILTER_TOL * (l2 + R2);
+    /* the outcome hangs on the signs of disc, h and c (ort_pick_root_unit) */
+    if (!(fabsf(disc) > tol) || !(h * h > tol) || !(fabsf(c) > tol)) return -1;
+    if (disc < 0.0f) return 0;
+    bool hpos = h > 0.0f;
+    if (hpos && c > 0.0f) return 0;
+    float sq = ortf_sqrt(disc);
+    float q = hpos ? -(h + sq) : (sq - h);
+    *t = (!hpos && c < 0.0f) ? q : c * ortf_rcp(q);
+    return 1;
+}
+/* dielectric interface with margins: 0 refracted, 1 reflected, -1 too close to call */
+ORT_HD int ortf_interface(OrtRayT<float>& r, float nx, float ny, float nz, const DevIfaceT<float>& f, float u) {
+    float c = fmaf(nx, r.dx, fmaf(ny, r.dy, nz * r.dz));
+    float costt = fabsf(c);
+    float s2 = fmaf(-costt, costt, 1.0f);
+    float ct2 = fmaf(-f.eta2, s2, 1.0f);
+    /* near normal incidence the reference switches to R = 0 at EXACTLY cos = 1; near the critical
+     * angle the branch itself is at stake */
+    if (!(s2 > 1e-4f) || !(fabsf(ct2) > ORT_FILTER_TOL)) return -1;
+    bool reflect = true;
+    float A = 0.0f;
+    if (ct2 > 0.0f) {
+        float cost2 = ortf_sqrt(ct2);
+        float ec = f.eta * costt, e2 = f.eta * cost2;
+        A = ec - cost2;
+        float B = ec + cost2, C = e2 - costt, D = e2 + costt;
+        float B2 = B * B, D2 = D * D, den = B2 * D2;
+        float num = fmaf(A * A, D2, (C * C) * B2);
+        float lhs = (u + u) * den;
+        if (!(fabsf(lhs - num) > (2.0f * ORT_FILTER_TOL) * den)) return -1; /* |u - R| < tol */
+        reflect = !(lhs > num);
+    }
+    if (reflect) {
+        float k = -2.0f * c;
+        r.dx = fmaf(k, nx, r.dx);
+        r.dy = fmaf(k, ny, r.dy);
+        r.dz = fmaf(k, nz, r.dz);
+        return 1;
+    }
+    float k = (c < 0.0f) ? A : -A;
+    r.dx = fmaf(f.eta, r.dx, k * nx);
+    r.dy = fmaf(f.eta, r.dy, k * ny);
+    r.dz = fmaf(f.eta, r.dz, k * nz);
+    return 0;
+}
+
+/* (u2, u3): the aim-point uniforms the caller already holds; the other draws are regenerated */
+ORT_HD int ort_ring_filter(const DevSceneT<float>& F, const DevJob& J, const OrtRng& g, float u2, float u3) {
+    uint32_t w[4];
+    ort_philox4x32_10(g.r0, g.r1, g.phase, 0u, g.k0, g.k1, w, g.rk);
+    float u0 = ortf_uniform(w[1]), u1 = ortf_uniform(w[3]);
+    /* ring source, ort_source_ring_u */
+    OrtRayT<float> r;
+    float s, c;
+    float rr = ortf_sqrt(fmaf(u0, F.r2_m_r1, F.r1));
+    ortf_sincos_turn(u1, &s, &c);
+    r.px = rr * c;
+    r.py = rr * s;
+    float q = F.ellipse ? r.py * F.ra_over_rb : r.py;
+    r.pz = F.bcz + ortf_sqrt(fmaf(-q, q, F.ra2));
+    float aim2 = u2 * F.lens_r2;
+    /* L2's aperture, decided in stage A on the fp64 u2; the recomputation in ort_l2_enter can only
+     * differ at the very edge */
+    if (!(aim2 < F.l2_radius2 * (1.0f - ORT_FILTER_TOL))) return 0;
+    float rl = ortf_sqrt(aim2);
+    ortf_sincos_turn(u3, &s, &c);
+    float ax = rl * c, ay = rl * s;
+    float ex = ax - r.px, ey = ay - r.py, ez = F.l2_fb - r.pz;
+    float inv = ortf_rsqrt(fmaf(ex, ex, fmaf(ey, ey, ez * ez)));
+    r.dx = ex * inv;
+    r.dy = ey * inv;
+    r.dz = ez * inv;
+    /* the flat face lies in the aim plane (ring_shortcut): the ray meets it at the aim point */
+    r.px = ax;
+    r.py = ay;
+    r.pz = F.l2_flat_z;
+    /* L2, ort_l2_body */
+    ort_philox4x32_10(g.r0, g.r1, g.phase, 2u, g.k0, g.k1, w, g.rk);
+    int k = ortf_interface(r, F.l2_fnx, F.l2_fny, F.l2_fnz, F.l2_in, ortf_uniform(w[1]));
+    if (k < 0) return 0; /* a reflection here is not tested by the reference: the ray goes on */
+    float t;
+    k = ortf_hit_sphere(r, F.l2_cx, F.l2_cy, F.l2_cz, F.l2_R2, &t);
+    if (k < 0) return 0;
+    if (k == 0) return ORT_ST_L2_SPHERE_MISS;
+    ort_advance(r, t);
+    k = ortf_interface(r, (F.l2_cx - r.px) * F.l2_invR, (F.l2_cy - r.py) * F.l2_invR, (F.l2_cz - r.pz) * F.l2_invR,
+                       F.l2_out, ortf_uniform(w[3]));
+    if (k < 0) return 0;
+    if (k == 1) return ORT_ST_L2_CURVED_REFLECT;
+    /* L3 up to its aperture, ort_l3_enter */
+    if (J.iris_before) {
+        if (!(fabsf(r.dz) > ORT_FILTER_TOL)) return 0;
+        float ti = (F.l3_iris1_z - r.pz) * ortf_rcp(r.dz);
+        float x = fmaf(r.dx, ti, r.px), y = fmaf(r.dy, ti, r.py);
+        float rho2 = fmaf(x, x, y * y);
+        if (!(fabsf(rho2 - F.l3_iris_r2) > ORT_FILTER_TOL * (rho2 + F.l3_iris_r2))) return 0;
+        if (rho2 > F.l3_iris_r2) return ORT_ST_L3_IRIS_BEFORE;
+    }
+    k = ortf_hit_sphere(r, F.l3_c1x, F.l3_c1y, F.l3_c1z, F.l3_R1_2, &t);
+    if (k < 0) return 0;
+    if (k == 0) return ORT_ST_L3_S1_MISS;
+    ort_advance(r, t);
+    float rho2 = fmaf(r.px, r.px, r.py * r.py);
+    if (!(fabsf(rho2 - F.l3_radius2) > ORT_FILTER_TOL * (rho2 + F.l3_radius2))) return 0;
+    return rho2 > F.l3_radius2 ? ORT_ST_L3_APERTURE : 0;
+}
+
+/* -------------------------------------------------------------------------------------------
  * One whole iteration of the reference's ray loops for a single ray (src/main.f90:90-109 /
  * :127-162 incl. telescope, src/optics_system.f90:6-52), with the explicit-ray conveniences of
  * ort_trace_rays: optional caller-supplied start state and ort_job.stop_after.

@@ -53,7 +53,14 @@ def harness():
         H.hh_trace_rays(C.byref(job), C.byref(scene), n, pi, di, po.ctypes.data, do.ctypes.data,
                         st.ctypes.data, b.ctypes.data)
         return dict(pos=po, dir=do, status=st, bin=b)
+    H.hh_ring_filter.argtypes = [C.POINTER(abi.Job), C.POINTER(abi.Scene), C.c_int64, C.c_void_p]
+
+    def ring_filter(job, scene, n):
+        v = np.zeros(n, np.int32)
+        shortcut = H.hh_ring_filter(C.byref(job), C.byref(scene), n, v.ctypes.data)
+        return v, bool(shortcut)
     run.set_image_source = set_image_source
+    run.ring_filter = ring_filter
     return run
 
 

@@ -70,3 +70,30 @@ extern "C" int hh_trace_rays(const ort_job* job, const ort_scene* scene, int64_t
     }
     return 0;
 }
+
+/* the ring loop's fp32 culling filter on rays [first, first+n): verdict[i] = -1 when stage A
+ * already ends the ray (aim outside L2's aperture), else ort_ring_filter's answer (0 = hand to
+ * fp64, s > 0 = certain status).  Returns the scene's ring_shortcut flag (the filter is only used
+ * when it is set). */
+extern "C" int hh_ring_filter(const ort_job* job, const ort_scene* scene, int64_t n, int32_t* verdict) {
+    DevScene S;
+    DevJob J;
+    ort_flatten_scene(*scene, *job, S);
+    ort_make_dev_job(*job, 1, job->first_ray, n, J);
+    DevSceneT<float> F;
+    ort_scene_to_float(S, F);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        OrtRng g;
+        uint64_t ray = (uint64_t)J.first_ray + (uint64_t)i;
+        g.k0 = (uint32_t)J.seed; g.k1 = (uint32_t)(J.seed >> 32);
+        g.rk = J.round_keys;
+        g.r0 = (uint32_t)ray; g.r1 = (uint32_t)(ray >> 32);
+        g.phase = (uint32_t)J.phase;
+        g.override_u = -1.0;
+        double u2, u3;
+        ort_draw2(g, 1, &u2, &u3);
+        verdict[i] = ort_ring_aims_outside_aperture(S, u2) ? -1 : ort_ring_filter(F, J, g, (float)u2, (float)u3);
+    }
+    return S.ring_shortcut;
+}

@@ -1,0 +1,98 @@
+"""The ring loop's single-precision culling filter (ort_ring_filter, ort_optics.cuh).
+
+A verdict s > 0 claims "this ray ends with status s, no need to trace it in fp64": it has to agree
+with the oracle on EVERY ray; a verdict 0 hands the ray to the fp64 stage and is always safe.  On
+CPU the filter is the host-compiled header; on the GPU box ORT_FLAG_VERIFY_FILTER makes the kernel
+run both paths on every ray and count disagreements."""
+import numpy as np
+import pytest
+
+from opticalraytrace_b200 import abi
+from tests import cases
+from tests.test_fuzz_scenes import random_case
+
+RING_SETUPS = [(cases.C1, {}), (cases.C2, {}), (cases.ELL, {}), (cases.ELLS, {}), (cases.OTHER, {}),
+               (cases.OTHER2, {}), (cases.C2, dict(iris="before", iris_radius=0.6)),
+               (cases.C1, dict(iris="before", iris_radius=0.3))]
+
+
+def _check_filter(orc, harness, scene, job, n):
+    verdict, shortcut = harness.ring_filter(job, scene, n)
+    ref = orc.trace_rays(job, scene, n)["status"]
+    if not shortcut:            # L2 moved out of the aim plane: the launcher does not use the filter
+        return 0, 0, 0
+    stage_a = verdict == -1
+    assert np.all(ref[stage_a] == 9)
+    certain = verdict > 0
+    bad = certain & (verdict != ref)
+    assert not bad.any(), (np.flatnonzero(bad)[:5], verdict[bad][:5], ref[bad][:5])
+    # rays the filter hands back although they do end before L3's aperture test: wasted, not wrong
+    in_b = ~stage_a
+    ended_in_b = in_b & np.isin(ref, [9, 10, 11, 12, 13, 14])
+    return int(in_b.sum()), int(certain.sum()), int(ended_in_b.sum())
+
+
+@pytest.mark.parametrize("k", range(len(RING_SETUPS)))
+def test_filter_verdicts_are_exact(orc, harness, k):
+    files, kw = RING_SETUPS[k]
+    scene = cases.scene_for(orc, files, 1)
+    n = 1_500_000
+    job = abi.default_job(1, first_ray=7 * 10 ** 9 * k, **kw)
+    in_b, certain, ended = _check_filter(orc, harness, scene, job, n)
+    # the filter must actually cull: nearly every ray that ends in stage B is called in fp32
+    assert certain > 0.97 * ended, (in_b, certain, ended)
+
+
+@pytest.mark.parametrize("k", range(0, 40, 1))
+def test_filter_on_random_scenes(orc, harness, k):
+    scene, phase, kw = random_case(orc, k)
+    kw.pop("use_bottle")
+    job = abi.default_job(1, first_ray=k * 10 ** 9, **kw)
+    _check_filter(orc, harness, scene, job, 200_000)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k", range(len(RING_SETUPS)))
+def test_cuda_filter_kernel_equals_oracle_and_unfiltered(ort, orc, k):
+    files, kw = RING_SETUPS[k]
+    scene = cases.scene_for(orc, files, 1)
+    n = 400_003
+    job = abi.default_job(1, n, first_ray=3 * 10 ** 9 * k, **kw)
+    img, lost, hist, tm = ort.trace(job, scene)
+    oimg, olost, ohist = orc.trace(job, scene)
+    assert np.array_equal(hist, ohist) and np.array_equal(img, oimg) and np.array_equal(lost, olost)
+    # at scale: filter on / off / verify agree to the last count
+    big = 3_000_000_000
+    job = abi.default_job(1, big, first_ray=10 ** 12 + k, **kw)
+    img, lost, hist, tm = ort.trace(job, scene)
+    job.flags = abi.FLAG_NO_FILTER
+    img0, lost0, hist0, tm0 = ort.trace(job, scene)
+    assert np.array_equal(hist, hist0) and np.array_equal(img, img0) and np.array_equal(lost, lost0)
+    job.flags = abi.FLAG_VERIFY_FILTER
+    img1, lost1, hist1, _ = ort.trace(job, scene)
+    called, wrong = int(hist1[0, abi.FILTER_SLOT_CALLED]), int(hist1[0, abi.FILTER_SLOT_WRONG])
+    ended_in_b = int(hist0[0, 10:15].sum())
+    assert wrong == 0
+    assert called > 0.97 * ended_in_b, (called, ended_in_b)
+    hist1[0, 30:] = 0
+    assert np.array_equal(hist1, hist0) and np.array_equal(img1, img0)
+    print("setup %d: %.3g rays/s filtered, %.3g rays/s unfiltered, filter called %.2f%% of stage-B deaths"
+          % (k, big / tm.trace_seconds, big / tm0.trace_seconds, 100.0 * called / max(ended_in_b, 1)))
+
+
+@pytest.mark.gpu
+def test_cuda_filter_on_random_scenes(ort, orc):
+    jobs, scenes = [], []
+    for k in range(40):
+        scene, phase, kw = random_case(orc, k)
+        kw.pop("use_bottle")
+        n = 200_000_000
+        job = abi.default_job(1, n, first_ray=k * 10 ** 10, **kw)
+        job.flags |= abi.FLAG_VERIFY_FILTER
+        img1, lost1, hist1, _ = ort.trace(job, scene, allow_trap=True)
+        assert int(hist1[0, abi.FILTER_SLOT_WRONG]) == 0, k
+        job.flags &= ~abi.FLAG_VERIFY_FILTER
+        img, lost, hist, _ = ort.trace(job, scene, allow_trap=True)
+        job.flags |= abi.FLAG_NO_FILTER
+        img0, lost0, hist0, _ = ort.trace(job, scene, allow_trap=True)
+        assert np.array_equal(hist, hist0) and np.array_equal(img, img0), k
