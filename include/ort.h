@@ -119,7 +119,8 @@ enum ort_status {
                                         with bottle!"`; crs: spot point beside the bottle */
 };
 #define ORT_NSTATUS 32
-#define ORT_FILTER_SLOT_CALLED 30 /* only with ORT_FLAG_VERIFY_FILTER */
+#define ORT_FILTER_SLOT_OVERFLOW 29 /* internal: non-zero makes ort_trace fail with ORT_ECUDA */
+#define ORT_FILTER_SLOT_CALLED 30   /* only with ORT_FLAG_VERIFY_FILTER */
 #define ORT_FILTER_SLOT_WRONG 31
 /* statuses 1..20 and 24 are what the reference adds to rcount / pcount
  * (src/optics_system.f90:32,42 and src/main.f90:150-151); 26 is an abort there */

@@ -110,6 +110,10 @@ struct DeviceCtx {
     size_t d_elems = 0;
     ncclComm_t comm = nullptr;
     long long* d_image_cdf = nullptr; /* image source: prefix sums of the ray budget */
+    uint32_t* d_list = nullptr;       /* ring loop: ray indices the fp32 filter hands to fp64 */
+    size_t list_cap = 0;
+    unsigned* d_nlist = nullptr;      /* ... and the length of that list, one slot per slice */
+    size_t nlist_cap = 0;
 };
 struct LibState {
     bool ready = false;
@@ -150,6 +154,8 @@ extern "C" int ort_finalize(void) {
         if (c.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c.comm);
         if (c.d_buf) cudaFree(c.d_buf);
         if (c.d_image_cdf) cudaFree(c.d_image_cdf);
+        if (c.d_list) cudaFree(c.d_list);
+        if (c.d_nlist) cudaFree(c.d_nlist);
         if (c.ev_start) cudaEventDestroy(c.ev_start);
         if (c.ev_traced) cudaEventDestroy(c.ev_traced);
         if (c.ev_reduced) cudaEventDestroy(c.ev_reduced);
@@ -352,35 +358,75 @@ static const int64_t ORT_CHUNK = (int64_t)1 << 31; /* rays per scene per launch 
 /* The ring loop's four-stage kernel with the fp32 culling filter (ort_kernels.cuh): fp64 jobs with
  * the default ring source on scenes whose L2 flat face lies in the aim plane. */
 template <typename R>
-static bool ring_filter_applies(const ort_job& job, const DevScene& s, bool flat) {
+static bool ring_filter_applies(const ort_job& job, const DevScene& s, bool flat, unsigned long long* aim_cut) {
     return sizeof(R) == sizeof(double) && !flat && job.phase == ORT_PHASE_RING && s.ring_shortcut &&
            (job.source_kind == ORT_SRC_POINT || job.source_kind == ORT_SRC_SPOT) &&
-           !(job.flags & ORT_FLAG_NO_FILTER);
+           !(job.flags & ORT_FLAG_NO_FILTER) && ort_ring_aim_cut(s, aim_cut);
 }
-static int enqueue_ring_filter(DeviceCtx& c, const ort_job& job, const DevScene& s, int nscenes, int64_t first,
-                               int64_t n, unsigned long long* d_img, unsigned long long* d_cnt, int64_t* launches) {
-    typedef void (*kern_t)(const DevSceneT<double>, const DevSceneT<float>, const DevJob, unsigned long long*,
-                           unsigned long long*);
-    kern_t k = (job.flags & ORT_FLAG_VERIFY_FILTER) ? ort_trace_ring_filter_kernel<true>
-                                                    : ort_trace_ring_filter_kernel<false>;
-    size_t smem = (size_t)ORT_WPB * sizeof(RingFilterShared);
-    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, ORT_TPB, smem));
-    if (occ < 1) occ = 1;
-    int grid = c.num_sms * occ;
+/* Slice of the ray range per cull/survivors launch pair: long enough that the tail of a launch
+ * is < 1 % of it, short enough that the list of ray indices stays a few hundred MB. */
+static const int64_t ORT_RING_SLICE = (int64_t)1 << 29;
+
+static int enqueue_ring_filter(DeviceCtx& c, const ort_job& job, const DevScene& s, unsigned long long aim_cut,
+                               int nscenes, int64_t first, int64_t n, unsigned long long* d_img,
+                               unsigned long long* d_cnt, int64_t* launches) {
+    const bool verify = (job.flags & ORT_FLAG_VERIFY_FILTER) != 0;
+    auto cull = verify ? ort_ring_cull_kernel<true> : ort_ring_cull_kernel<false>;
+    auto surv = verify ? ort_ring_survivors_kernel<true> : ort_ring_survivors_kernel<false>;
+    const size_t smem_cull = (size_t)ORT_WPB * sizeof(SlimQueue);
+    const size_t smem_surv = (size_t)ORT_WPB * sizeof(WarpQueue<double>);
+    CK(cudaFuncSetAttribute(cull, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cull));
+    CK(cudaFuncSetAttribute(surv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_surv));
+    int occ_cull = 0, occ_surv = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_cull, cull, ORT_TPB, smem_cull));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_surv, surv, ORT_TPB, smem_surv));
+    if (occ_cull < 1) occ_cull = 1;
+    if (occ_surv < 1) occ_surv = 1;
+
+    /* the list holds the rays that pass stage A at most: Binomial(slice, p), p = aim_cut / 2^64 */
+    const int64_t slice = n < ORT_RING_SLICE ? n : ORT_RING_SLICE;
+    const double p_pass = (double)aim_cut * (1.0 / 18446744073709551616.0);
+    double want_cap = (double)slice * p_pass + 8.0 * std::sqrt((double)slice) + 1024.0;
+    if (want_cap > (double)slice) want_cap = (double)slice;
+    const size_t capacity = (size_t)want_cap;
+    const int64_t nslices = (n + ORT_RING_SLICE - 1) / ORT_RING_SLICE;
+    if (c.list_cap < capacity) {
+        if (c.d_list) CK(cudaFree(c.d_list));
+        c.d_list = nullptr;
+        c.list_cap = 0;
+        CK(cudaMalloc(&c.d_list, capacity * sizeof(uint32_t)));
+        c.list_cap = capacity;
+    }
+    if (c.nlist_cap < (size_t)nslices) {
+        if (c.d_nlist) CK(cudaFree(c.d_nlist));
+        c.d_nlist = nullptr;
+        c.nlist_cap = 0;
+        CK(cudaMalloc(&c.d_nlist, (size_t)nslices * sizeof(unsigned)));
+        c.nlist_cap = (size_t)nslices;
+    }
+    CK(cudaMemsetAsync(c.d_nlist, 0, (size_t)nslices * sizeof(unsigned), c.stream));
+
     DevSceneT<float> sf;
     ort_scene_to_float(s, sf);
-    for (int64_t off = 0; off < n; off += ORT_CHUNK) {
-        int64_t m = n - off < ORT_CHUNK ? n - off : ORT_CHUNK;
+    int64_t k = 0;
+    for (int64_t off = 0; off < n; off += ORT_RING_SLICE, ++k) {
+        int64_t m = n - off < ORT_RING_SLICE ? n - off : ORT_RING_SLICE;
         DevJob dj;
         ort_make_dev_job(job, nscenes, first + off, m, dj);
         int64_t batches = (m + 31) / 32;
         int64_t want = (batches + ORT_WPB - 1) / ORT_WPB;
+        int grid = c.num_sms * occ_cull;
         int gsz = (int)(want < grid ? (want > 0 ? want : 1) : grid);
-        k<<<gsz, ORT_TPB, smem, c.stream>>>(s, sf, dj, d_img, d_cnt);
+        cull<<<gsz, ORT_TPB, smem_cull, c.stream>>>(sf, dj, aim_cut, c.d_list, c.d_nlist + k, (unsigned)capacity, d_cnt);
         CK(cudaGetLastError());
-        ++*launches;
+        /* the list length is only known on the device: size the grid for the expectation */
+        double expect = verify ? (double)m * p_pass : (double)m * p_pass * 0.15;
+        int64_t sb = ((int64_t)expect / 32 + ORT_WPB) / ORT_WPB;
+        int sgrid = c.num_sms * occ_surv;
+        int sgsz = (int)(sb < sgrid ? (sb > 0 ? sb : 1) : sgrid);
+        surv<<<sgsz, ORT_TPB, smem_surv, c.stream>>>(s, sf, dj, c.d_list, c.d_nlist + k, (unsigned)capacity, d_img, d_cnt);
+        CK(cudaGetLastError());
+        *launches += 2;
     }
     return ORT_OK;
 }
@@ -419,8 +465,9 @@ static int enqueue_trace_t(DeviceCtx& c, const ort_job& job, const std::vector<D
     for (int sc = 0; sc < nscenes; ++sc) {
         DevSceneT<R> dsr;
         scene_as(ds[sc], dsr);
-        if (ring_filter_applies<R>(job, ds[sc], flat)) {
-            int rc = enqueue_ring_filter(c, job, ds[sc], nscenes, first, n, d_img + (size_t)sc * ORT_IMG_BINS,
+        unsigned long long aim_cut = 0;
+        if (ring_filter_applies<R>(job, ds[sc], flat, &aim_cut)) {
+            int rc = enqueue_ring_filter(c, job, ds[sc], aim_cut, nscenes, first, n, d_img + (size_t)sc * ORT_IMG_BINS,
                                          d_cnt + (size_t)sc * ORT_NSTATUS, launches);
             if (rc != ORT_OK) return rc;
             continue;
@@ -528,7 +575,7 @@ extern "C" int ort_trace(const ort_job* job, const ort_scene* scenes, int nscene
         CK(cudaStreamSynchronize(g.devs[d].stream));
     }
     if (image) memcpy(image, g.h_pinned, img_elems * 8);
-    bool trapped = false;
+    bool trapped = false, list_overflow = false;
     for (int s = 0; s < nscenes; ++s) {
         const unsigned long long* h = g.h_pinned + img_elems + (size_t)s * ORT_NSTATUS;
         int64_t l = 0;
@@ -538,6 +585,7 @@ extern "C" int ort_trace(const ort_job* job, const ort_scene* scenes, int nscene
         }
         if (lost) lost[s] = l;
         if (h[ORT_ST_L3_S3_MISS] || h[ORT_ST_TAUINT_MISS] || h[ORT_ST_SOURCE_MISS]) trapped = true;
+        if (h[ORT_FILTER_SLOT_OVERFLOW]) list_overflow = true;
     }
     if (timing) {
         double tmax = 0.0, rmax = 0.0;
@@ -563,6 +611,11 @@ extern "C" int ort_trace(const ort_job* job, const ort_scene* scenes, int nscene
         timing->d2h_bytes = (int64_t)d2h;
         timing->wall_seconds =
             std::chrono::duration<double>(std::chrono::steady_clock::now() - w0).count();
+    }
+    if (list_overflow) {
+        ort_set_error("ort_trace: the ring filter's survivor list overflowed (results incomplete); "
+                      "retry with ORT_FLAG_NO_FILTER");
+        return ORT_ECUDA;
     }
     if (trapped) {
         ort_set_error("trace hit a reference `error stop` invariant (status 18, 24 or 26); results returned");

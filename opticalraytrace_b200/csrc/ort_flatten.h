@@ -109,6 +109,28 @@ inline void ort_flatten_scene(const ort_scene& s, const ort_job& j, DevScene& d)
                        std::fabs(d.l2_flat_z - d.l2_fb) <= 4e-16 * std::fabs(d.l2_fb)) ? 1 : 0;
 }
 
+/* Stage A of the ring loop on the raw draw: the smallest 64-bit word w for which
+ * u2 = (w >> 11) 2^-53 fails L2's aperture test exactly as the kernels evaluate it,
+ * u2 * lens_r2 > l2_radius2 (ort_ring_aims_outside_aperture).  The expression is monotone in w,
+ * so a bisection finds it.  Returns false when no draw fails (then the caller does not use the
+ * integer test). */
+inline bool ort_ring_aim_cut(const DevScene& d, unsigned long long* cut) {
+    auto outside = [&](unsigned long long bits) {
+        double u2 = (double)bits * (1.0 / 9007199254740992.0);
+        return u2 * d.lens_r2 > d.l2_radius2;
+    };
+    const unsigned long long top = (1ull << 53) - 1;
+    if (!outside(top)) return false;
+    unsigned long long lo = 0, hi = top; /* outside(hi) holds */
+    while (lo < hi) {
+        unsigned long long mid = lo + ((hi - lo) >> 1);
+        if (outside(mid)) hi = mid;
+        else lo = mid + 1;
+    }
+    *cut = lo << 11;
+    return true;
+}
+
 /* fp32 variant: every hoisted scalar is computed in double above and rounded once here.
  * DevSceneT<R> is N reals followed by 4 int32, in the same order for every R. */
 inline void ort_scene_to_float(const DevScene& s, DevSceneT<float>& d) {

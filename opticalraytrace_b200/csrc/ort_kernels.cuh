@@ -294,24 +294,29 @@ ort_trace_kernel(const __grid_constant__ DevSceneT<R> S, const __grid_constant__
 }
 
 /* ---- ring loop with the fp32 culling filter (ort_ring_filter) ------------------------------
- * Four stages: A draws the aim point and drops the rays aimed outside L2's aperture; F runs the
- * single-precision filter on the survivors and counts the rays it can call; B is the ordinary fp64
- * stage for the few the filter hands on (the ones that reach L3, and the near-calls); C as before.
+ * Two kernels per slice of the ray range, because 99 % of the ring rays never need fp64 and a
+ * kernel that contains the fp64 stages pays their 80 registers on every warp:
+ *
+ *   ort_ring_cull_kernel       integer + fp32 only, ~40 registers, 6 blocks (48 warps) per SM.
+ *       A: Philox block 1 on the ray index; the aim-point aperture test on the raw 64-bit draw
+ *          (aim_cut, see ort_ring_aim_cut) ends 69 % of the rays;
+ *       F: the single-precision filter on the compacted survivors; the rays it can call are counted,
+ *          the others (they reach L3, or a decision was too close) are appended to a list of ray
+ *          indices in global memory -- 4 bytes per listed ray, ~0.2 % .. 4 % of the rays.
+ *   ort_ring_survivors_kernel  the ordinary fp64 stages B and C over that list (the draws are
+ *       regenerated from the ray index).
+ *
  * Used when the scene has ring_shortcut, precision is 64 and ORT_FLAG_NO_FILTER is not set; the
- * results are identical to ort_trace_kernel's.
- * VERIFY (ORT_FLAG_VERIFY_FILTER): F passes every ray on and B compares the filter's verdict with
- * what fp64 finds: counters[ORT_FILTER_SLOT_CALLED] = rays the filter called,
- * counters[ORT_FILTER_SLOT_WRONG] = calls that disagree with fp64 (must stay 0). */
+ * results are identical to ort_trace_kernel's.  VERIFY (ORT_FLAG_VERIFY_FILTER): F lists every ray
+ * and the survivors kernel compares the filter's verdict with what fp64 finds:
+ * counters[ORT_FILTER_SLOT_CALLED] = rays the filter called, counters[ORT_FILTER_SLOT_WRONG] =
+ * calls that disagree with fp64 (must stay 0). */
 struct SlimQueue {
-    double a[ORT_QCAP], b[ORT_QCAP];
+    unsigned long long a[ORT_QCAP], b[ORT_QCAP]; /* the raw 64 bits behind u2 and u3 */
     uint32_t id[ORT_QCAP];
 };
-struct RingFilterShared {
-    SlimQueue q0, q1;
-    WarpQueue<double> q2;
-};
-__device__ __forceinline__ void ort_slim_push(SlimQueue& q, int& n, bool alive, double a, double b, uint32_t id,
-                                              unsigned lane) {
+__device__ __forceinline__ void ort_slim_push(SlimQueue& q, int& n, bool alive, unsigned long long a,
+                                              unsigned long long b, uint32_t id, unsigned lane) {
     unsigned m = __ballot_sync(ORT_FULL, alive);
     if (alive) {
         int p = n + __popc(m & ((1u << lane) - 1u));
@@ -323,7 +328,8 @@ __device__ __forceinline__ void ort_slim_push(SlimQueue& q, int& n, bool alive, 
     n += __popc(m);
     __syncwarp();
 }
-__device__ __forceinline__ bool ort_slim_pop(SlimQueue& q, int& n, double& a, double& b, uint32_t& id, unsigned lane) {
+__device__ __forceinline__ bool ort_slim_pop(SlimQueue& q, int& n, unsigned long long& a, unsigned long long& b,
+                                             uint32_t& id, unsigned lane) {
     int cnt = n < 32 ? n : 32;
     int base = n - cnt;
     bool act = (int)lane < cnt;
@@ -339,77 +345,129 @@ __device__ __forceinline__ bool ort_slim_pop(SlimQueue& q, int& n, double& a, do
     return act;
 }
 
+#ifndef ORT_CULL_MIN_BLOCKS
+#define ORT_CULL_MIN_BLOCKS 6
+#endif
+/* list[0 .. *nlist) receives the ray indices (relative to J.first_ray) handed to fp64; entries that
+ * would not fit in `capacity` are counted in counters[ORT_FILTER_SLOT_OVERFLOW] instead, which
+ * ort_trace reports as an error (the launcher sizes the list 16 sigma above its expectation). */
 template <bool VERIFY>
-__global__ void __launch_bounds__(ORT_TPB, ORT_MIN_BLOCKS)
-ort_trace_ring_filter_kernel(const __grid_constant__ DevSceneT<double> S, const __grid_constant__ DevSceneT<float> F,
-                             const __grid_constant__ DevJob J, unsigned long long* __restrict__ img,
-                             unsigned long long* __restrict__ counters) {
+__global__ void __launch_bounds__(ORT_TPB, ORT_CULL_MIN_BLOCKS)
+ort_ring_cull_kernel(const __grid_constant__ DevSceneT<float> F, const __grid_constant__ DevJob J,
+                     const unsigned long long aim_cut, uint32_t* __restrict__ list, unsigned* __restrict__ nlist,
+                     const unsigned capacity, unsigned long long* __restrict__ counters) {
     extern __shared__ __align__(16) unsigned char ort_smem[];
-    RingFilterShared& ws = reinterpret_cast<RingFilterShared*>(ort_smem)[threadIdx.x >> 5];
+    SlimQueue& q0 = reinterpret_cast<SlimQueue*>(ort_smem)[threadIdx.x >> 5];
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t nwarps = gridDim.x * ORT_WPB;
     const uint32_t gwarp = blockIdx.x * ORT_WPB + (threadIdx.x >> 5);
     const uint32_t nrays = (uint32_t)J.nrays;
     const uint32_t nbatches = (nrays + 31u) >> 5;
 
+    unsigned c9 = 0, c10 = 0, c11 = 0, c12 = 0, c13 = 0, c14 = 0;
+    int n0 = 0;
+    uint32_t b = gwarp;
+    for (;;) {
+        const bool emit = n0 < 32 && b < nbatches;
+        if (!emit && n0 == 0) break;
+        if (emit) {
+            uint32_t id = b * 32u + lane;
+            b += nwarps;
+            bool pass = false;
+            unsigned long long wa = 0, wb = 0;
+            if (id < nrays) {
+                OrtRng g = ort_make_rng_prod(J, id);
+                uint32_t w[4];
+                ort_philox4x32_10(g.r0, g.r1, g.phase, 1u, g.k0, g.k1, w, g.rk);
+                wa = ((unsigned long long)w[1] << 32) | w[0];
+                wb = ((unsigned long long)w[3] << 32) | w[2];
+                pass = wa < aim_cut;
+                c9 += !pass;
+            }
+            ort_slim_push(q0, n0, pass, wa, wb, id, lane);
+        } else {
+            unsigned long long wa = 0, wb = 0;
+            uint32_t id = 0;
+            bool act = ort_slim_pop(q0, n0, wa, wb, id, lane);
+            int st = -1;
+            if (act) {
+                OrtRng g = ort_make_rng_prod(J, id);
+                st = VERIFY ? 0 : ort_ring_filter(F, J, g, ortf_uniform((uint32_t)(wa >> 32)), ortf_uniform((uint32_t)(wb >> 32)));
+                c10 += st == ORT_ST_L2_SPHERE_MISS;
+                c11 += st == ORT_ST_L2_CURVED_REFLECT;
+                c12 += st == ORT_ST_L3_IRIS_BEFORE;
+                c13 += st == ORT_ST_L3_S1_MISS;
+                c14 += st == ORT_ST_L3_APERTURE;
+            }
+            unsigned m = __ballot_sync(ORT_FULL, st == 0);
+            if (m) {
+                unsigned base = 0;
+                if (lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(nlist, (unsigned)__popc(m));
+                base = __shfl_sync(ORT_FULL, base, __ffs(m) - 1);
+                if (st == 0) {
+                    unsigned p = base + __popc(m & ((1u << lane) - 1u));
+                    if (p < capacity) list[p] = id;
+                    else atomicAdd(counters + ORT_FILTER_SLOT_OVERFLOW, 1ull);
+                }
+            }
+        }
+    }
+    /* per-lane tallies -> one atomic per status and warp */
+    c9 = __reduce_add_sync(ORT_FULL, c9);
+    c10 = __reduce_add_sync(ORT_FULL, c10);
+    c11 = __reduce_add_sync(ORT_FULL, c11);
+    c12 = __reduce_add_sync(ORT_FULL, c12);
+    c13 = __reduce_add_sync(ORT_FULL, c13);
+    c14 = __reduce_add_sync(ORT_FULL, c14);
+    unsigned mine = lane == 9 ? c9 : lane == 10 ? c10 : lane == 11 ? c11 : lane == 12 ? c12 : lane == 13 ? c13 : lane == 14 ? c14 : 0u;
+    if (mine) atomicAdd(counters + lane, (unsigned long long)mine);
+}
+
+/* fp64 stages B and C over the listed rays */
+template <bool VERIFY>
+__global__ void __launch_bounds__(ORT_TPB, ORT_MIN_BLOCKS)
+ort_ring_survivors_kernel(const __grid_constant__ DevSceneT<double> S, const __grid_constant__ DevSceneT<float> F,
+                          const __grid_constant__ DevJob J, const uint32_t* __restrict__ list,
+                          const unsigned* __restrict__ nlist, const unsigned capacity,
+                          unsigned long long* __restrict__ img, unsigned long long* __restrict__ counters) {
+    extern __shared__ __align__(16) unsigned char ort_smem[];
+    WarpQueue<double>& q = reinterpret_cast<WarpQueue<double>*>(ort_smem)[threadIdx.x >> 5];
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t nwarps = gridDim.x * ORT_WPB;
+    const uint32_t gwarp = blockIdx.x * ORT_WPB + (threadIdx.x >> 5);
+    const uint32_t total = *nlist < capacity ? *nlist : capacity;
+    const uint32_t nbatches = (total + 31u) >> 5;
+
     OrtCounts cnt;
 #pragma unroll
     for (int k = 0; k < ORT_NSTATUS; ++k) cnt.c[k] = 0;
-    int n0 = 0, n1 = 0, n2 = 0;
+    int n2 = 0;
     uint32_t b = gwarp;
     for (;;) {
-        int stage;
-        if (n2 >= 32) stage = 3;
-        else if (n1 >= 32) stage = 2;
-        else if (n0 >= 32) stage = 1;
-        else if (b < nbatches) stage = 0;
-        else if (n0 > 0) stage = 1; /* drain from the top so the later stages run full */
-        else if (n1 > 0) stage = 2;
-        else if (n2 > 0) stage = 3;
-        else break;
-
+        const bool take = n2 < 32 && b < nbatches;
+        if (!take && n2 == 0) break;
+        OrtRayT<double> r;
         uint32_t id = 0;
-        if (stage == 0) {
-            id = b * 32u + lane;
+        if (take) {
+            uint32_t i = b * 32u + lane;
             b += nwarps;
-            int st = -1;
-            double u2 = 0.0, u3 = 0.0;
-            if (id < nrays) {
+            int st = -1, verdict = 0;
+            if (i < total) {
+                id = list[i];
                 OrtRng g = ort_make_rng_prod(J, id);
-                ort_draw2(g, 1, &u2, &u3);
-                st = ort_ring_aims_outside_aperture(S, u2) ? ORT_ST_L2_APERTURE : 0;
-            }
-            ort_slim_push(ws.q0, n0, st == 0, u2, u3, id, lane);
-            ort_count<ORT_ST_L2_APERTURE>(cnt, st);
-        } else if (stage == 1) {
-            double u2 = 0.0, u3 = 0.0;
-            bool act = ort_slim_pop(ws.q0, n0, u2, u3, id, lane);
-            int st = -1;
-            if (act) {
-                OrtRng g = ort_make_rng_prod(J, id);
-                st = VERIFY ? 0 : ort_ring_filter(F, J, g, (float)u2, (float)u3);
-            }
-            ort_slim_push(ws.q1, n1, st == 0, u2, u3, id, lane);
-            ort_count_b(cnt, st);
-        } else if (stage == 2) {
-            OrtRayT<double> r;
-            bool act = ort_slim_pop(ws.q1, n1, r.px, r.py, id, lane);
-            int st = -1;
-            if (act) {
-                OrtRng g = ort_make_rng_prod(J, id);
-                int verdict = VERIFY ? ort_ring_filter(F, J, g, (float)r.px, (float)r.py) : 0;
+                ort_draw2(g, 1, &r.px, &r.py);
+                if (VERIFY) verdict = ort_ring_filter(F, J, g, (float)r.px, (float)r.py);
                 r.pz = r.dx = r.dy = r.dz = 0.0;
                 st = ort_stage_b<ORT_PHASE_RING, ORT_SRC_POINT>(S, J, g, r);
-                if (VERIFY) {
-                    cnt.c[ORT_FILTER_SLOT_CALLED] += __popc(__ballot_sync(__activemask(), verdict > 0));
-                    cnt.c[ORT_FILTER_SLOT_WRONG] += __popc(__ballot_sync(__activemask(), verdict > 0 && verdict != st));
-                }
             }
-            ort_q_push(ws.q2, n2, st == 0, r, id, lane);
+            if (VERIFY) {
+                cnt.c[ORT_FILTER_SLOT_CALLED] += __popc(__ballot_sync(ORT_FULL, verdict > 0));
+                cnt.c[ORT_FILTER_SLOT_WRONG] += __popc(__ballot_sync(ORT_FULL, verdict > 0 && verdict != st));
+            }
+            ort_q_push(q, n2, st == 0, r, id, lane);
             ort_count_b(cnt, st);
         } else {
-            OrtRayT<double> r;
-            bool act = ort_q_pop(ws.q2, n2, r, id, lane);
+            bool act = ort_q_pop(q, n2, r, id, lane);
             int st = -1, xp = 0, yp = 0;
             if (act) {
                 OrtRng g = ort_make_rng_prod(J, id);

@@ -1114,64 +1114,61 @@ ORT_HD float ortf_uniform(uint32_t hi) {
     return (float)(hi >> 8) * 5.9604644775390625e-8f;
 }
 
-/* sphere intersection with margins: 1 hit (t set), 0 miss, -1 too close to call */
-ORT_HD int ortf_hit_sphere(const OrtRayT<float>& r, float cx, float cy, float cz, float R2, float* t) {
+/* The helpers below do not branch on a near-call: they OR it into `unc` and carry on with whatever
+ * fp32 says; the caller leaves at the ray's first definite end and answers 0 (ask fp64) when
+ * anything before it was too close.  One exit per possible end, everything else straight-line. */
+
+/* sphere intersection: false = miss.  The outcome hangs on the signs of disc, h and c
+ * (ort_pick_root_unit); any of them within the margin of zero sets unc. */
+ORT_HD bool ortf_hit_sphere(const OrtRayT<float>& r, float cx, float cy, float cz, float R2, float* t, bool& unc) {
     float lx = r.px - cx, ly = r.py - cy, lz = r.pz - cz;
     float h = fmaf(r.dx, lx, fmaf(r.dy, ly, r.dz * lz));
     float l2 = fmaf(lx, lx, fmaf(ly, ly, lz * lz));
     float c = l2 - R2;
     float disc = fmaf(h, h, -c);
     float tol = ORT_FILTER_TOL * (l2 + R2);
-    /* the outcome hangs on the signs of disc, h and c (ort_pick_root_unit) */
-    if (!(fabsf(disc) > tol) || !(h * h > tol) || !(fabsf(c) > tol)) return -1;
-    if (disc < 0.0f) return 0;
+    unc |= !(fminf(fminf(fabsf(disc), h * h), fabsf(c)) > tol);
     bool hpos = h > 0.0f;
-    if (hpos && c > 0.0f) return 0;
+    if (disc < 0.0f || (hpos && c > 0.0f)) return false;
     float sq = ortf_sqrt(disc);
     float q = hpos ? -(h + sq) : (sq - h);
     *t = (!hpos && c < 0.0f) ? q : c * ortf_rcp(q);
-    return 1;
+    return true;
 }
-/* dielectric interface with margins: 0 refracted, 1 reflected, -1 too close to call */
-ORT_HD int ortf_interface(OrtRayT<float>& r, float nx, float ny, float nz, const DevIfaceT<float>& f, float u) {
+/* dielectric interface: true = reflected; the new direction is written either way.  Near normal
+ * incidence (the reference switches to R = 0 at EXACTLY cos = 1), near the critical angle and a
+ * draw within the margin of R set unc. */
+ORT_HD bool ortf_interface(OrtRayT<float>& r, float nx, float ny, float nz, const DevIfaceT<float>& f, float u,
+                           bool& unc) {
     float c = fmaf(nx, r.dx, fmaf(ny, r.dy, nz * r.dz));
     float costt = fabsf(c);
     float s2 = fmaf(-costt, costt, 1.0f);
     float ct2 = fmaf(-f.eta2, s2, 1.0f);
-    /* near normal incidence the reference switches to R = 0 at EXACTLY cos = 1; near the critical
-     * angle the branch itself is at stake */
-    if (!(s2 > 1e-4f) || !(fabsf(ct2) > ORT_FILTER_TOL)) return -1;
-    bool reflect = true;
-    float A = 0.0f;
-    if (ct2 > 0.0f) {
-        float cost2 = ortf_sqrt(ct2);
-        float ec = f.eta * costt, e2 = f.eta * cost2;
-        A = ec - cost2;
-        float B = ec + cost2, C = e2 - costt, D = e2 + costt;
-        float B2 = B * B, D2 = D * D, den = B2 * D2;
-        float num = fmaf(A * A, D2, (C * C) * B2);
-        float lhs = (u + u) * den;
-        if (!(fabsf(lhs - num) > (2.0f * ORT_FILTER_TOL) * den)) return -1; /* |u - R| < tol */
-        reflect = !(lhs > num);
-    }
-    if (reflect) {
-        float k = -2.0f * c;
-        r.dx = fmaf(k, nx, r.dx);
-        r.dy = fmaf(k, ny, r.dy);
-        r.dz = fmaf(k, nz, r.dz);
-        return 1;
-    }
-    float k = (c < 0.0f) ? A : -A;
-    r.dx = fmaf(f.eta, r.dx, k * nx);
-    r.dy = fmaf(f.eta, r.dy, k * ny);
-    r.dz = fmaf(f.eta, r.dz, k * nz);
-    return 0;
+    float cost2 = ortf_sqrt(fmaxf(ct2, 0.0f));
+    float ec = f.eta * costt, e2 = f.eta * cost2;
+    float A = ec - cost2, B = ec + cost2, C = e2 - costt, D = e2 + costt;
+    float B2 = B * B, D2 = D * D, den = B2 * D2;
+    float num = fmaf(A * A, D2, (C * C) * B2);
+    float lhs = (u + u) * den;
+    bool tir = !(ct2 > 0.0f);
+    unc |= !(s2 > 1e-4f) || !(fabsf(ct2) > ORT_FILTER_TOL) ||
+           (!tir && !(fabsf(lhs - num) > (2.0f * ORT_FILTER_TOL) * den)); /* |u - R| < tol */
+    bool reflect = tir || !(lhs > num);
+    /* reflect: d - 2c n;  refract: eta d + k n, k = +-(eta cos_i - cos_t) opposing the normal */
+    float a = reflect ? 1.0f : f.eta;
+    float k = reflect ? -2.0f * c : ((c < 0.0f) ? A : -A);
+    r.dx = fmaf(a, r.dx, k * nx);
+    r.dy = fmaf(a, r.dy, k * ny);
+    r.dz = fmaf(a, r.dz, k * nz);
+    return reflect;
 }
 
 /* (u2, u3): the aim-point uniforms the caller already holds; the other draws are regenerated */
 ORT_HD int ort_ring_filter(const DevSceneT<float>& F, const DevJob& J, const OrtRng& g, float u2, float u3) {
-    uint32_t w[4];
+    /* both Philox blocks up front: four independent multiply chains in flight instead of two */
+    uint32_t w[4], v[4];
     ort_philox4x32_10(g.r0, g.r1, g.phase, 0u, g.k0, g.k1, w, g.rk);
+    ort_philox4x32_10(g.r0, g.r1, g.phase, 2u, g.k0, g.k1, v, g.rk);
     float u0 = ortf_uniform(w[1]), u1 = ortf_uniform(w[3]);
     /* ring source, ort_source_ring_u */
     OrtRayT<float> r;
@@ -1183,9 +1180,9 @@ ORT_HD int ort_ring_filter(const DevSceneT<float>& F, const DevJob& J, const Ort
     float q = F.ellipse ? r.py * F.ra_over_rb : r.py;
     r.pz = F.bcz + ortf_sqrt(fmaf(-q, q, F.ra2));
     float aim2 = u2 * F.lens_r2;
-    /* L2's aperture, decided in stage A on the fp64 u2; the recomputation in ort_l2_enter can only
-     * differ at the very edge */
-    if (!(aim2 < F.l2_radius2 * (1.0f - ORT_FILTER_TOL))) return 0;
+    /* L2's aperture was decided in stage A on the fp64 u2; the recomputation in ort_l2_enter can
+     * only differ at the very edge */
+    bool unc = !(aim2 < F.l2_radius2 * (1.0f - ORT_FILTER_TOL));
     float rl = ortf_sqrt(aim2);
     ortf_sincos_turn(u3, &s, &c);
     float ax = rl * c, ay = rl * s;
@@ -1198,35 +1195,28 @@ ORT_HD int ort_ring_filter(const DevSceneT<float>& F, const DevJob& J, const Ort
     r.px = ax;
     r.py = ay;
     r.pz = F.l2_flat_z;
-    /* L2, ort_l2_body */
-    ort_philox4x32_10(g.r0, g.r1, g.phase, 2u, g.k0, g.k1, w, g.rk);
-    int k = ortf_interface(r, F.l2_fnx, F.l2_fny, F.l2_fnz, F.l2_in, ortf_uniform(w[1]));
-    if (k < 0) return 0; /* a reflection here is not tested by the reference: the ray goes on */
+    /* L2, ort_l2_body; a reflection at the flat face is not tested by the reference: the ray goes on */
+    (void)ortf_interface(r, F.l2_fnx, F.l2_fny, F.l2_fnz, F.l2_in, ortf_uniform(v[1]), unc);
     float t;
-    k = ortf_hit_sphere(r, F.l2_cx, F.l2_cy, F.l2_cz, F.l2_R2, &t);
-    if (k < 0) return 0;
-    if (k == 0) return ORT_ST_L2_SPHERE_MISS;
+    if (!ortf_hit_sphere(r, F.l2_cx, F.l2_cy, F.l2_cz, F.l2_R2, &t, unc)) return unc ? 0 : ORT_ST_L2_SPHERE_MISS;
     ort_advance(r, t);
-    k = ortf_interface(r, (F.l2_cx - r.px) * F.l2_invR, (F.l2_cy - r.py) * F.l2_invR, (F.l2_cz - r.pz) * F.l2_invR,
-                       F.l2_out, ortf_uniform(w[3]));
-    if (k < 0) return 0;
-    if (k == 1) return ORT_ST_L2_CURVED_REFLECT;
+    if (ortf_interface(r, (F.l2_cx - r.px) * F.l2_invR, (F.l2_cy - r.py) * F.l2_invR, (F.l2_cz - r.pz) * F.l2_invR,
+                       F.l2_out, ortf_uniform(v[3]), unc))
+        return unc ? 0 : ORT_ST_L2_CURVED_REFLECT;
     /* L3 up to its aperture, ort_l3_enter */
     if (J.iris_before) {
-        if (!(fabsf(r.dz) > ORT_FILTER_TOL)) return 0;
+        unc |= !(fabsf(r.dz) > ORT_FILTER_TOL);
         float ti = (F.l3_iris1_z - r.pz) * ortf_rcp(r.dz);
         float x = fmaf(r.dx, ti, r.px), y = fmaf(r.dy, ti, r.py);
         float rho2 = fmaf(x, x, y * y);
-        if (!(fabsf(rho2 - F.l3_iris_r2) > ORT_FILTER_TOL * (rho2 + F.l3_iris_r2))) return 0;
-        if (rho2 > F.l3_iris_r2) return ORT_ST_L3_IRIS_BEFORE;
+        unc |= !(fabsf(rho2 - F.l3_iris_r2) > ORT_FILTER_TOL * (rho2 + F.l3_iris_r2));
+        if (rho2 > F.l3_iris_r2) return unc ? 0 : ORT_ST_L3_IRIS_BEFORE;
     }
-    k = ortf_hit_sphere(r, F.l3_c1x, F.l3_c1y, F.l3_c1z, F.l3_R1_2, &t);
-    if (k < 0) return 0;
-    if (k == 0) return ORT_ST_L3_S1_MISS;
+    if (!ortf_hit_sphere(r, F.l3_c1x, F.l3_c1y, F.l3_c1z, F.l3_R1_2, &t, unc)) return unc ? 0 : ORT_ST_L3_S1_MISS;
     ort_advance(r, t);
     float rho2 = fmaf(r.px, r.px, r.py * r.py);
-    if (!(fabsf(rho2 - F.l3_radius2) > ORT_FILTER_TOL * (rho2 + F.l3_radius2))) return 0;
-    return rho2 > F.l3_radius2 ? ORT_ST_L3_APERTURE : 0;
+    unc |= !(fabsf(rho2 - F.l3_radius2) > ORT_FILTER_TOL * (rho2 + F.l3_radius2));
+    return (!unc && rho2 > F.l3_radius2) ? ORT_ST_L3_APERTURE : 0;
 }
 
 /* -------------------------------------------------------------------------------------------

@@ -59,6 +59,14 @@ def harness():
         v = np.zeros(n, np.int32)
         shortcut = H.hh_ring_filter(C.byref(job), C.byref(scene), n, v.ctypes.data)
         return v, bool(shortcut)
+    H.hh_ring_aim_cut.argtypes = [C.POINTER(abi.Job), C.POINTER(abi.Scene), C.POINTER(C.c_int)]
+    H.hh_ring_aim_cut.restype = C.c_uint64
+
+    def ring_aim_cut(job, scene):
+        have = C.c_int(0)
+        cut = H.hh_ring_aim_cut(C.byref(job), C.byref(scene), C.byref(have))
+        return int(cut), bool(have.value)
+    run.ring_aim_cut = ring_aim_cut
     run.set_image_source = set_image_source
     run.ring_filter = ring_filter
     return run

@@ -97,3 +97,12 @@ extern "C" int hh_ring_filter(const ort_job* job, const ort_scene* scene, int64_
     }
     return S.ring_shortcut;
 }
+
+/* the integer form of stage A's aperture test: returns the cut (0 when none exists) */
+extern "C" unsigned long long hh_ring_aim_cut(const ort_job* job, const ort_scene* scene, int* have) {
+    DevScene S;
+    ort_flatten_scene(*scene, *job, S);
+    unsigned long long cut = 0;
+    *have = ort_ring_aim_cut(S, &cut) ? 1 : 0;
+    return cut;
+}

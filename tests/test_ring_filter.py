@@ -96,3 +96,20 @@ def test_cuda_filter_on_random_scenes(ort, orc):
         job.flags |= abi.FLAG_NO_FILTER
         img0, lost0, hist0, _ = ort.trace(job, scene, allow_trap=True)
         assert np.array_equal(hist, hist0) and np.array_equal(img, img0), k
+
+
+def test_integer_aperture_cut_is_the_fp64_test(orc, harness):
+    """Stage A compares the raw 64-bit draw with a cut found by bisection: the draws just below and
+    at the cut must fall on the two sides of the fp64 expression u2 * lens_r2 > radius^2, for every
+    lens of the shipped set (ort_ring_aim_cut, ort_flatten.h)."""
+    for files in (cases.C1, cases.C2, cases.OTHER, cases.OTHER2):
+        scene = cases.scene_for(orc, files, 1)
+        job = abi.default_job(1)
+        cut, have = harness.ring_aim_cut(job, scene)
+        assert have and cut % 2048 == 0
+        lens_r2 = (scene.L2.radius + 10e-3) ** 2
+        rad2 = scene.L2.radius ** 2
+        for w, want in ((cut - 1, False), (cut, True), (cut + 2047, True), (cut - 2048, False)):
+            u2 = float(w >> 11) * 2.0 ** -53
+            assert (u2 * lens_r2 > rad2) is want
+        assert abs((cut >> 11) * 2.0 ** -53 - rad2 / lens_r2) < 1e-15
