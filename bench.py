@@ -19,7 +19,12 @@ sources, so there are no input arrays: the only per-step traffic is the scene (H
            (scene H2D, image D2H inside), barrier + device synchronize on both sides
   roofline: FP64 ALU.  achieved = sum over final ray statuses of count x algorithmic flops
            (SURVEY.md 8(d) stage table) / device time; peak = DFMA micro-kernel
-           measured in this run (MEASURED_PEAKS.json has no FP64 entry).
+           measured in this run (MEASURED_PEAKS.json has no FP64 entry).  For the ring loop the
+           dominant kernel (ort_ring_cull_kernel) decides 99 % of the rays in integer + fp32
+           arithmetic and issues no fp64 at all, so the algorithmic-fp64 fraction says how much
+           of the reference's fp64 work per second is being REPLACED, not how busy the FP64 pipe
+           is; `roofline.issue` adds the bound that kernel actually runs against (warp
+           instructions issued / issue slots, instruction count from the committed ncu profile).
   cpu_baseline / --impl reference: the reference is Fortran and no Fortran compiler exists in
            this image, so the CPU arm is the C++/OpenMP oracle (kind "port": statement-by-
            statement restatement of the Fortran path) on all host cores.
@@ -107,6 +112,20 @@ def flops_by_status(phase, use_bottle=True, iris_before=False, iris_after=False)
     return f
 
 
+def ncu_inst_per_ray(phase_name):
+    """warp instructions per ray of the dominant kernel, from the committed ncu summary:
+    smsp__inst_executed.sum / rays of the profiled launch (tools/gpu_profile.sh uses 2^27)."""
+    path = os.path.join(ROOT, "profiles", "r01_%s_full.txt" % phase_name)
+    try:
+        for line in open(path):
+            f = line.split()
+            if len(f) >= 2 and f[0] == "smsp__inst_executed.sum":
+                return float(f[1]) / float(1 << 27)
+    except OSError:
+        pass
+    return None
+
+
 def ncu_traffic(phase_name):
     """dram__bytes_read.sum + dram__bytes_write.sum of one trace-kernel launch, from the committed
     ncu --set full summary (profiles/r01_<loop>_full.txt); None when absent."""
@@ -122,6 +141,20 @@ def ncu_traffic(phase_name):
     except OSError:
         return None
     return total if seen else None
+
+
+def issue_bound(args, total_rays, dev_s, world, clocks):
+    """The bound the loops actually run against: warp instructions issued per second over the
+    issue slots available (148 SMs x 4 schedulers x SM clock under load)."""
+    ipr = ncu_inst_per_ray(args.phase) if (args.config == 2 and args.precision == 64 and not args.flat) else None
+    mhz = (clocks or {}).get("sm_mhz")
+    if not ipr or not mhz:
+        return None
+    achieved = total_rays * ipr / dev_s
+    peak = 148 * 4 * mhz * 1e6 * world
+    return {"warp_inst_per_ray": ipr, "achieved_inst_per_s": achieved, "peak_inst_per_s": peak,
+            "frac": achieved / peak,
+            "source": "smsp__inst_executed.sum of profiles/r01_%s_full.txt / 2^27 rays" % args.phase}
 
 
 class ClockSampler:
@@ -353,7 +386,8 @@ def main():
                                          "traffic, the image stays in L2",
                          "peak_source": "DFMA micro-kernel measured in this run on rank 0 at %.0f MHz, "
                                         "x n_gpus (MEASURED_PEAKS.json holds no FP64 figure)" % peak_mhz,
-                         "flops_per_launched_ray": flops / (total_rays)},
+                         "flops_per_launched_ray": flops / (total_rays),
+                         "issue": issue_bound(args, total_rays, dev_s, world, clocks)},
             "cpu_baseline": cpu,
             "status_fractions": {abi.STATUS_NAMES[i]: hist[i] / total_rays
                                  for i in range(26) if hist[i]},

@@ -272,13 +272,18 @@ def test_on_axis_ray_sees_zero_reflectance(ort, orc):
 
 def test_more_rays_than_one_launch_holds(ort, orc):
     """Ray ids inside a launch are 32-bit offsets, so ort_trace splits jobs into launches of at
-    most 2^31 rays: a job of 2^32 + 5 rays (three launches) must account for every ray once and
-    equal the sum of its parts, also far out in the ray-index space (1e11-ray jobs, config 5)."""
+    most 2^31 rays (2^29-ray slices, two kernels each, on the ring loop's filter path): a job of
+    2^32 + 5 rays must account for every ray once and equal the sum of its parts, also far out in
+    the ray-index space (1e11-ray jobs, config 5)."""
     scene = cases.scene_for(orc, cases.C2, 1)
     n = (1 << 32) + 5
     first = 10 ** 11
     img, lost, hist, tm = ort.trace(abi.default_job(1, n, first_ray=first), scene)
-    assert tm.kernel_launches == 3 and int(hist.sum()) == n and int(img.sum()) == int(hist[0, 0])
+    assert tm.kernel_launches == 2 * 9 and int(hist.sum()) == n and int(img.sum()) == int(hist[0, 0])
+    img0, lost0, hist0, tm0 = ort.trace(abi.default_job(1, n, first_ray=first, flags=abi.FLAG_NO_FILTER), scene)
+    assert tm0.kernel_launches == 3 and np.array_equal(img0, img) and np.array_equal(hist0, hist)
+    pimg, _, phist, ptm = ort.trace(abi.default_job(2, n, first_ray=first), cases.scene_for(orc, cases.C2, 2))
+    assert ptm.kernel_launches == 3 and int(phist.sum()) == n and int(pimg.sum()) == int(phist[0, 0])
     acc_img, acc_hist = np.zeros_like(img), np.zeros_like(hist)
     for lo, cnt in ((0, 1 << 31), (1 << 31, 1 << 31), (1 << 32, 5)):
         part = ort.trace(abi.default_job(1, cnt, first_ray=first + lo), scene)

@@ -13,7 +13,7 @@ done
 for PH in ring point; do
   ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
       --log-file $OUT/launches_${PH}_${TAG}.csv python bench.py --phase $PH $SMALL > $OUT/ncu_launch_${PH}_${TAG}.log 2>&1
-  ncu --set full --clock-control none --import-source on -k regex:ort_trace_ -s 3 -c 1 \
+  ncu --set full --clock-control none --import-source on -k 'regex:ort_(trace_|ring_cull)' -s 3 -c 1 \
       -f -o $OUT/prof_${PH}_${TAG} python bench.py --phase $PH $SMALL > $OUT/ncu_full_${PH}_${TAG}.log 2>&1
 done
 ls -la $OUT
