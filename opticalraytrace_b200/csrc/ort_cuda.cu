@@ -10,6 +10,7 @@
 #include <nccl.h> /* types and prototypes only: NCCL is dlopen()ed, never linked */
 
 #include <chrono>
+#include <cstdlib>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -388,7 +389,11 @@ static int enqueue_ring_filter(DeviceCtx& c, const ort_job& job, const DevScene&
     const double p_pass = (double)aim_cut * (1.0 / 18446744073709551616.0);
     double want_cap = (double)slice * p_pass + 8.0 * std::sqrt((double)slice) + 1024.0;
     if (want_cap > (double)slice) want_cap = (double)slice;
-    const size_t capacity = (size_t)want_cap;
+    size_t capacity = (size_t)want_cap;
+    if (const char* e = getenv("ORT_TEST_RING_LIST_CAP")) { /* tests only: provoke the overflow report */
+        long v = atol(e);
+        if (v > 0 && (size_t)v < capacity) capacity = (size_t)v;
+    }
     const int64_t nslices = (n + ORT_RING_SLICE - 1) / ORT_RING_SLICE;
     if (c.list_cap < capacity) {
         if (c.d_list) CK(cudaFree(c.d_list));

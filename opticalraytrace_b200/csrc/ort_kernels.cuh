@@ -311,23 +311,14 @@ ort_trace_kernel(const __grid_constant__ DevSceneT<R> S, const __grid_constant__
  * and the survivors kernel compares the filter's verdict with what fp64 finds:
  * counters[ORT_FILTER_SLOT_CALLED] = rays the filter called, counters[ORT_FILTER_SLOT_WRONG] =
  * calls that disagree with fp64 (must stay 0). */
+#ifndef ORT_CULL_UNROLL
+#define ORT_CULL_UNROLL 2 /* batches of 32 rays per stage-A pass */
+#endif
+#define ORT_CULL_QCAP (32 + 32 * ORT_CULL_UNROLL) /* < 32 leftovers + the survivors of one pass */
 struct SlimQueue {
-    unsigned long long a[ORT_QCAP], b[ORT_QCAP]; /* the raw 64 bits behind u2 and u3 */
-    uint32_t id[ORT_QCAP];
+    unsigned long long a[ORT_CULL_QCAP], b[ORT_CULL_QCAP]; /* the raw 64 bits behind u2 and u3 */
+    uint32_t id[ORT_CULL_QCAP];
 };
-__device__ __forceinline__ void ort_slim_push(SlimQueue& q, int& n, bool alive, unsigned long long a,
-                                              unsigned long long b, uint32_t id, unsigned lane) {
-    unsigned m = __ballot_sync(ORT_FULL, alive);
-    if (alive) {
-        int p = n + __popc(m & ((1u << lane) - 1u));
-        ORT_ASSERT(p >= 0 && p < ORT_QCAP);
-        q.a[p] = a;
-        q.b[p] = b;
-        q.id[p] = id;
-    }
-    n += __popc(m);
-    __syncwarp();
-}
 __device__ __forceinline__ bool ort_slim_pop(SlimQueue& q, int& n, unsigned long long& a, unsigned long long& b,
                                              uint32_t& id, unsigned lane) {
     int cnt = n < 32 ? n : 32;
@@ -335,7 +326,7 @@ __device__ __forceinline__ bool ort_slim_pop(SlimQueue& q, int& n, unsigned long
     bool act = (int)lane < cnt;
     if (act) {
         int p = base + lane;
-        ORT_ASSERT(p >= 0 && p < ORT_QCAP);
+        ORT_ASSERT(p >= 0 && p < ORT_CULL_QCAP);
         a = q.a[p];
         b = q.b[p];
         id = q.id[p];
@@ -371,20 +362,37 @@ ort_ring_cull_kernel(const __grid_constant__ DevSceneT<float> F, const __grid_co
         const bool emit = n0 < 32 && b < nbatches;
         if (!emit && n0 == 0) break;
         if (emit) {
-            uint32_t id = b * 32u + lane;
-            b += nwarps;
-            bool pass = false;
-            unsigned long long wa = 0, wb = 0;
-            if (id < nrays) {
-                OrtRng g = ort_make_rng_prod(J, id);
+            /* ORT_CULL_UNROLL batches per pass: that many pairs of independent Philox multiply
+             * chains in flight, and the loop / queue bookkeeping is paid once per pass.  Lanes
+             * past the end of the slice compute a draw nobody uses. */
+            unsigned long long wa[ORT_CULL_UNROLL], wb[ORT_CULL_UNROLL];
+            uint32_t id[ORT_CULL_UNROLL];
+            bool pass[ORT_CULL_UNROLL];
+#pragma unroll
+            for (int k = 0; k < ORT_CULL_UNROLL; ++k) {
+                id[k] = (b + (uint32_t)k * nwarps) * 32u + lane;
+                OrtRng g = ort_make_rng_prod(J, id[k]);
                 uint32_t w[4];
                 ort_philox4x32_10(g.r0, g.r1, g.phase, 1u, g.k0, g.k1, w, g.rk);
-                wa = ((unsigned long long)w[1] << 32) | w[0];
-                wb = ((unsigned long long)w[3] << 32) | w[2];
-                pass = wa < aim_cut;
-                c9 += !pass;
+                wa[k] = ((unsigned long long)w[1] << 32) | w[0];
+                wb[k] = ((unsigned long long)w[3] << 32) | w[2];
+                const bool in = id[k] < nrays;
+                pass[k] = in && wa[k] < aim_cut;
+                c9 += (unsigned)(in && !pass[k]);
             }
-            ort_slim_push(q0, n0, pass, wa, wb, id, lane);
+            b += (uint32_t)ORT_CULL_UNROLL * nwarps;
+            const unsigned below = (1u << lane) - 1u;
+#pragma unroll
+            for (int k = 0; k < ORT_CULL_UNROLL; ++k) {
+                const unsigned m = __ballot_sync(ORT_FULL, pass[k]);
+                if (pass[k]) {
+                    int p = n0 + __popc(m & below);
+                    ORT_ASSERT(p >= 0 && p < ORT_CULL_QCAP);
+                    q0.a[p] = wa[k]; q0.b[p] = wb[k]; q0.id[p] = id[k];
+                }
+                n0 += __popc(m);
+            }
+            __syncwarp();
         } else {
             unsigned long long wa = 0, wb = 0;
             uint32_t id = 0;

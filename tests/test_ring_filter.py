@@ -113,3 +113,18 @@ def test_integer_aperture_cut_is_the_fp64_test(orc, harness):
             u2 = float(w >> 11) * 2.0 ** -53
             assert (u2 * lens_r2 > rad2) is want
         assert abs((cut >> 11) * 2.0 ** -53 - rad2 / lens_r2) < 1e-15
+
+
+@pytest.mark.gpu
+def test_survivor_list_overflow_is_reported(ort, orc, monkeypatch):
+    """The list of rays handed to fp64 is sized 16 sigma above its expectation; if it ever were
+    too small the call must fail loudly instead of dropping rays."""
+    from opticalraytrace_b200.lib import OrtError
+    scene = cases.scene_for(orc, cases.C1, 1)
+    job = abi.default_job(1, 2_000_000)
+    monkeypatch.setenv("ORT_TEST_RING_LIST_CAP", "100")
+    with pytest.raises(OrtError, match="survivor list overflowed"):
+        ort.trace(job, scene)
+    monkeypatch.delenv("ORT_TEST_RING_LIST_CAP")
+    img, lost, hist, _ = ort.trace(job, scene)
+    assert int(hist.sum()) == 2_000_000
