@@ -111,8 +111,11 @@ struct DeviceCtx {
     size_t d_elems = 0;
     ncclComm_t comm = nullptr;
     long long* d_image_cdf = nullptr; /* image source: prefix sums of the ray budget */
-    uint32_t* d_list = nullptr;       /* ring loop: ray indices the fp32 filter hands to fp64 */
+    uint32_t* d_list = nullptr;       /* ring loop: ray indices the fp32 filter hands to fp64, two
+                                         buffers of list_cap entries used alternately */
     size_t list_cap = 0;
+    cudaStream_t stream2 = nullptr;   /* the fp64 survivors kernels run here, behind the cull kernels */
+    cudaEvent_t ev_cull[2] = {nullptr, nullptr}, ev_surv[2] = {nullptr, nullptr};
     unsigned* d_nlist = nullptr;      /* ... and the length of that list, one slot per slice */
     size_t nlist_cap = 0;
 };
@@ -145,6 +148,11 @@ static int ctx_open(DeviceCtx& c, int dev) {
     CK(cudaEventCreate(&c.ev_traced));
     CK(cudaEventCreate(&c.ev_reduced));
     CK(cudaEventCreate(&c.ev_copied));
+    CK(cudaStreamCreateWithFlags(&c.stream2, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CK(cudaEventCreateWithFlags(&c.ev_cull[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c.ev_surv[i], cudaEventDisableTiming));
+    }
     return ORT_OK;
 }
 
@@ -161,6 +169,11 @@ extern "C" int ort_finalize(void) {
         if (c.ev_traced) cudaEventDestroy(c.ev_traced);
         if (c.ev_reduced) cudaEventDestroy(c.ev_reduced);
         if (c.ev_copied) cudaEventDestroy(c.ev_copied);
+        for (int i = 0; i < 2; ++i) {
+            if (c.ev_cull[i]) cudaEventDestroy(c.ev_cull[i]);
+            if (c.ev_surv[i]) cudaEventDestroy(c.ev_surv[i]);
+        }
+        if (c.stream2) cudaStreamDestroy(c.stream2);
         if (c.stream) cudaStreamDestroy(c.stream);
     }
     if (g.h_pinned) cudaFreeHost(g.h_pinned);
@@ -399,7 +412,7 @@ static int enqueue_ring_filter(DeviceCtx& c, const ort_job& job, const DevScene&
         if (c.d_list) CK(cudaFree(c.d_list));
         c.d_list = nullptr;
         c.list_cap = 0;
-        CK(cudaMalloc(&c.d_list, capacity * sizeof(uint32_t)));
+        CK(cudaMalloc(&c.d_list, 2 * capacity * sizeof(uint32_t)));
         c.list_cap = capacity;
     }
     if (c.nlist_cap < (size_t)nslices) {
@@ -413,26 +426,37 @@ static int enqueue_ring_filter(DeviceCtx& c, const ort_job& job, const DevScene&
 
     DevSceneT<float> sf;
     ort_scene_to_float(s, sf);
+    /* cull(k) runs on the main stream, survivors(k) on the second one behind it, so that the small
+     * fp64 kernel fills the tail of cull(k+1) instead of standing between two cull kernels; the
+     * two list buffers alternate, and cull(k+2) waits until survivors(k) has read its buffer */
     int64_t k = 0;
     for (int64_t off = 0; off < n; off += ORT_RING_SLICE, ++k) {
         int64_t m = n - off < ORT_RING_SLICE ? n - off : ORT_RING_SLICE;
+        const int buf = (int)(k & 1);
+        uint32_t* list = c.d_list + (size_t)buf * c.list_cap;
         DevJob dj;
         ort_make_dev_job(job, nscenes, first + off, m, dj);
         int64_t batches = (m + 31) / 32;
         int64_t want = (batches + ORT_WPB - 1) / ORT_WPB;
         int grid = c.num_sms * occ_cull;
         int gsz = (int)(want < grid ? (want > 0 ? want : 1) : grid);
-        cull<<<gsz, ORT_TPB, smem_cull, c.stream>>>(sf, dj, aim_cut, c.d_list, c.d_nlist + k, (unsigned)capacity, d_cnt);
+        if (k >= 2) CK(cudaStreamWaitEvent(c.stream, c.ev_surv[buf], 0));
+        cull<<<gsz, ORT_TPB, smem_cull, c.stream>>>(sf, dj, aim_cut, list, c.d_nlist + k, (unsigned)capacity, d_cnt);
         CK(cudaGetLastError());
+        CK(cudaEventRecord(c.ev_cull[buf], c.stream));
         /* the list length is only known on the device: size the grid for the expectation */
         double expect = verify ? (double)m * p_pass : (double)m * p_pass * 0.15;
         int64_t sb = ((int64_t)expect / 32 + ORT_WPB) / ORT_WPB;
         int sgrid = c.num_sms * occ_surv;
         int sgsz = (int)(sb < sgrid ? (sb > 0 ? sb : 1) : sgrid);
-        surv<<<sgsz, ORT_TPB, smem_surv, c.stream>>>(s, sf, dj, c.d_list, c.d_nlist + k, (unsigned)capacity, d_img, d_cnt);
+        CK(cudaStreamWaitEvent(c.stream2, c.ev_cull[buf], 0));
+        surv<<<sgsz, ORT_TPB, smem_surv, c.stream2>>>(s, sf, dj, list, c.d_nlist + k, (unsigned)capacity, d_img, d_cnt);
         CK(cudaGetLastError());
+        CK(cudaEventRecord(c.ev_surv[buf], c.stream2));
         *launches += 2;
     }
+    /* join: whatever follows on the main stream (next scene, reduce, read-back) sees every count */
+    for (int64_t j = k > 2 ? k - 2 : 0; j < k; ++j) CK(cudaStreamWaitEvent(c.stream, c.ev_surv[j & 1], 0));
     return ORT_OK;
 }
 
