@@ -1127,7 +1127,7 @@ ORT_HD bool ortf_hit_sphere(const OrtRayT<float>& r, float cx, float cy, float c
     float c = l2 - R2;
     float disc = fmaf(h, h, -c);
     float tol = ORT_FILTER_TOL * (l2 + R2);
-    unc |= !(fminf(fminf(fabsf(disc), h * h), fabsf(c)) > tol);
+    unc |= !(fabsf(disc) > tol) || !(h * h > tol) || !(fabsf(c) > tol); /* each test also catches a NaN */
     bool hpos = h > 0.0f;
     if (disc < 0.0f || (hpos && c > 0.0f)) return false;
     float sq = ortf_sqrt(disc);

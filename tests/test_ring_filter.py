@@ -128,3 +128,43 @@ def test_survivor_list_overflow_is_reported(ort, orc, monkeypatch):
     monkeypatch.delenv("ORT_TEST_RING_LIST_CAP")
     img, lost, hist, _ = ort.trace(job, scene)
     assert int(hist.sum()) == 2_000_000
+
+
+EXTREMES = [
+    ("nearly flat L2", lambda sc: setattr(sc.L2, "n2", 1.0005)),
+    ("dense L2", lambda sc: setattr(sc.L2, "n2", 2.6)),
+    ("dense L3", lambda sc: (setattr(sc.L3, "n2", 2.2), setattr(sc.L3, "n3", 2.9))),
+    ("L3 far away", lambda sc: sc.L3.centre1.__setitem__(2, sc.L3.centre1[2] + 0.4)),
+    ("L3 nearly touching", lambda sc: sc.L3.centre1.__setitem__(2, sc.L3.centre1[2] - 0.02)),
+    ("huge L3 radius of curvature", lambda sc: (setattr(sc.L3, "R1", sc.L3.R1 * 50),
+                                                sc.L3.centre1.__setitem__(2, sc.L3.centre1[2] + sc.L3.R1 * 49 / 50))),
+    ("tiny L3 aperture", lambda sc: setattr(sc.L3, "radius", sc.L3.radius * 0.05)),
+    ("wide ring", lambda sc: (setattr(sc, "r1", sc.r1 * 0.1), setattr(sc, "r2", sc.r2 * 3.0))),
+]
+
+
+@pytest.mark.parametrize("k", range(len(EXTREMES)))
+def test_filter_on_extreme_geometries(orc, harness, k):
+    """Far outside the shipped parameter range the filter may hand everything to fp64, but a
+    verdict it does give must still be the oracle's."""
+    name, tweak = EXTREMES[k]
+    scene = cases.scene_for(orc, cases.C2, 1)
+    tweak(scene)
+    job = abi.default_job(1, first_ray=5 * 10 ** 8 * k)
+    in_b, certain, ended = _check_filter(orc, harness, scene, job, 400_000)
+    print(name, in_b, certain, ended)
+
+
+@pytest.mark.gpu
+def test_cuda_filter_on_extreme_geometries(ort, orc):
+    for k, (name, tweak) in enumerate(EXTREMES):
+        scene = cases.scene_for(orc, cases.C2, 1)
+        tweak(scene)
+        job = abi.default_job(1, 300_000_000, first_ray=5 * 10 ** 8 * k, flags=abi.FLAG_VERIFY_FILTER)
+        hist = ort.trace(job, scene, allow_trap=True)[2]
+        assert int(hist[0, abi.FILTER_SLOT_WRONG]) == 0, name
+        job.nrays = 300_000
+        job.flags = 0
+        img, lost, hist, _ = ort.trace(job, scene, allow_trap=True)
+        oimg, olost, ohist = orc.trace(job, scene)
+        assert np.array_equal(hist, ohist) and np.array_equal(img, oimg), name
