@@ -309,6 +309,32 @@ int ort_write_images(const char* base_with_folder, const uint64_t* ring, const u
 int ort_append_trans_stats(const char* folder, const ort_settings* settings,
                            const ort_scene* scene_after, int64_t rcount, int64_t pcount);
 
+/* ------------------------------------------------------------------------------------------
+ * Beam-propagation pre-processor: replaces the reference's bpm.py, the
+ * script that writes `bessel-normal.dat`, the nxy x nxy fp64 intensity map of the Bessel beam that
+ * the `image` source samples (ort_load_image_source reads 512 x 512).  Lengths in micrometres as in
+ * the script.  The library must be initialised; the work runs on its first device (cuFFT).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    double w0;          /* beam waist, bpm.py:84 (582*4) */
+    double wavelength;  /* :85 (0.785) */
+    double axicon_deg;  /* :87 (5) */
+    double n_axicon;    /* :88 (1.45) */
+    double xymax;       /* lateral extent of the grid, :93 (5000) */
+    double ring_radius; /* centre of the ring-shaped start field, :120 (1612) */
+    double ring_width;  /* its 1/e half width, :120 (300) */
+    int32_t nxy;        /* grid points per side, :94 (512) */
+    int32_t nz;         /* axial voxels: dz = 3 w0 (k / k_r) / nz, :95-100 (1000) */
+    int32_t steps;      /* free-space steps before the lens; < 0: nz / 10 as in :126 */
+    int32_t reserved;
+} ort_bpm;
+int ort_bpm_defaults(ort_bpm* p);
+int ort_bpm_struct_size(void);
+/* intensity[nxy * nxy] in the element order of the file bpm.py writes (|e^T|^2, bpm.py:203-204) */
+int ort_bpm_bessel(const ort_bpm* p, double* intensity);
+/* the same, written as raw fp64 to `path` (bpm.py:205 writes ./bessel-normal.dat) */
+int ort_bpm_write_file(const ort_bpm* p, const char* path);
+
 #ifdef __cplusplus
 }
 #endif

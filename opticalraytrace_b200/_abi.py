@@ -86,6 +86,13 @@ class Timing(C.Structure):
                 ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
 
 
+class Bpm(C.Structure):
+    """ort_bpm: the parameters of the reference's bpm.py (lengths in micrometres)"""
+    _fields_ = [(n, C.c_double) for n in
+                ("w0", "wavelength", "axicon_deg", "n_axicon", "xymax", "ring_radius", "ring_width")] + [
+        ("nxy", C.c_int32), ("nz", C.c_int32), ("steps", C.c_int32), ("reserved", C.c_int32)]
+
+
 class Settings(C.Structure):
     _fields_ = [(n, C.c_double) for n in
                 ("ring_width", "wavelength", "alpha_deg", "n_axicon", "image_diameter",

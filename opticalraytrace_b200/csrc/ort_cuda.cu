@@ -130,6 +130,8 @@ struct LibState {
 };
 static LibState g;
 
+int ort_internal_primary_device(void) { return (g.ready && !g.devs.empty()) ? g.devs[0].dev : -1; }
+
 extern "C" int ort_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) {

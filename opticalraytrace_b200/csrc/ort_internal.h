@@ -9,6 +9,8 @@
 __attribute__((format(printf, 1, 2)))
 #endif
 void ort_set_error(const char* fmt, ...);
+/* CUDA device index of the library's first device, or -1 when it is not initialised */
+int ort_internal_primary_device(void);
 
 
 #endif

@@ -23,6 +23,7 @@ EXPORTS = [
     "ort_load_plano", "ort_load_doublet", "ort_load_bottle", "ort_read_settings",
     "ort_build_scene", "ort_job_from_settings", "ort_output_basename", "ort_write_images",
     "ort_append_trans_stats",
+    "ort_bpm_defaults", "ort_bpm_struct_size", "ort_bpm_bessel", "ort_bpm_write_file",
 ]
 
 
@@ -69,6 +70,9 @@ def load():
     L.ort_write_images.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p]
     L.ort_append_trans_stats.argtypes = [C.c_char_p, C.POINTER(abi.Settings),
                                          C.POINTER(abi.Scene), C.c_int64, C.c_int64]
+    L.ort_bpm_defaults.argtypes = [C.POINTER(abi.Bpm)]
+    L.ort_bpm_bessel.argtypes = [C.POINTER(abi.Bpm), C.c_void_p]
+    L.ort_bpm_write_file.argtypes = [C.POINTER(abi.Bpm), C.c_char_p]
     _lib = L
     return L
 
@@ -217,6 +221,25 @@ def set_image_source(budget):
     b = np.ascontiguousarray(budget, dtype=np.int32)
     assert b.size == abi.SRCIMG_N * abi.SRCIMG_N
     return check(load().ort_set_image_source(b.ctypes.data))
+
+
+def bpm_defaults():
+    p = abi.Bpm()
+    check(load().ort_bpm_defaults(C.byref(p)))
+    return p
+
+
+def bpm_bessel(params=None):
+    """ort_bpm_bessel -> float64[nxy, nxy] in the element order of the reference's bessel-normal.dat"""
+    p = params if params is not None else bpm_defaults()
+    out = np.zeros((p.nxy, p.nxy), dtype=np.float64)
+    check(load().ort_bpm_bessel(C.byref(p), out.ctypes.data))
+    return out
+
+
+def bpm_write_file(path, params=None):
+    p = params if params is not None else bpm_defaults()
+    check(load().ort_bpm_write_file(C.byref(p), os.fsencode(path)))
 
 
 def write_tracks(job, scene, path):

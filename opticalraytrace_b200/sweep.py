@@ -13,7 +13,8 @@ Experiments (same option letters as `runner.py:351-389`):
   -i  iris position x size experiment                                (runner.py:158-186)
   -o  bottle offset experiment on the large bottle                   (runner.py:189-206)
   -l  L2 x L3 focal-length experiment                                (runner.py:231-261, :394-397)
-  -b  bessel images: the `image` source for the four set-ups         (runner.py:209-228)
+  -b  bessel images: the `image` source for the four set-ups         (runner.py:209-228);
+      needs res/bessel-smear.dat -- `python -m opticalraytrace_b200.bpm -o res/bessel-smear.dat`
   --isb  iSORS against Bessel illumination over seven offsets        (runner.py:266-320; the
       reference defines this one without wiring it to an option)
 (-bp is a stub in the reference, runner.py:264-265, and stays one here.)
