@@ -12,21 +12,25 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import bpm_oracle  # noqa: E402
 
 GOLD = np.load(os.path.join(ROOT, "tests", "golden", "bpm_v1.npz"))
-TOL = 1e-9   # of the peak intensity; FFT libraries differ in rounding (observed ~1e-14)
+TOL = 1e-9   # of the peak intensity; FFT libraries differ in rounding (observed 4e-14 after 100 steps)
 
 
-def _check_fingerprint(img, tol):
+def _check_fingerprint(img, tol, argmax=False):
     peak = float(GOLD["peak"])
     assert img.shape == (512, 512)
     assert np.abs(img[256, :] - GOLD["row"]).max() <= tol * peak
     assert np.abs(img[:, 256] - GOLD["col"]).max() <= tol * peak
     assert np.abs(img[::8, ::8] - GOLD["sub"]).max() <= tol * peak
     assert abs(img.sum() - float(GOLD["total"])) <= tol * float(GOLD["total"])
-    assert tuple(np.unravel_index(np.argmax(img), img.shape)) == tuple(GOLD["argmax"])
+    # the ring has mirror-image maxima that differ in the last bits: only a bit-faithful
+    # restatement can be asked for the same argmax
+    if argmax:
+        assert tuple(np.unravel_index(np.argmax(img), img.shape)) == tuple(GOLD["argmax"])
+    assert abs(img.max() - peak) <= tol * peak
 
 
 def test_oracle_reproduces_the_reference_script():
-    _check_fingerprint(bpm_oracle.bessel_intensity(), 1e-14)
+    _check_fingerprint(bpm_oracle.bessel_intensity(), 1e-14, argmax=True)
 
 
 def test_bpm_defaults_are_the_scripts_constants(ortlib):
