@@ -1058,16 +1058,24 @@ ORT_HD int ort_image(const DevSceneT<R>& S, OrtRayT<R>& r, int* xp, int* yp) {
  *             ends with status s -- exactly what the fp64 path would count;
  *     0     : the ray survives to L3, or some decision was too close to call -> the caller runs
  *             the ordinary fp64 stage on it (ort_stage_b), which alone moves rays forward.
- * Measured (tools/filter_margin.py, host build, 1e7 rays past L2's aperture over shipped and
- * randomised geometries): with NO margin at all fp32 misjudges 2 rays in 1e7, i.e. its error is
- * ~1e-7 of the compared quantities (the divisions by near-zero discriminants that could amplify it
- * are exactly the near-calls that are handed back); the margin used is 5e-4, more than three
- * orders of magnitude above that, and costs ~1 % of the rays an unnecessary fp64 pass.
- * ORT_FLAG_VERIFY_FILTER runs both paths on every ray and counts disagreements
- * (tests/test_ring_filter.py), ORT_FLAG_NO_FILTER switches the filter off.
+ * Measured (tools/filter_margin.py, profiles/r01_filter_margin.txt; ORT_FLAG_VERIFY_FILTER runs
+ * filter and fp64 on every ray and counts disagreements, over 4 shipped and 8 randomised
+ * geometries): with a margin of 1e-6 the filter is wrong ~1e-9 of the time, with 1e-5 ~1e-10, with
+ * 5e-5 never in 1.4e11 verdicts; the shipped margin is 5e-4, ten times that again (0 wrong in
+ * 3.5e11 verdicts), and costs ~1 % of the rays an unnecessary fp64 pass.  This is an empirical
+ * bound, not a proof: an fp32 error analysis that is rigorous for arbitrary scenes would need
+ * interval arithmetic.  ORT_FLAG_NO_FILTER switches the filter off.
  * ----------------------------------------------------------------------------------------- */
 #ifndef ORT_FILTER_TOL
-#define ORT_FILTER_TOL 5e-4f
+#define ORT_FILTER_TOL 5e-4f /* relative margin of every sign decision */
+#endif
+/* conditioning guard: a ray transmitted just inside the critical angle CONTINUES with a direction
+ * computed from sqrt(cos^2 theta_t), which amplifies fp32 rounding by 1 / (2 cos theta_t); every later
+ * decision would inherit that, so such rays go to fp64 whatever their own margins say.  (Measured:
+ * without this guard the wrong-verdict rate falls only slowly with the margin -- 3 in 6e9 at 5e-5;
+ * with it, none in 1.4e11 at 5e-5.  The analogous guard on grazing sphere hits changes nothing.) */
+#ifndef ORT_FILTER_COND_I
+#define ORT_FILTER_COND_I 1e-2f /* smallest cos^2 of the transmitted angle a continuing ray may have */
 #endif
 
 ORT_HD float ortf_rcp(float x) {
@@ -1153,6 +1161,9 @@ ORT_HD bool ortf_interface(OrtRayT<float>& r, float nx, float ny, float nz, cons
     bool tir = !(ct2 > 0.0f);
     unc |= !(s2 > 1e-4f) || !(fabsf(ct2) > ORT_FILTER_TOL) ||
            (!tir && !(fabsf(lhs - num) > (2.0f * ORT_FILTER_TOL) * den)); /* |u - R| < tol */
+    /* transmission just inside the critical angle: sqrt(ct2) amplifies the rounding of the
+     * refracted direction, and every later decision would inherit it */
+    unc |= !tir && !(ct2 > ORT_FILTER_COND_I);
     bool reflect = tir || !(lhs > num);
     /* reflect: d - 2c n;  refract: eta d + k n, k = +-(eta cos_i - cos_t) opposing the normal */
     float a = reflect ? 1.0f : f.eta;
