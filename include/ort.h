@@ -310,6 +310,23 @@ int ort_append_trans_stats(const char* folder, const ort_settings* settings,
                            const ort_scene* scene_after, int64_t rcount, int64_t pcount);
 
 /* ------------------------------------------------------------------------------------------
+ * Volume image: makeImage3D / writeImage3D, src/imageMod.f90:61-90,117-133.
+ * The reference's generic `makeImage` picks this routine when `image` has rank 4; its main program
+ * only ever passes rank 3, so this is the path a maintainer gets by changing that declaration.
+ * From the image plane every surviving ray is sampled at ORT_VOL_DEPTH depths diameter/200 apart
+ * (no NA test); each sample inside the 401 x 401 window increments its voxel, the first one
+ * outside ends the ray.  volume[(depth * 401 + (yp + 200)) * 401 + (xp + 200)] -- the memory order
+ * of image(-200:200, -200:200, 200, layer); uint32 counts (one layer: 128.6 MB).  Status BINNED =
+ * at least one voxel hit, OFF_DETECTOR = none.  Runs on the library's first device.
+ * ---------------------------------------------------------------------------------------- */
+#define ORT_VOL_DEPTH 200
+int ort_trace_volume(const ort_job* job, const ort_scene* scene, uint32_t* volume, int64_t* lost,
+                     int64_t* status_hist);
+/* <base>-vol-ring.dat and <base>-vol-point.dat: raw fp64, src/imageMod.f90:117-133.  Either
+ * volume may be NULL (that file is then not written). */
+int ort_write_volume(const char* base_with_folder, const uint32_t* vol_ring, const uint32_t* vol_point);
+
+/* ------------------------------------------------------------------------------------------
  * Beam-propagation pre-processor: replaces the reference's bpm.py, the
  * script that writes `bessel-normal.dat`, the nxy x nxy fp64 intensity map of the Bessel beam that
  * the `image` source samples (ort_load_image_source reads 512 x 512).  Lengths in micrometres as in

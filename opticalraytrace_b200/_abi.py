@@ -9,6 +9,7 @@ ORT_IMG_N = 401
 ORT_IMG_HALF = 200
 ORT_IMG_BINS = ORT_IMG_N * ORT_IMG_N
 ORT_NSTATUS = 32
+VOL_DEPTH = 200
 
 ORT_OK, ORT_EINVAL, ORT_ENODEVICE, ORT_ECUDA, ORT_ENCCL, ORT_EIO, ORT_EPARSE, ORT_ETRACE = (
     0, -1, -2, -3, -4, -5, -6, -7)

@@ -815,6 +815,68 @@ extern "C" int ort_math_selftest(int64_t n, uint64_t max_ulp[4]) {
  * tracker files (reference src/stackMod.f90:38-52, src/main.f90:103-107,144-160,
  * src/optics_system.f90:28-50)
  * ---------------------------------------------------------------------------------------- */
+/* makeImage3D on the first device; see include/ort.h */
+extern "C" int ort_trace_volume(const ort_job* job, const ort_scene* scene, uint32_t* volume, int64_t* lost,
+                                int64_t* status_hist) {
+    if (!g.ready) {
+        ort_set_error("ort_trace_volume: library not initialised (ort_init / ort_init_rank)");
+        return ORT_ENODEVICE;
+    }
+    int rc = validate_job(job);
+    if (rc) return rc;
+    if (!scene || !volume || job->precision != 64 || job->uniform_override >= 0.0 ||
+        (job->source_kind == ORT_SRC_IMAGE && job->phase == ORT_PHASE_POINT)) {
+        ort_set_error("ort_trace_volume: needs a scene, a volume buffer, precision 64 and a generated source "
+                      "other than `image`");
+        return ORT_EINVAL;
+    }
+    DeviceCtx& c = g.devs[0];
+    CK(cudaSetDevice(c.dev));
+    DevScene ds;
+    ort_flatten_scene(*scene, *job, ds);
+    const size_t nvox = (size_t)ORT_VOL_DEPTH * ORT_IMG_BINS;
+    unsigned* d_vol = nullptr;
+    unsigned long long* d_cnt = nullptr;
+    unsigned long long h_cnt[ORT_NSTATUS];
+    cudaError_t e = cudaMalloc(&d_vol, nvox * sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMalloc(&d_cnt, ORT_NSTATUS * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_vol, 0, nvox * sizeof(unsigned), c.stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_cnt, 0, ORT_NSTATUS * sizeof(unsigned long long), c.stream);
+    for (int64_t off = 0; e == cudaSuccess && off < job->nrays; off += ORT_CHUNK) {
+        int64_t m = job->nrays - off < ORT_CHUNK ? job->nrays - off : ORT_CHUNK;
+        ort_job jj = *job;
+        jj.stop_after = ORT_STOP_L3;
+        DevJob dj;
+        ort_make_dev_job(jj, 1, job->first_ray + off, m, dj);
+        int64_t want = (m + ORT_TPB - 1) / ORT_TPB;
+        int64_t cap = (int64_t)c.num_sms * 8;
+        ort_volume_kernel<<<(unsigned)(want < cap ? want : cap), ORT_TPB, 0, c.stream>>>(ds, dj, job->image_diameter / 200.0, d_vol, d_cnt);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(volume, d_vol, nvox * sizeof(unsigned), cudaMemcpyDeviceToHost, c.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_cnt, d_cnt, sizeof h_cnt, cudaMemcpyDeviceToHost, c.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);
+    if (d_vol) cudaFree(d_vol);
+    if (d_cnt) cudaFree(d_cnt);
+    if (e != cudaSuccess) {
+        ort_set_error("ort_trace_volume: %s", cudaGetErrorString(e));
+        return ORT_ECUDA;
+    }
+    int64_t l = 0;
+    bool trapped = false;
+    for (int k = 0; k < ORT_NSTATUS; ++k) {
+        if (ORT_STATUS_IS_LOST(k)) l += (int64_t)h_cnt[k];
+        if (status_hist) status_hist[k] = (int64_t)h_cnt[k];
+    }
+    if (h_cnt[ORT_ST_L3_S3_MISS] || h_cnt[ORT_ST_TAUINT_MISS] || h_cnt[ORT_ST_SOURCE_MISS]) trapped = true;
+    if (lost) *lost = l;
+    if (trapped) {
+        ort_set_error("trace hit a reference `error stop` invariant (status 18, 24 or 26); results returned");
+        return ORT_ETRACE;
+    }
+    return ORT_OK;
+}
+
 extern "C" int ort_write_tracks(const ort_job* job, const ort_scene* scene, const char* path) {
     if (!job || !scene || !path) return ORT_EINVAL;
     const int64_t n = job->nrays;

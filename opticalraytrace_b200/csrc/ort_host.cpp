@@ -477,6 +477,35 @@ int ort_write_images(const char* base, const uint64_t* ring, const uint64_t* poi
     return ORT_OK;
 }
 
+/* writeImage3D, src/imageMod.f90:117-133: real(image(:,:,:,layer)) as one raw stream per layer */
+int ort_write_volume(const char* base, const uint32_t* vol_ring, const uint32_t* vol_point) {
+    if (!base) return ORT_EINVAL;
+    const uint32_t* vols[2] = {vol_ring, vol_point};
+    const char* suffix[2] = {"-vol-ring.dat", "-vol-point.dat"};
+    std::vector<double> tmp(ORT_IMG_BINS);
+    for (int k = 0; k < 2; ++k) {
+        if (!vols[k]) continue;
+        std::string name = std::string(base) + suffix[k];
+        FILE* fh = std::fopen(name.c_str(), "wb");
+        if (!fh) {
+            ort_set_error("cannot write %s", name.c_str());
+            return ORT_EIO;
+        }
+        bool ok = true;
+        for (int z = 0; z < ORT_VOL_DEPTH && ok; ++z) {
+            const uint32_t* slab = vols[k] + (size_t)z * ORT_IMG_BINS;
+            for (int i = 0; i < ORT_IMG_BINS; ++i) tmp[i] = (double)slab[i];
+            ok = std::fwrite(tmp.data(), sizeof(double), tmp.size(), fh) == tmp.size();
+        }
+        if (std::fclose(fh) != 0) ok = false;
+        if (!ok) {
+            ort_set_error("short write on %s", name.c_str());
+            return ORT_EIO;
+        }
+    }
+    return ORT_OK;
+}
+
 /* src/main.f90:168-178 */
 int ort_append_trans_stats(const char* folder, const ort_settings* st, const ort_scene* sc, int64_t rcount,
                            int64_t pcount) {

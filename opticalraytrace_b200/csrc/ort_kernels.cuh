@@ -544,6 +544,45 @@ ort_rays_kernel(const __grid_constant__ DevSceneT<R> S, const __grid_constant__ 
     bin[n + i] = yp;
 }
 
+/* Volume image (makeImage3D, src/imageMod.f90:61-90): one thread per ray through the whole path up
+ * to L3 (J.stop_after = ORT_STOP_L3), then the transfer to the image plane and the march through
+ * ORT_VOL_DEPTH depths with one 32-bit RED per sample.  A diagnostic path: no compaction, the
+ * status histogram goes through shared memory. */
+__global__ void __launch_bounds__(ORT_TPB)
+ort_volume_kernel(const __grid_constant__ DevSceneT<double> S, const __grid_constant__ DevJob J, const double dzs,
+                  unsigned* __restrict__ vol, unsigned long long* __restrict__ counters) {
+    __shared__ unsigned hist[ORT_NSTATUS];
+    if (threadIdx.x < ORT_NSTATUS) hist[threadIdx.x] = 0;
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < J.nrays;
+         i += (long long)gridDim.x * blockDim.x) {
+        OrtRng g = ort_make_rng_prod(J, (uint32_t)i);
+        OrtRayT<double> r;
+        int x = 0, y = 0;
+        int st = ort_full_path(S, J, g, false, r, &x, &y);
+        if (st == ORT_ST_STOPPED) {
+            double d = ort_div_z(S.img_z - r.pz, r.dz);
+            ort_advance(r, d);
+            int hits = 0;
+            for (int k = 0; k < ORT_VOL_DEPTH; ++k) {
+                const double t = k * dzs;
+                const double fx = floor(fma(r.dx, t, r.px) * S.inv_binwid), fy = floor(fma(r.dy, t, r.py) * S.inv_binwid);
+                if (!(fabs(fx) <= 200.0) || !(fabs(fy) <= 200.0)) break;
+                const size_t idx = ((size_t)k * ORT_IMG_N + (size_t)((int)fy + ORT_IMG_HALF)) * ORT_IMG_N +
+                                   (size_t)((int)fx + ORT_IMG_HALF);
+                ORT_ASSERT(idx < (size_t)ORT_VOL_DEPTH * ORT_IMG_BINS);
+                atomicAdd(vol + idx, 1u);
+                ++hits;
+            }
+            st = hits ? ORT_ST_BINNED : ORT_ST_OFF_DETECTOR;
+        }
+        atomicAdd(&hist[st], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < ORT_NSTATUS && hist[threadIdx.x])
+        atomicAdd(counters + threadIdx.x, (unsigned long long)hist[threadIdx.x]);
+}
+
 __global__ void ort_uniforms_kernel(uint64_t seed, int32_t phase, int64_t ray, int32_t first_slot, int32_t n,
                                     double* __restrict__ out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;

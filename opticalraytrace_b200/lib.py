@@ -24,6 +24,7 @@ EXPORTS = [
     "ort_build_scene", "ort_job_from_settings", "ort_output_basename", "ort_write_images",
     "ort_append_trans_stats",
     "ort_bpm_defaults", "ort_bpm_struct_size", "ort_bpm_bessel", "ort_bpm_write_file",
+    "ort_trace_volume", "ort_write_volume",
 ]
 
 
@@ -70,6 +71,8 @@ def load():
     L.ort_write_images.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p]
     L.ort_append_trans_stats.argtypes = [C.c_char_p, C.POINTER(abi.Settings),
                                          C.POINTER(abi.Scene), C.c_int64, C.c_int64]
+    L.ort_trace_volume.argtypes = [C.POINTER(abi.Job), C.POINTER(abi.Scene), C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ort_write_volume.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p]
     L.ort_bpm_defaults.argtypes = [C.POINTER(abi.Bpm)]
     L.ort_bpm_bessel.argtypes = [C.POINTER(abi.Bpm), C.c_void_p]
     L.ort_bpm_write_file.argtypes = [C.POINTER(abi.Bpm), C.c_char_p]
@@ -221,6 +224,22 @@ def set_image_source(budget):
     b = np.ascontiguousarray(budget, dtype=np.int32)
     assert b.size == abi.SRCIMG_N * abi.SRCIMG_N
     return check(load().ort_set_image_source(b.ctypes.data))
+
+
+def trace_volume(job, scene, allow_trap=False):
+    """ort_trace_volume (makeImage3D) -> (volume[200, 401, 401] uint32, lost, hist[32])"""
+    vol = np.zeros((abi.VOL_DEPTH, abi.ORT_IMG_N, abi.ORT_IMG_N), dtype=np.uint32)
+    lost = np.zeros(1, dtype=np.int64)
+    hist = np.zeros(abi.ORT_NSTATUS, dtype=np.int64)
+    check(load().ort_trace_volume(C.byref(job), C.byref(scene), vol.ctypes.data, lost.ctypes.data,
+                                  hist.ctypes.data), allow=(abi.ORT_ETRACE,) if allow_trap else ())
+    return vol, int(lost[0]), hist
+
+
+def write_volume(base, vol_ring=None, vol_point=None):
+    """ort_write_volume (writeImage3D): <base>-vol-ring.dat / <base>-vol-point.dat, raw fp64"""
+    vols = [None if v is None else np.ascontiguousarray(v, dtype=np.uint32) for v in (vol_ring, vol_point)]
+    check(load().ort_write_volume(os.fsencode(base), *(None if v is None else v.ctypes.data for v in vols)))
 
 
 def bpm_defaults():

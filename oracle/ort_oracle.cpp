@@ -1091,6 +1091,64 @@ int orc_trace(const ort_job* job, const ort_scene* scenes, int nscenes, uint64_t
     return 0;
 }
 
+/* Volume image: makeImage3D, src/imageMod.f90:61-90, in the place of makeImage2D (same call,
+ * `image` of rank 4).  The reference never reaches it (main's image has rank 3); restated so that
+ * the CUDA version has something to be compared with.  No NA test, no `> 1000` test: from the
+ * image plane the ray is sampled at 200 depths dz = diameter / 200 apart and every sample inside
+ * the 401 x 401 window increments its voxel; the first sample outside ends the ray.
+ * volume[(i * 401 + (yp + 200)) * 401 + (xp + 200)], i = depth: the memory order of
+ * image(-200:200, -200:200, 200, layer).  Status: BINNED when at least one voxel was hit, else
+ * OFF_DETECTOR; non-finite samples count as outside. */
+int orc_trace_volume(const ort_job* job, const ort_scene* scene, uint32_t* volume, int64_t* lost,
+                     int64_t* status_hist, int nthreads) {
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+    const ort_scene& S = *scene;
+    ort_job J = *job;
+    J.stop_after = ORT_STOP_L3;
+    std::memset(volume, 0, sizeof(uint32_t) * (size_t)ORT_VOL_DEPTH * ORT_IMG_BINS);
+    int64_t hist[ORT_NSTATUS] = {0};
+    const double binwid = J.image_diameter / 401.;
+    const double dz = J.image_diameter / 200.;
+#pragma omp parallel
+    {
+        int64_t h[ORT_NSTATUS] = {0};
+#pragma omp for schedule(static)
+        for (int64_t i = 0; i < J.nrays; ++i) {
+            RayOut o = trace_one(J, S, J.first_ray + i, false, {0, 0, 0}, {0, 0, 1});
+            if (o.status != ORT_ST_STOPPED) {
+                h[o.status]++;
+                continue;
+            }
+            vec pos = o.pos, dir = o.dir;
+            double d = ((S.img_plane + J.fibre_offset) - pos.z) / dir.z; /* src/optics_system.f90:48-49 */
+            pos = pos + dir * d;
+            int hits = 0;
+            for (int k = 0; k < ORT_VOL_DEPTH; ++k) {
+                vec np = pos + dir * (k * dz);
+                double fx = std::floor(np.x / binwid), fy = std::floor(np.y / binwid);
+                if (!(std::fabs(fx) <= 200.0) || !(std::fabs(fy) <= 200.0)) break;
+                size_t idx = ((size_t)k * ORT_IMG_N + (size_t)((int)fy + ORT_IMG_HALF)) * ORT_IMG_N +
+                             (size_t)((int)fx + ORT_IMG_HALF);
+#pragma omp atomic
+                volume[idx] += 1;
+                ++hits;
+            }
+            h[hits ? ORT_ST_BINNED : ORT_ST_OFF_DETECTOR]++;
+        }
+#pragma omp critical
+        for (int k = 0; k < ORT_NSTATUS; ++k) hist[k] += h[k];
+    }
+    int64_t l = 0;
+    for (int k = 0; k < ORT_NSTATUS; ++k)
+        if (ORT_STATUS_IS_LOST(k)) l += hist[k];
+    if (lost) *lost = l;
+    if (status_hist)
+        for (int k = 0; k < ORT_NSTATUS; ++k) status_hist[k] = hist[k];
+    return 0;
+}
+
 int orc_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -45,6 +45,8 @@ def lib():
                                      C.c_void_p]
         L.orc_trace.argtypes = [C.POINTER(abi.Job), C.POINTER(abi.Scene), C.c_int, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_trace_volume.argtypes = [C.POINTER(abi.Job), C.POINTER(abi.Scene), C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_int]
         L.orc_fresnel.restype = C.c_double
         L.orc_fresnel.argtypes = [DP, DP, C.c_double, C.c_double]
         L.orc_sellmeier.restype = C.c_double
@@ -122,6 +124,16 @@ def trace(job, scenes, nthreads=0):
     _chk(lib().orc_trace(C.byref(job), arr, ns, image.ctypes.data, lost.ctypes.data,
                          hist.ctypes.data, nthreads), "trace")
     return image, lost, hist
+
+
+def trace_volume(job, scene, nthreads=0):
+    """makeImage3D -> volume[200,401,401] uint32, lost, hist[32]"""
+    vol = np.zeros((200, abi.ORT_IMG_N, abi.ORT_IMG_N), dtype=np.uint32)
+    lost = np.zeros(1, dtype=np.int64)
+    hist = np.zeros(abi.ORT_NSTATUS, dtype=np.int64)
+    _chk(lib().orc_trace_volume(C.byref(job), C.byref(scene), vol.ctypes.data, lost.ctypes.data,
+                                hist.ctypes.data, nthreads), "trace_volume")
+    return vol, int(lost[0]), hist
 
 
 def load_image_source(path, nphotons, seed=123456789):
