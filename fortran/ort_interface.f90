@@ -19,6 +19,7 @@ module ort_interface
     integer(c_int), parameter :: ORT_PHASE_RING = 1, ORT_PHASE_POINT = 2
     integer(c_int), parameter :: ORT_IMG_N = 401, ORT_IMG_BINS = 401*401, ORT_NSTATUS = 32
     integer(c_int), parameter :: ORT_ETRACE = -7
+    integer(c_int), parameter :: ORT_FLAG_NO_FILTER = 8, ORT_FLAG_VERIFY_FILTER = 16   ! ort_job%flags, ring loop
     integer(c_int), parameter :: ORT_SRC_POINT = 0, ORT_SRC_CRS = 1, ORT_SRC_ISORS = 2, ORT_SRC_SPOT = 3
 
     type, bind(C) :: ort_plano                 ! reference src/lens.f90:8-20
@@ -106,6 +107,18 @@ module ort_interface
             real(c_double),     intent(out) :: pos_out(*), dir_out(*)
             integer(c_int32_t), intent(out) :: status(*), bin_xy(*)
         end function ort_trace_rays
+
+        ! makeImage3D (src/imageMod.f90:61-90): volume(401*401*200) is integer(c_int32_t), the memory
+        ! order of image(-200:200, -200:200, 200, layer)
+        integer(c_int) function ort_trace_volume(job, scene, volume, lost, status_hist) &
+                bind(C, name="ort_trace_volume")
+            import :: c_int, c_int32_t, c_int64_t, ort_job, ort_scene
+            type(ort_job),      intent(in)  :: job
+            type(ort_scene),    intent(in)  :: scene
+            integer(c_int32_t), intent(out) :: volume(*)
+            integer(c_int64_t), intent(out) :: lost
+            integer(c_int64_t), intent(out) :: status_hist(*)
+        end function ort_trace_volume
     end interface
 
 contains
