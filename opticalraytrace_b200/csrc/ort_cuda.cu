@@ -377,7 +377,8 @@ template <typename R>
 static bool ring_filter_applies(const ort_job& job, const DevScene& s, bool flat, unsigned long long* aim_cut) {
     return sizeof(R) == sizeof(double) && !flat && job.phase == ORT_PHASE_RING && s.ring_shortcut &&
            (job.source_kind == ORT_SRC_POINT || job.source_kind == ORT_SRC_SPOT) &&
-           !(job.flags & ORT_FLAG_NO_FILTER) && ort_ring_aim_cut(s, aim_cut);
+           !(job.flags & ORT_FLAG_NO_FILTER) && ort_ring_filter_in_range(s, job.iris_before != 0) &&
+           ort_ring_aim_cut(s, aim_cut);
 }
 /* Slice of the ray range per cull/survivors launch pair: long enough that the tail of a launch
  * is < 1 % of it, short enough that the list of ray indices stays a few hundred MB. */

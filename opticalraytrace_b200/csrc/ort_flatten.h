@@ -131,6 +131,27 @@ inline bool ort_ring_aim_cut(const DevScene& d, unsigned long long* cut) {
     return true;
 }
 
+/* The ring loop's fp32 culling filter (ort_ring_filter) was validated on geometries whose largest
+ * coordinate is ~12x their smallest aperture (profiles/r01_filter_margin.txt).  Its margins are
+ * relative, but fp32 coordinates are absolute: with everything shifted far from the origin, or a
+ * pin-hole aperture, rounding of the coordinates themselves reaches the margins.  The launcher
+ * therefore uses the filter only while (largest |coordinate| + radius of curvature) <= 200 x
+ * (smallest aperture radius) -- fp32 coordinate rounding <= 1.2e-5 of an aperture, forty times
+ * below the 5e-4 margin -- and falls back to the all-fp64 kernel otherwise. */
+inline bool ort_ring_filter_in_range(const DevScene& d, bool iris_before) {
+    double big = std::fabs(d.bcz) + std::sqrt(d.ra2);
+    big = std::fmax(big, std::fabs(d.l2_fb));
+    big = std::fmax(big, std::fabs(d.l2_cz) + std::sqrt(d.l2_R2));
+    big = std::fmax(big, std::fabs(d.l3_c1z) + std::sqrt(d.l3_R1_2));
+    big = std::fmax(big, std::sqrt(d.lens_r2));
+    double small = std::fmin(std::sqrt(d.l2_radius2), std::sqrt(d.l3_radius2));
+    if (iris_before) {
+        big = std::fmax(big, std::fabs(d.l3_iris1_z));
+        small = std::fmin(small, std::sqrt(d.l3_iris_r2));
+    }
+    return std::isfinite(big) && small > 0.0 && big <= 200.0 * small;
+}
+
 /* fp32 variant: every hoisted scalar is computed in double above and rounded once here.
  * DevSceneT<R> is N reals followed by 4 int32, in the same order for every R. */
 inline void ort_scene_to_float(const DevScene& s, DevSceneT<float>& d) {

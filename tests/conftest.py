@@ -67,6 +67,8 @@ def harness():
         cut = H.hh_ring_aim_cut(C.byref(job), C.byref(scene), C.byref(have))
         return int(cut), bool(have.value)
     run.ring_aim_cut = ring_aim_cut
+    H.hh_ring_filter_in_range.argtypes = [C.POINTER(abi.Job), C.POINTER(abi.Scene)]
+    run.ring_filter_in_range = lambda job, scene: bool(H.hh_ring_filter_in_range(C.byref(job), C.byref(scene)))
     run.set_image_source = set_image_source
     run.ring_filter = ring_filter
     return run

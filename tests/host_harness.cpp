@@ -106,3 +106,10 @@ extern "C" unsigned long long hh_ring_aim_cut(const ort_job* job, const ort_scen
     *have = ort_ring_aim_cut(S, &cut) ? 1 : 0;
     return cut;
 }
+
+/* the launcher's range guard for the ring filter */
+extern "C" int hh_ring_filter_in_range(const ort_job* job, const ort_scene* scene) {
+    DevScene S;
+    ort_flatten_scene(*scene, *job, S);
+    return ort_ring_filter_in_range(S, job->iris_before != 0) ? 1 : 0;
+}

@@ -168,3 +168,21 @@ def test_cuda_filter_on_extreme_geometries(ort, orc):
         img, lost, hist, _ = ort.trace(job, scene, allow_trap=True)
         oimg, olost, ohist = orc.trace(job, scene)
         assert np.array_equal(hist, ohist) and np.array_equal(img, oimg), name
+
+
+def test_range_guard(orc, harness):
+    """The launcher only uses the filter on geometries like the ones it was validated on: every
+    shipped set-up is in range, a system moved 50 m off the origin or with a pin-hole L3 is not
+    (those run the all-fp64 kernel)."""
+    job = abi.default_job(1)
+    for files in (cases.C1, cases.C2, cases.ELL, cases.ELLS, cases.OTHER, cases.OTHER2):
+        assert harness.ring_filter_in_range(job, cases.scene_for(orc, files, 1))
+    far = cases.scene_for(orc, cases.C2, 1)
+    for c in (far.bottle.centre, far.L2.centre, far.L3.centre1, far.L3.centre2, far.L3.centre3):
+        c[2] += 50.0
+    assert not harness.ring_filter_in_range(job, far)
+    pin = cases.scene_for(orc, cases.C2, 1)
+    pin.L3.radius *= 0.02
+    assert not harness.ring_filter_in_range(job, pin)
+    iris = abi.default_job(1, iris="before", iris_radius=0.01)
+    assert not harness.ring_filter_in_range(iris, cases.scene_for(orc, cases.C2, 1))
