@@ -5,7 +5,11 @@
  *                                    per ray, warp-private shared-memory queues that compact
  *                                    the live rays between surfaces, warp-aggregated 64-bit
  *                                    reductions into the detector image.
+ *   ort_ring_cull_kernel             the ring loop's first kernel: integer aim-point test + the
+ *                                    single-precision culling filter; no fp64, 48 warps per SM.
+ *   ort_ring_survivors_kernel        fp64 stages over the ray indices the cull kernel lists.
  *   ort_trace_flat_kernel<...>       the same path without compaction (diagnostic / evidence).
+ *   ort_volume_kernel                makeImage3D (opt-in volume image).
  *   ort_rays_kernel                  explicit ray list, per-ray outputs (parity entry point).
  *   ort_uniforms_kernel              exposes the counter-based generator.
  *   ort_dfma_peak_kernel             FP64 FMA peak micro-benchmark (roofline denominator).
