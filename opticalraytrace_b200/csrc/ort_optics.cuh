@@ -1062,7 +1062,7 @@ ORT_HD int ort_image(const DevSceneT<R>& S, OrtRayT<R>& r, int* xp, int* yp) {
  * filter and fp64 on every ray and counts disagreements, over 4 shipped and 8 randomised
  * geometries): with a margin of 1e-6 the filter is wrong ~1e-9 of the time, with 1e-5 ~1e-10, with
  * 5e-5 never in 1.4e11 verdicts; the shipped margin is 5e-4, ten times that again (0 wrong in
- * 3.5e11 verdicts), and costs ~1 % of the rays an unnecessary fp64 pass.  This is an empirical
+ * 5.9e12 verdicts), and costs ~1 % of the rays an unnecessary fp64 pass.  This is an empirical
  * bound, not a proof: an fp32 error analysis that is rigorous for arbitrary scenes would need
  * interval arithmetic.  ORT_FLAG_NO_FILTER switches the filter off.
  * ----------------------------------------------------------------------------------------- */

@@ -67,12 +67,14 @@ def cpu(nrays):
                   % (tol or "shipped", wrong, back, inb))
 
 
-def gpu(nrays):
+def gpu(nrays, first_ray=0, only=None):
     from opticalraytrace_b200 import lib
     lib.init(1)
     try:
         for name, sc, kw in setups():
-            job = abi.default_job(1, nrays, flags=kw.pop("flags", 0) | abi.FLAG_VERIFY_FILTER, **kw)
+            if only and not name.startswith(only):
+                continue
+            job = abi.default_job(1, nrays, first_ray=first_ray, flags=kw.pop("flags", 0) | abi.FLAG_VERIFY_FILTER, **kw)
             _, _, hist, tm = lib.trace(job, sc, want_image=False, allow_trap=True)
             print("%-10s %.3g rays: filter called %d, wrong %d  (%.1f s)"
                   % (name, nrays, hist[0, abi.FILTER_SLOT_CALLED], hist[0, abi.FILTER_SLOT_WRONG], tm.trace_seconds))
@@ -84,5 +86,7 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
     ap.add_argument("--rays", type=int, default=4_000_000)
     ap.add_argument("--gpu", type=int, default=0, metavar="RAYS")
+    ap.add_argument("--first-ray", type=int, default=0, help="start of the ray-index range (GPU part)")
+    ap.add_argument("--only", default=None, help="only the set-ups whose name starts with this (GPU part)")
     a = ap.parse_args()
-    gpu(a.gpu) if a.gpu else cpu(a.rays)
+    gpu(a.gpu, a.first_ray, a.only) if a.gpu else cpu(a.rays)
