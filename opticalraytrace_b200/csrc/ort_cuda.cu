@@ -447,8 +447,9 @@ static int enqueue_ring_filter(DeviceCtx& c, const ort_job& job, const DevScene&
         cull<<<gsz, ORT_TPB, smem_cull, c.stream>>>(sf, dj, aim_cut, list, c.d_nlist + k, (unsigned)capacity, d_cnt);
         CK(cudaGetLastError());
         CK(cudaEventRecord(c.ev_cull[buf], c.stream));
-        /* the list length is only known on the device: size the grid for the expectation */
-        double expect = verify ? (double)m * p_pass : (double)m * p_pass * 0.15;
+        /* the list length is only known on the device: size the grid for the longest list there can
+         * be (every ray that passes stage A); blocks that find nothing to do leave at once */
+        double expect = (double)m * p_pass;
         int64_t sb = ((int64_t)expect / 32 + ORT_WPB) / ORT_WPB;
         int sgrid = c.num_sms * occ_surv;
         int sgsz = (int)(sb < sgrid ? (sb > 0 ? sb : 1) : sgrid);
