@@ -359,7 +359,10 @@ ort_ring_cull_kernel(const __grid_constant__ DevSceneT<float> F, const __grid_co
     const uint32_t nrays = (uint32_t)J.nrays;
     const uint32_t nbatches = (nrays + 31u) >> 5;
 
-    unsigned c9 = 0, c10 = 0, c11 = 0, c12 = 0, c13 = 0, c14 = 0;
+    unsigned c10 = 0, c11 = 0, c12 = 0, c13 = 0, c14 = 0;
+    unsigned npassed = 0; /* warp-uniform: rays of this warp that passed stage A */
+    unsigned below;       /* lanes below this one */
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(below));
     int n0 = 0;
     uint32_t b = gwarp;
     for (;;) {
@@ -380,12 +383,10 @@ ort_ring_cull_kernel(const __grid_constant__ DevSceneT<float> F, const __grid_co
                 ort_philox4x32_10(g.r0, g.r1, g.phase, 1u, g.k0, g.k1, w, g.rk);
                 wa[k] = ((unsigned long long)w[1] << 32) | w[0];
                 wb[k] = ((unsigned long long)w[3] << 32) | w[2];
-                const bool in = id[k] < nrays;
-                pass[k] = in && wa[k] < aim_cut;
-                c9 += (unsigned)(in && !pass[k]);
+                pass[k] = id[k] < nrays && wa[k] < aim_cut;
             }
             b += (uint32_t)ORT_CULL_UNROLL * nwarps;
-            const unsigned below = (1u << lane) - 1u;
+            const int before = n0;
 #pragma unroll
             for (int k = 0; k < ORT_CULL_UNROLL; ++k) {
                 const unsigned m = __ballot_sync(ORT_FULL, pass[k]);
@@ -396,6 +397,7 @@ ort_ring_cull_kernel(const __grid_constant__ DevSceneT<float> F, const __grid_co
                 }
                 n0 += __popc(m);
             }
+            npassed += (unsigned)(n0 - before);
             __syncwarp();
         } else {
             unsigned long long wa = 0, wb = 0;
@@ -424,8 +426,17 @@ ort_ring_cull_kernel(const __grid_constant__ DevSceneT<float> F, const __grid_co
             }
         }
     }
+    /* rays that ended in stage A = rays this warp drew - rays that passed.  The warp drew the
+     * batches gwarp, gwarp + nwarps, ... below nbatches; only the last batch of the slice can be
+     * ragged */
+    unsigned c9 = 0;
+    if (gwarp < nbatches) {
+        const uint32_t mine_batches = (nbatches - 1u - gwarp) / nwarps + 1u;
+        unsigned drew = mine_batches * 32u;
+        if ((nbatches - 1u - gwarp) % nwarps == 0u) drew -= nbatches * 32u - nrays; /* owns the last batch */
+        c9 = drew - npassed;
+    }
     /* per-lane tallies -> one atomic per status and warp */
-    c9 = __reduce_add_sync(ORT_FULL, c9);
     c10 = __reduce_add_sync(ORT_FULL, c10);
     c11 = __reduce_add_sync(ORT_FULL, c11);
     c12 = __reduce_add_sync(ORT_FULL, c12);
