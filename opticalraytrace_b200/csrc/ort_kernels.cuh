@@ -340,6 +340,11 @@ __device__ __forceinline__ bool ort_slim_pop(SlimQueue& q, int& n, unsigned long
     return act;
 }
 
+template <int K>
+__device__ __forceinline__ void ort_tally(unsigned& c, int st) {
+    asm("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %1, %2;\n\t@p add.u32 %0, %0, 1;\n\t}" : "+r"(c) : "r"(st), "n"(K));
+}
+
 #ifndef ORT_CULL_MIN_BLOCKS
 #define ORT_CULL_MIN_BLOCKS 6
 #endif
@@ -407,11 +412,13 @@ ort_ring_cull_kernel(const __grid_constant__ DevSceneT<float> F, const __grid_co
             if (act) {
                 OrtRng g = ort_make_rng_prod(J, id);
                 st = VERIFY ? 0 : ort_ring_filter(F, J, g, ortf_uniform((uint32_t)(wa >> 32)), ortf_uniform((uint32_t)(wb >> 32)));
-                c10 += st == ORT_ST_L2_SPHERE_MISS;
-                c11 += st == ORT_ST_L2_CURVED_REFLECT;
-                c12 += st == ORT_ST_L3_IRIS_BEFORE;
-                c13 += st == ORT_ST_L3_S1_MISS;
-                c14 += st == ORT_ST_L3_APERTURE;
+                /* one compare + one predicated add per status (left to itself the compiler builds
+                 * add / conditional move / move triples here) */
+                ort_tally<ORT_ST_L2_SPHERE_MISS>(c10, st);
+                ort_tally<ORT_ST_L2_CURVED_REFLECT>(c11, st);
+                ort_tally<ORT_ST_L3_IRIS_BEFORE>(c12, st);
+                ort_tally<ORT_ST_L3_S1_MISS>(c13, st);
+                ort_tally<ORT_ST_L3_APERTURE>(c14, st);
             }
             unsigned m = __ballot_sync(ORT_FULL, st == 0);
             if (m) {
