@@ -322,6 +322,7 @@ ort_trace_kernel(const __grid_constant__ DevSceneT<R> S, const __grid_constant__
 struct SlimQueue {
     unsigned long long a[ORT_CULL_QCAP], b[ORT_CULL_QCAP]; /* the raw 64 bits behind u2 and u3 */
     uint32_t id[ORT_CULL_QCAP];
+    uint32_t hb[64]; /* ray indices on their way to the survivors list */
 };
 __device__ __forceinline__ bool ort_slim_pop(SlimQueue& q, int& n, unsigned long long& a, unsigned long long& b,
                                              uint32_t& id, unsigned lane) {
@@ -338,6 +339,19 @@ __device__ __forceinline__ bool ort_slim_pop(SlimQueue& q, int& n, unsigned long
     n = base;
     __syncwarp();
     return act;
+}
+
+/* `count` (<= 32, warp-uniform) entries, one per lane, to the end of the global list */
+__device__ __forceinline__ void ort_list_append(uint32_t* __restrict__ list, unsigned* __restrict__ nlist,
+                                                unsigned capacity, unsigned long long* __restrict__ counters,
+                                                uint32_t value, unsigned count, unsigned lane) {
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(nlist, count);
+    base = __shfl_sync(ORT_FULL, base, 0);
+    if (lane < count) {
+        if (base + lane < capacity) list[base + lane] = value;
+        else atomicAdd(counters + ORT_FILTER_SLOT_OVERFLOW, 1ull);
+    }
 }
 
 template <int K>
@@ -366,6 +380,7 @@ ort_ring_cull_kernel(const __grid_constant__ DevSceneT<float> F, const __grid_co
 
     unsigned c10 = 0, c11 = 0, c12 = 0, c13 = 0, c14 = 0;
     unsigned npassed = 0; /* warp-uniform: rays of this warp that passed stage A */
+    int nh = 0;           /* entries parked in q0.hb */
     unsigned below;       /* lanes below this one */
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(below));
     int n0 = 0;
@@ -420,19 +435,24 @@ ort_ring_cull_kernel(const __grid_constant__ DevSceneT<float> F, const __grid_co
                 ort_tally<ORT_ST_L3_S1_MISS>(c13, st);
                 ort_tally<ORT_ST_L3_APERTURE>(c14, st);
             }
-            unsigned m = __ballot_sync(ORT_FULL, st == 0);
-            if (m) {
-                unsigned base = 0;
-                if (lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(nlist, (unsigned)__popc(m));
-                base = __shfl_sync(ORT_FULL, base, __ffs(m) - 1);
-                if (st == 0) {
-                    unsigned p = base + __popc(m & ((1u << lane) - 1u));
-                    if (p < capacity) list[p] = id;
-                    else atomicAdd(counters + ORT_FILTER_SLOT_OVERFLOW, 1ull);
-                }
+            /* rays for fp64: parked in a warp-private buffer and written to the list 32 at a time
+             * (one atomic and one coalesced store per 32 entries) */
+            const unsigned m = __ballot_sync(ORT_FULL, st == 0);
+            if (st == 0) {
+                int p = nh + __popc(m & below);
+                ORT_ASSERT(p >= 0 && p < 64);
+                q0.hb[p] = id;
+            }
+            nh += __popc(m);
+            __syncwarp();
+            if (nh >= 32) {
+                nh -= 32;
+                ort_list_append(list, nlist, capacity, counters, q0.hb[nh + lane], 32u, lane);
+                __syncwarp();
             }
         }
     }
+    if (nh > 0) ort_list_append(list, nlist, capacity, counters, (int)lane < nh ? q0.hb[lane] : 0u, (unsigned)nh, lane);
     /* rays that ended in stage A = rays this warp drew - rays that passed.  The warp drew the
      * batches gwarp, gwarp + nwarps, ... below nbatches; only the last batch of the slice can be
      * ragged */
