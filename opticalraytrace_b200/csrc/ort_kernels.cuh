@@ -320,20 +320,22 @@ ort_trace_kernel(const __grid_constant__ DevSceneT<R> S, const __grid_constant__
 #endif
 #define ORT_CULL_QCAP (32 + 32 * ORT_CULL_UNROLL) /* < 32 leftovers + the survivors of one pass */
 struct SlimQueue {
-    unsigned long long a[ORT_CULL_QCAP], b[ORT_CULL_QCAP]; /* the raw 64 bits behind u2 and u3 */
+    unsigned long long hi[ORT_CULL_QCAP]; /* the high words behind u2 (low half) and u3 (high half):
+                                             all the filter needs; fp64 regenerates the draws */
     uint32_t id[ORT_CULL_QCAP];
     uint32_t hb[64]; /* ray indices on their way to the survivors list */
 };
-__device__ __forceinline__ bool ort_slim_pop(SlimQueue& q, int& n, unsigned long long& a, unsigned long long& b,
-                                             uint32_t& id, unsigned lane) {
+__device__ __forceinline__ bool ort_slim_pop(SlimQueue& q, int& n, uint32_t& hi2, uint32_t& hi3, uint32_t& id,
+                                             unsigned lane) {
     int cnt = n < 32 ? n : 32;
     int base = n - cnt;
     bool act = (int)lane < cnt;
     if (act) {
         int p = base + lane;
         ORT_ASSERT(p >= 0 && p < ORT_CULL_QCAP);
-        a = q.a[p];
-        b = q.b[p];
+        unsigned long long h = q.hi[p];
+        hi2 = (uint32_t)h;
+        hi3 = (uint32_t)(h >> 32);
         id = q.id[p];
     }
     n = base;
@@ -392,7 +394,7 @@ ort_ring_cull_kernel(const __grid_constant__ DevSceneT<float> F, const __grid_co
             /* ORT_CULL_UNROLL batches per pass: that many pairs of independent Philox multiply
              * chains in flight, and the loop / queue bookkeeping is paid once per pass.  Lanes
              * past the end of the slice compute a draw nobody uses. */
-            unsigned long long wa[ORT_CULL_UNROLL], wb[ORT_CULL_UNROLL];
+            unsigned long long hi[ORT_CULL_UNROLL];
             uint32_t id[ORT_CULL_UNROLL];
             bool pass[ORT_CULL_UNROLL];
 #pragma unroll
@@ -401,9 +403,9 @@ ort_ring_cull_kernel(const __grid_constant__ DevSceneT<float> F, const __grid_co
                 OrtRng g = ort_make_rng_prod(J, id[k]);
                 uint32_t w[4];
                 ort_philox4x32_10(g.r0, g.r1, g.phase, 1u, g.k0, g.k1, w, g.rk);
-                wa[k] = ((unsigned long long)w[1] << 32) | w[0];
-                wb[k] = ((unsigned long long)w[3] << 32) | w[2];
-                pass[k] = id[k] < nrays && wa[k] < aim_cut;
+                const unsigned long long wa = ((unsigned long long)w[1] << 32) | w[0];
+                hi[k] = ((unsigned long long)w[3] << 32) | w[1];
+                pass[k] = id[k] < nrays && wa < aim_cut;
             }
             b += (uint32_t)ORT_CULL_UNROLL * nwarps;
             const int before = n0;
@@ -413,20 +415,19 @@ ort_ring_cull_kernel(const __grid_constant__ DevSceneT<float> F, const __grid_co
                 if (pass[k]) {
                     int p = n0 + __popc(m & below);
                     ORT_ASSERT(p >= 0 && p < ORT_CULL_QCAP);
-                    q0.a[p] = wa[k]; q0.b[p] = wb[k]; q0.id[p] = id[k];
+                    q0.hi[p] = hi[k]; q0.id[p] = id[k];
                 }
                 n0 += __popc(m);
             }
             npassed += (unsigned)(n0 - before);
             __syncwarp();
         } else {
-            unsigned long long wa = 0, wb = 0;
-            uint32_t id = 0;
-            bool act = ort_slim_pop(q0, n0, wa, wb, id, lane);
+            uint32_t hi2 = 0, hi3 = 0, id = 0;
+            bool act = ort_slim_pop(q0, n0, hi2, hi3, id, lane);
             int st = -1;
             if (act) {
                 OrtRng g = ort_make_rng_prod(J, id);
-                st = VERIFY ? 0 : ort_ring_filter(F, J, g, ortf_uniform((uint32_t)(wa >> 32)), ortf_uniform((uint32_t)(wb >> 32)));
+                st = VERIFY ? 0 : ort_ring_filter(F, J, g, ortf_uniform(hi2), ortf_uniform(hi3));
                 /* one compare + one predicated add per status (left to itself the compiler builds
                  * add / conditional move / move triples here) */
                 ort_tally<ORT_ST_L2_SPHERE_MISS>(c10, st);
