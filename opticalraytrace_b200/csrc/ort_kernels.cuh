@@ -380,6 +380,7 @@ ort_ring_cull_kernel(const __grid_constant__ DevSceneT<float> F, const __grid_co
     const uint32_t nrays = (uint32_t)J.nrays;
     const uint32_t nbatches = (nrays + 31u) >> 5;
 
+    const uint32_t cut_hi = (uint32_t)(aim_cut >> 32);
     unsigned c10 = 0, c11 = 0, c12 = 0, c13 = 0, c14 = 0;
     unsigned npassed = 0; /* warp-uniform: rays of this warp that passed stage A */
     int nh = 0;           /* entries parked in q0.hb */
@@ -403,9 +404,11 @@ ort_ring_cull_kernel(const __grid_constant__ DevSceneT<float> F, const __grid_co
                 OrtRng g = ort_make_rng_prod(J, id[k]);
                 uint32_t w[4];
                 ort_philox4x32_10(g.r0, g.r1, g.phase, 1u, g.k0, g.k1, w, g.rk);
-                const unsigned long long wa = ((unsigned long long)w[1] << 32) | w[0];
                 hi[k] = ((unsigned long long)w[3] << 32) | w[1];
-                pass[k] = id[k] < nrays && wa < aim_cut;
+                /* decided on the high word alone; a draw whose high word EQUALS the cut's (2^-32 of
+                 * the rays) goes on: it sits on the aperture edge, where the filter hands it to
+                 * fp64, and ort_l2_enter there makes the exact call */
+                pass[k] = id[k] < nrays && w[1] <= cut_hi;
             }
             b += (uint32_t)ORT_CULL_UNROLL * nwarps;
             const int before = n0;
