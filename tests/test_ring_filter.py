@@ -186,3 +186,24 @@ def test_range_guard(orc, harness):
     assert not harness.ring_filter_in_range(job, pin)
     iris = abi.default_job(1, iris="before", iris_radius=0.01)
     assert not harness.ring_filter_in_range(iris, cases.scene_for(orc, cases.C2, 1))
+
+
+def test_high_word_rule_of_stage_a(orc, harness):
+    """The cull kernel decides stage A on the high 32 bits of the draw: below the cut's high word
+    the fp64 aperture expression must say inside, above it outside; only an equal high word
+    (2^-32 of the rays) is left to fp64."""
+    rng = np.random.default_rng(5)
+    scene = cases.scene_for(orc, cases.C2, 1)
+    cut, have = harness.ring_aim_cut(abi.default_job(1), scene)
+    assert have
+    cut_hi = cut >> 32
+    lens_r2 = (scene.L2.radius + 10e-3) ** 2
+    rad2 = scene.L2.radius ** 2
+    his = np.concatenate([rng.integers(0, 2 ** 32, 20000, dtype=np.uint64),
+                          np.array([cut_hi - 1, cut_hi + 1, 0, 2 ** 32 - 1], dtype=np.uint64)])
+    los = rng.integers(0, 2 ** 32, his.size, dtype=np.uint64)
+    for hi, lo in zip(his.tolist(), los.tolist()):
+        if hi == cut_hi:
+            continue
+        u2 = float(((hi << 32) | lo) >> 11) * 2.0 ** -53
+        assert (u2 * lens_r2 > rad2) == (hi > cut_hi)
