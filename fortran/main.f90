@@ -3,10 +3,11 @@ program raytrace
 ! Everything else -- setup_sim, the loaders and dispersion laws of src/lens.f90, the scalar
 ! prologue, trans-stats.dat, the transmission prints, writeImage -- is the reference's own code,
 ! linked unmodified (constants, utils, vector_class, stackMod, random_mod, stokes, imageMod,
-! surfaces, lens, sourceMod, setupMod).  source_type point, crs, isors and spot take this path;
-! image (SURVEY.md section 8(f)) does not yet.
+! surfaces, lens, sourceMod, setupMod).  All five source_types take this path (image: the budget
+! init_emit_image built in setup_sim is handed to the library), and so does the ray tracker.
 !
-! Not compiled in this repository's image (no Fortran compiler); see INTEGRATION.md.
+! UNCOMPILED: this repository's image has no Fortran compiler; tests/test_fortran_lint.py is the
+! stand-in (declarations, argument counts against the interfaces); see INTEGRATION.md.
 
     use lensMod,      only : plano_convex, achromatic_doublet, glass_bottle
     use utils,        only : str
@@ -42,7 +43,6 @@ program raytrace
     image = 0
 
     call setup_sim(L2, L3, bottle, imgin, nphotonsLocal)
-    if(image_source)error stop "B200 path: the image source_type is not wired up yet"
 
     filename = trim(adjustl(source_type))//"_bottle_"//str(use_bottle)//"_Ra_"// &
             str(bottle%radiusa,7)//"_Rb_"//str(bottle%radiusb,7)//"_offset_"//&
@@ -83,6 +83,11 @@ program raytrace
     if(crs_source)job%source_kind = ORT_SRC_CRS
     if(isors_source)job%source_kind = ORT_SRC_ISORS
     if(spot_source)job%source_kind = ORT_SRC_SPOT
+    if(image_source)then
+        ! emit_image (src/sourceMod.f90:303-361) scans imgin; the library searches its prefix sums
+        job%source_kind = ORT_SRC_IMAGE
+        if(ort_set_image_source(imgin) /= 0)error stop "ort_set_image_source failed"
+    end if
     job%iris_radius = iris_radius;  job%fibre_offset = fibre_offset;  job%image_diameter = image_diameter
     job%uniform_override = -1.d0
     job%seed = 123456789_c_int64_t          ! init_rng(123456789), src/main.f90:79
@@ -95,6 +100,11 @@ program raytrace
     if(rc /= 0 .and. rc /= ORT_ETRACE)error stop "ort_trace (ring) failed"
     rcount = lost(1)
     image(:, :, 1) = reshape(int(counts), [401, 401])
+    ! tracker, was src/main.f90:72-74,103,107 (+ src/optics_system.f90:28-50)
+    if(use_tracker)then
+        rc = ort_write_tracks(job, scene, folder//filename//"-ringtrace.dat"//c_null_char)
+        if(rc /= 0 .and. rc /= ORT_ETRACE)error stop "ort_write_tracks (ring) failed"
+    end if
 
     ! lenses at 843 nm for the point loop, src/main.f90:113-117
     wavelength = 843d-9
@@ -109,6 +119,11 @@ program raytrace
     if(rc /= 0 .and. rc /= ORT_ETRACE)error stop "ort_trace (point) failed"
     pcount = lost(1)
     image(:, :, 2) = reshape(int(counts), [401, 401])
+    ! tracker, was src/main.f90:121-124,144-160
+    if(use_tracker)then
+        rc = ort_write_tracks(job, scene, folder//filename//"-pointtrace.dat"//c_null_char)
+        if(rc /= 0 .and. rc /= ORT_ETRACE)error stop "ort_write_tracks (point) failed"
+    end if
     rc = ort_finalize()
 
     ! ---- epilogue, unchanged (src/main.f90:168-185) -------------------------------------------

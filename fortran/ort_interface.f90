@@ -6,9 +6,13 @@ module ort_interface
 ! c_double / c_int32_t / c_int64_t, so there is no padding surprise); `ort_struct_sizes` lets a
 ! program check that at start-up (see fortran/main.f90).
 !
-! NOTE: the build image has no Fortran compiler, so this file is kept deliberately thin and has
-! been checked by inspection only; tests/test_abi.py verifies that every bind(C) name below is
-! exported by libort.so.  Build line once a compiler is available:
+! NOTE: the build image has no Fortran compiler, so this file has never been through one
+! ("uncompiled").  What stands in for the compiler is tests/test_fortran_lint.py: it tokenises this
+! file and fails on any dummy argument without a declaration, on any `type, bind(C)` whose field
+! list (names, order, kinds, extents) differs from the C struct of the same name in include/ort.h,
+! on any parameter whose value differs from the #define of the same name, and on any bind(C)
+! name or argument count that differs from the C prototype; tests/test_abi.py checks that
+! libort.so exports every bind(C) name.  Build line once a compiler is available:
 !   gfortran -O2 -cpp -freal-4-real-8 fortran/ort_interface.f90 fortran/main.f90 \
 !            -Lopticalraytrace_b200 -lort -Wl,-rpath,$PWD/opticalraytrace_b200 -o bin/raytrace
 
@@ -20,7 +24,8 @@ module ort_interface
     integer(c_int), parameter :: ORT_IMG_N = 401, ORT_IMG_BINS = 401*401, ORT_NSTATUS = 32
     integer(c_int), parameter :: ORT_ETRACE = -7
     integer(c_int), parameter :: ORT_FLAG_NO_FILTER = 8, ORT_FLAG_VERIFY_FILTER = 16   ! ort_job%flags, ring loop
-    integer(c_int), parameter :: ORT_SRC_POINT = 0, ORT_SRC_CRS = 1, ORT_SRC_ISORS = 2, ORT_SRC_SPOT = 3
+    integer(c_int), parameter :: ORT_SRC_POINT = 0, ORT_SRC_CRS = 1, ORT_SRC_ISORS = 2, ORT_SRC_SPOT = 3, ORT_SRC_IMAGE = 4
+    integer(c_int), parameter :: ORT_SRCIMG_N = 512
 
     type, bind(C) :: ort_plano                 ! reference src/lens.f90:8-20
         real(c_double) :: thickness, diameter, radius, fb, f, n1, n2, curve_radius
@@ -119,6 +124,32 @@ module ort_interface
             integer(c_int64_t), intent(out) :: lost
             integer(c_int64_t), intent(out) :: status_hist(*)
         end function ort_trace_volume
+
+        ! source_type image: `budget` is imgin(512, 512) exactly as the reference's init_emit_image
+        ! (src/sourceMod.f90:363-408) leaves it -- default integer, Fortran memory order
+        integer(c_int) function ort_set_image_source(budget) bind(C, name="ort_set_image_source")
+            import :: c_int, c_int32_t
+            integer(c_int32_t), intent(in) :: budget(*)
+        end function ort_set_image_source
+
+        ! the library's own init_emit_image (counter-based draws instead of ran2): path is a
+        ! C string (trim(name)//c_null_char)
+        integer(c_int) function ort_load_image_source(path, nphotons, seed, budget) &
+                bind(C, name="ort_load_image_source")
+            import :: c_int, c_int32_t, c_int64_t, c_char
+            character(kind=c_char), intent(in)  :: path(*)
+            integer(c_int64_t),     value       :: nphotons, seed
+            integer(c_int32_t),     intent(out) :: budget(*)
+        end function ort_load_image_source
+
+        ! the ray tracker (src/stackMod.f90, src/main.f90:103-107,144-160): writes the trace file
+        ! of job%phase for rays first_ray .. first_ray+nrays-1 (nrays <= 10000)
+        integer(c_int) function ort_write_tracks(job, scene, path) bind(C, name="ort_write_tracks")
+            import :: c_int, c_char, ort_job, ort_scene
+            type(ort_job),          intent(in) :: job
+            type(ort_scene),        intent(in) :: scene
+            character(kind=c_char), intent(in) :: path(*)
+        end function ort_write_tracks
     end interface
 
 contains
@@ -133,6 +164,7 @@ contains
         type(achromatic_doublet), intent(in)  :: L3
         real,                     intent(in)  :: cosThetaMax, r1, r2, img_plane, point_offset
         type(ort_scene),          intent(out) :: s
+        real(c_double), optional, intent(in)  :: spot_size, isors_offset, ring_width
 
         s%bottle%nbottle = bottle%nbottle;   s%bottle%ncontents = bottle%ncontents
         s%bottle%thickness = bottle%thickness
