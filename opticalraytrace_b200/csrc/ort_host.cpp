@@ -420,9 +420,16 @@ int ort_load_image_source(const char* path, int64_t nphotons, uint64_t seed, int
         for (int j = 0; j < N; ++j) {
             double share = ((double)nphotons * f[(size_t)i * N + j]) / tot;
             long long whole = (long long)share;
-            double frac = share - (double)whole, u, unused;
+            double frac = share - (double)whole;
+            if (whole + 1 > (long long)INT32_MAX) {
+                /* the reference cannot get here (its nphotons is int32); a share this large would
+                 * wrap and be dropped silently */
+                ort_set_error("ort_load_image_source: pixel (%d,%d) would get %lld rays, more than an int32 budget "
+                              "holds; split the job", i + 1, j + 1, whole + 1);
+                return ORT_EINVAL;
+            }
             g.r0 = (uint32_t)(i * N + j);
-            ort_draw2(g, 0, &u, &unused);
+            const double u = ort_slot<double>(g, 0u);
             budget[(size_t)j * N + i] = (int32_t)((u < frac && frac > 0) ? whole + 1 : whole);
         }
     }

@@ -54,9 +54,16 @@ struct WarpQueue {
     R px[ORT_QCAP], py[ORT_QCAP], pz[ORT_QCAP], dx[ORT_QCAP], dy[ORT_QCAP], dz[ORT_QCAP];
     uint32_t id[ORT_QCAP]; /* ray index relative to DevJob.first_ray */
 };
+/* the queue in front of L2 also carries L2's two decision words (slots 4 and 5: words 3 of the
+ * Philox blocks 0 and 1 the emitting stage generated), so that L2 costs no generator call */
+template <typename R>
+struct WarpQueueL2 : WarpQueue<R> {
+    uint32_t wf[ORT_QCAP], wc[ORT_QCAP];
+};
 template <typename R>
 struct WarpShared {
-    WarpQueue<R> q[2];
+    WarpQueueL2<R> q0;
+    WarpQueue<R> q1;
 };
 
 __device__ __forceinline__ OrtRng ort_make_rng(const DevJob& J, uint32_t local_id) {
@@ -79,13 +86,15 @@ __device__ __forceinline__ OrtRng ort_make_rng_prod(const DevJob& J, uint32_t lo
     return g;
 }
 
-/* SLIM: the entry carries only (px, py) -- the ring loop's stage 0 hands on two uniforms */
+/* SLIM: the entry carries only (px, py) -- the ring loop's stage 0 hands on two uniforms.  Returns
+ * the slot the entry went to (or -1). */
 template <bool SLIM = false, typename R>
-__device__ __forceinline__ void ort_q_push(WarpQueue<R>& q, int& n, bool alive, const OrtRayT<R>& r,
-                                           uint32_t id, unsigned lane) {
+__device__ __forceinline__ int ort_q_push(WarpQueue<R>& q, int& n, bool alive, const OrtRayT<R>& r,
+                                          uint32_t id, unsigned lane) {
     unsigned m = __ballot_sync(ORT_FULL, alive);
+    int p = -1;
     if (alive) {
-        int p = n + __popc(m & ((1u << lane) - 1u));
+        p = n + __popc(m & ((1u << lane) - 1u));
         ORT_ASSERT(p >= 0 && p < ORT_QCAP);
         q.px[p] = r.px; q.py[p] = r.py;
         if (!SLIM) {
@@ -95,15 +104,16 @@ __device__ __forceinline__ void ort_q_push(WarpQueue<R>& q, int& n, bool alive, 
         q.id[p] = id;
     }
     n += __popc(m);
-    __syncwarp();
+    return p;
 }
+/* ... and the slot the entry came from (or -1) */
 template <bool SLIM = false, typename R>
-__device__ __forceinline__ bool ort_q_pop(WarpQueue<R>& q, int& n, OrtRayT<R>& r, uint32_t& id, unsigned lane) {
+__device__ __forceinline__ int ort_q_pop(WarpQueue<R>& q, int& n, OrtRayT<R>& r, uint32_t& id, unsigned lane) {
     int cnt = n < 32 ? n : 32;
     int base = n - cnt;
-    bool act = (int)lane < cnt;
-    if (act) {
-        int p = base + lane;
+    int p = -1;
+    if ((int)lane < cnt) {
+        p = base + lane;
         ORT_ASSERT(p >= 0 && p < ORT_QCAP);
         r.px = q.px[p]; r.py = q.py[p];
         if (!SLIM) {
@@ -113,8 +123,7 @@ __device__ __forceinline__ bool ort_q_pop(WarpQueue<R>& q, int& n, OrtRayT<R>& r
         id = q.id[p];
     }
     n = base;
-    __syncwarp();
-    return act;
+    return p;
 }
 
 /* Histogram of final ray statuses.  Every warp keeps one counter per status it can produce, as
@@ -168,39 +177,49 @@ __device__ __forceinline__ void ort_bin(unsigned long long* img, bool binned, in
  * C: the three refractions of L3, transfer to the image plane, acceptance + binning. */
 template <int PHASE, int BOTTLE, int SRC, typename R>
 __device__ __forceinline__ int ort_stage_a(const DevSceneT<R>& S, const DevJob& J, const OrtRng& g, uint32_t id,
-                                           OrtRayT<R>& r) {
+                                           OrtRayT<R>& r, uint32_t& wf, uint32_t& wc) {
     if (PHASE == ORT_PHASE_RING && SRC == ORT_SRC_POINT && S.ring_shortcut) {
-        R u2, u3;
-        ort_draw2(g, 1, &u2, &u3);
+        uint32_t b[4];
+        ort_block(g, 1u, b);
+        const R u2 = ort_bits_to_uniform<R>(b[0], b[1]);
         r.px = u2;
-        r.py = u3;
+        r.py = ort_word_to_uniform<R>(b[2]);
         r.pz = r.dx = r.dy = r.dz = R(0.0);
+        wf = 0u;
+        wc = b[3];
         return ort_ring_aims_outside_aperture(S, u2) ? ORT_ST_L2_APERTURE : 0;
     }
-    int es = ort_emit<PHASE, SRC>(S, J, g, J.first_ray + (long long)id, r);
+    OrtDraws01 D;
+    ort_draws01(g, D);
+    wf = D.a[3];
+    wc = D.b[3];
+    int es = ort_emit<PHASE, SRC>(S, J, g, D, J.first_ray + (long long)id, r);
     if (es) return es;
     if (PHASE == ORT_PHASE_POINT) {
         if (BOTTLE == 1) {
-            int st = ort_bottle_forward<false>(S, g, r);
+            int st = ort_bottle_forward<false>(S, g, D, r);
             if (st) return st;
         } else if (BOTTLE == 2) {
-            int st = ort_bottle_forward<true>(S, g, r);
+            int st = ort_bottle_forward<true>(S, g, D, r);
             if (st) return st;
         }
     }
     return ort_l2_enter(S, r);
 }
 template <int PHASE, int SRC, typename R>
-__device__ __forceinline__ int ort_stage_b(const DevSceneT<R>& S, const DevJob& J, const OrtRng& g, OrtRayT<R>& r) {
+__device__ __forceinline__ int ort_stage_b(const DevSceneT<R>& S, const DevJob& J, const OrtRng& g, OrtRayT<R>& r,
+                                           uint32_t wf, uint32_t wc) {
     if (PHASE == ORT_PHASE_RING && SRC == ORT_SRC_POINT && S.ring_shortcut) {
-        R u0, u1, u2 = r.px, u3 = r.py;
-        ort_draw2(g, 0, &u0, &u1);
-        ort_source_ring_u(S, u0, u1, u2, u3, r);
+        uint32_t a[4];
+        ort_block(g, 0u, a);
+        R u2 = r.px, u3 = r.py;
+        wf = a[3];
+        ort_source_ring_u(S, ort_bits_to_uniform<R>(a[0], a[1]), ort_word_to_uniform<R>(a[2]), u2, u3, r);
         int st0 = ort_l2_enter(S, r); /* same arithmetic as the general path; cannot fail except
                                          within rounding of the aperture edge */
         if (st0) return st0;
     }
-    int st = ort_l2_body(S, g, r);
+    int st = ort_l2_body(S, g, wf, wc, r);
     if (st) return st;
     return ort_l3_enter(S, J.iris_before != 0, r);
 }
@@ -267,24 +286,33 @@ ort_trace_kernel(const __grid_constant__ DevSceneT<R> S, const __grid_constant__
             id = b * 32u + lane;
             b += nwarps;
             int st = -1;
+            uint32_t wf = 0u, wc = 0u;
             if (id < nrays) {
                 OrtRng g = ort_make_rng_prod(J, id);
-                st = ort_stage_a<PHASE, BOTTLE, SRC>(S, J, g, id, r);
+                st = ort_stage_a<PHASE, BOTTLE, SRC>(S, J, g, id, r, wf, wc);
             }
-            if (slim) ort_q_push<true>(ws.q[0], n1, st == 0, r, id, lane);
-            else ort_q_push(ws.q[0], n1, st == 0, r, id, lane);
+            const int p = slim ? ort_q_push<true>(ws.q0, n1, st == 0, r, id, lane) : ort_q_push(ws.q0, n1, st == 0, r, id, lane);
+            if (p >= 0) {
+                if (!slim) ws.q0.wf[p] = wf;
+                ws.q0.wc[p] = wc;
+            }
+            __syncwarp();
             ort_count_a<PHASE, BOTTLE, SRC>(cnt, st);
         } else if (stage == 1) {
-            bool act = slim ? ort_q_pop<true>(ws.q[0], n1, r, id, lane) : ort_q_pop(ws.q[0], n1, r, id, lane);
+            const int p = slim ? ort_q_pop<true>(ws.q0, n1, r, id, lane) : ort_q_pop(ws.q0, n1, r, id, lane);
             int st = -1;
-            if (act) {
+            if (p >= 0) {
+                const uint32_t wf = slim ? 0u : ws.q0.wf[p], wc = ws.q0.wc[p];
                 OrtRng g = ort_make_rng_prod(J, id);
-                st = ort_stage_b<PHASE, SRC>(S, J, g, r);
+                st = ort_stage_b<PHASE, SRC>(S, J, g, r, wf, wc);
             }
-            ort_q_push(ws.q[1], n2, st == 0, r, id, lane);
+            __syncwarp();
+            ort_q_push(ws.q1, n2, st == 0, r, id, lane);
+            __syncwarp();
             ort_count_b(cnt, st);
         } else {
-            bool act = ort_q_pop(ws.q[1], n2, r, id, lane);
+            const bool act = ort_q_pop(ws.q1, n2, r, id, lane) >= 0;
+            __syncwarp();
             int st = -1, xp = 0, yp = 0;
             if (act) {
                 OrtRng g = ort_make_rng_prod(J, id);
@@ -320,23 +348,19 @@ ort_trace_kernel(const __grid_constant__ DevSceneT<R> S, const __grid_constant__
 #endif
 #define ORT_CULL_QCAP (32 + 32 * ORT_CULL_UNROLL) /* < 32 leftovers + the survivors of one pass */
 struct SlimQueue {
-    unsigned long long hi[ORT_CULL_QCAP]; /* the high words behind u2 (low half) and u3 (high half):
-                                             all the filter needs; fp64 regenerates the draws */
-    uint32_t id[ORT_CULL_QCAP];
-    uint32_t hb[64]; /* ray indices on their way to the survivors list */
+    uint4 e[ORT_CULL_QCAP]; /* x: high word of the aim-disc r^2 draw, y: aim angle word, z: L2 curved-face
+                               decision word (words 1, 2, 3 of the ray's block 1 -- all the filter
+                               needs of it; fp64 regenerates the block), w: ray index */
+    uint32_t hb[64];        /* ray indices on their way to the survivors list */
 };
-__device__ __forceinline__ bool ort_slim_pop(SlimQueue& q, int& n, uint32_t& hi2, uint32_t& hi3, uint32_t& id,
-                                             unsigned lane) {
+__device__ __forceinline__ bool ort_slim_pop(SlimQueue& q, int& n, uint4& e, unsigned lane) {
     int cnt = n < 32 ? n : 32;
     int base = n - cnt;
     bool act = (int)lane < cnt;
     if (act) {
         int p = base + lane;
         ORT_ASSERT(p >= 0 && p < ORT_CULL_QCAP);
-        unsigned long long h = q.hi[p];
-        hi2 = (uint32_t)h;
-        hi3 = (uint32_t)(h >> 32);
-        id = q.id[p];
+        e = q.e[p];
     }
     n = base;
     __syncwarp();
@@ -395,20 +419,19 @@ ort_ring_cull_kernel(const __grid_constant__ DevSceneT<float> F, const __grid_co
             /* ORT_CULL_UNROLL batches per pass: that many pairs of independent Philox multiply
              * chains in flight, and the loop / queue bookkeeping is paid once per pass.  Lanes
              * past the end of the slice compute a draw nobody uses. */
-            unsigned long long hi[ORT_CULL_UNROLL];
-            uint32_t id[ORT_CULL_UNROLL];
+            uint4 ent[ORT_CULL_UNROLL];
             bool pass[ORT_CULL_UNROLL];
 #pragma unroll
             for (int k = 0; k < ORT_CULL_UNROLL; ++k) {
-                id[k] = (b + (uint32_t)k * nwarps) * 32u + lane;
-                OrtRng g = ort_make_rng_prod(J, id[k]);
+                const uint32_t id = (b + (uint32_t)k * nwarps) * 32u + lane;
+                OrtRng g = ort_make_rng_prod(J, id);
                 uint32_t w[4];
-                ort_philox4x32_10(g.r0, g.r1, g.phase, 1u, g.k0, g.k1, w, g.rk);
-                hi[k] = ((unsigned long long)w[3] << 32) | w[1];
+                ort_block(g, 1u, w); /* w[0], the low word of the r^2 draw, is never formed */
+                ent[k] = make_uint4(w[1], w[2], w[3], id);
                 /* decided on the high word alone; a draw whose high word EQUALS the cut's (2^-32 of
                  * the rays) goes on: it sits on the aperture edge, where the filter hands it to
                  * fp64, and ort_l2_enter there makes the exact call */
-                pass[k] = id[k] < nrays && w[1] <= cut_hi;
+                pass[k] = id < nrays && w[1] <= cut_hi;
             }
             b += (uint32_t)ORT_CULL_UNROLL * nwarps;
             const int before = n0;
@@ -418,19 +441,20 @@ ort_ring_cull_kernel(const __grid_constant__ DevSceneT<float> F, const __grid_co
                 if (pass[k]) {
                     int p = n0 + __popc(m & below);
                     ORT_ASSERT(p >= 0 && p < ORT_CULL_QCAP);
-                    q0.hi[p] = hi[k]; q0.id[p] = id[k];
+                    q0.e[p] = ent[k];
                 }
                 n0 += __popc(m);
             }
             npassed += (unsigned)(n0 - before);
             __syncwarp();
         } else {
-            uint32_t hi2 = 0, hi3 = 0, id = 0;
-            bool act = ort_slim_pop(q0, n0, hi2, hi3, id, lane);
+            uint4 e = make_uint4(0u, 0u, 0u, 0u);
+            bool act = ort_slim_pop(q0, n0, e, lane);
+            const uint32_t id = e.w;
             int st = -1;
             if (act) {
                 OrtRng g = ort_make_rng_prod(J, id);
-                st = VERIFY ? 0 : ort_ring_filter(F, J, g, ortf_uniform(hi2), ortf_uniform(hi3));
+                st = VERIFY ? 0 : ort_ring_filter(F, J, g, e.x, e.y, e.z);
                 /* one compare + one predicated add per status (left to itself the compiler builds
                  * add / conditional move / move triples here) */
                 ort_tally<ORT_ST_L2_SPHERE_MISS>(c10, st);
@@ -509,19 +533,25 @@ ort_ring_survivors_kernel(const __grid_constant__ DevSceneT<double> S, const __g
             if (i < total) {
                 id = list[i];
                 OrtRng g = ort_make_rng_prod(J, id);
-                ort_draw2(g, 1, &r.px, &r.py);
-                if (VERIFY) verdict = ort_ring_filter(F, J, g, (float)r.px, (float)r.py);
+                uint32_t w[4];
+                ort_block(g, 1u, w);
+                r.px = ort_bits_to_uniform<double>(w[0], w[1]);
+                r.py = ort_word_to_uniform<double>(w[2]);
+                /* exactly the words the cull kernel hands the filter */
+                if (VERIFY) verdict = ort_ring_filter(F, J, g, w[1], w[2], w[3]);
                 r.pz = r.dx = r.dy = r.dz = 0.0;
-                st = ort_stage_b<ORT_PHASE_RING, ORT_SRC_POINT>(S, J, g, r);
+                st = ort_stage_b<ORT_PHASE_RING, ORT_SRC_POINT>(S, J, g, r, 0u, w[3]);
             }
             if (VERIFY) {
                 cnt.c[ORT_FILTER_SLOT_CALLED] += __popc(__ballot_sync(ORT_FULL, verdict > 0));
                 cnt.c[ORT_FILTER_SLOT_WRONG] += __popc(__ballot_sync(ORT_FULL, verdict > 0 && verdict != st));
             }
             ort_q_push(q, n2, st == 0, r, id, lane);
+            __syncwarp();
             ort_count_b(cnt, st);
         } else {
-            bool act = ort_q_pop(q, n2, r, id, lane);
+            const bool act = ort_q_pop(q, n2, r, id, lane) >= 0;
+            __syncwarp();
             int st = -1, xp = 0, yp = 0;
             if (act) {
                 OrtRng g = ort_make_rng_prod(J, id);
@@ -555,8 +585,9 @@ ort_trace_flat_kernel(const __grid_constant__ DevSceneT<R> S, const __grid_const
         if (id < nrays) {
             OrtRng g = ort_make_rng_prod(J, id);
             OrtRayT<R> r;
-            st = ort_stage_a<PHASE, BOTTLE, ORT_SRC_POINT>(S, J, g, id, r);
-            if (st == 0) st = ort_stage_b<PHASE, ORT_SRC_POINT>(S, J, g, r);
+            uint32_t wf, wc;
+            st = ort_stage_a<PHASE, BOTTLE, ORT_SRC_POINT>(S, J, g, id, r, wf, wc);
+            if (st == 0) st = ort_stage_b<PHASE, ORT_SRC_POINT>(S, J, g, r, wf, wc);
             if (st == 0) st = ort_stage_c(S, J, g, r, &xp, &yp);
         }
         ort_bin(img, st == ORT_ST_BINNED, xp, yp, lane);
@@ -639,10 +670,7 @@ __global__ void ort_uniforms_kernel(uint64_t seed, int32_t phase, int64_t ray, i
     g.r0 = (uint32_t)(uint64_t)ray; g.r1 = (uint32_t)((uint64_t)ray >> 32);
     g.phase = (uint32_t)phase;
     g.override_u = -1.0;
-    uint32_t slot = (uint32_t)(first_slot + i);
-    double a, b;
-    ort_draw2(g, slot >> 1, &a, &b);
-    out[i] = (slot & 1u) ? b : a;
+    out[i] = ort_slot<double>(g, (uint32_t)(first_slot + i));
 }
 
 /* FP64 FMA peak: 8 independent DFMA chains per thread, ITERS x 8 x 2 flops per thread */
@@ -679,8 +707,8 @@ __global__ void ort_math_selftest_kernel(long long n, unsigned long long* __rest
     OrtRng g;
     g.k0 = 0x5eedu; g.k1 = 0; g.rk = nullptr; g.r0 = (uint32_t)i; g.r1 = (uint32_t)(i >> 32); g.phase = 7; g.override_u = -1.0;
     double u0, u1, u2, u3;
-    ort_draw2(g, 0, &u0, &u1);
-    ort_draw2(g, 1, &u2, &u3);
+    ort_draw2(g, 8, &u0, &u1);
+    ort_draw2(g, 9, &u2, &u3);
     double x = exp2(80.0 * u0 - 40.0) * (1.0 + u1);
     double a = (exp2(80.0 * u2 - 40.0) * (1.0 + u3)) * ((i & 1) ? -1.0 : 1.0);
     atomicMax(worst + 0, ort_ulp_diff(ort_rcp(x), 1.0 / x));

@@ -362,14 +362,28 @@ ORT_HD float ort_sub_rn(float a, float b) {
 
 /* -------------------------------------------------------------------------------------------
  * Counter-based uniforms -- replaces the reference's ran2() (src/random_mod.f90:39-46).
- * Philox4x32-10, counter = (ray_lo, ray_hi, phase, block), key = (seed_lo, seed_hi).
- * Block b yields draw slots 2b and 2b+1; u = (64 bits >> 11) * 2^-53 in [0,1).
- * Slot map (fixed, independent of control flow):
- *   0,1  source (ring: r, theta | point: phi, cos theta)
- *   2,3  ring: aim-disc r, theta | point: bottle inner, outer reflect_refract
- *   4,5  L2 flat, L2 curved      6,7,8  L3 surfaces 1,2,3
- *   16.. scatter loops (tauint / albedo / stokes), consumed sequentially
+ * Philox4x32-7 (Salmon et al., SC'11: the 7-round variant is the fewest rounds that pass BigCrush,
+ * "Crush-resistant"; 10 is Random123's default with its safety margin).  counter = (ray_lo, ray_hi,
+ * phase, block), key = (seed_lo, seed_hi).  A block is four 32-bit words w0..w3 and serves
+ *     one WIDE draw   u = ((w1:w0) >> 11) * 2^-53   53 bits like gfortran's random_number: radial
+ *                     draws (annulus / aim-disc radius^2, cos theta), whose small values matter;
+ *     NARROW draws    u = w * 2^-32                 angles and reflect-or-refract decisions.
+ * Slot map, rev 2 (fixed, independent of control flow; `ort_uniforms` exposes it):
+ *     slot : block.words      ring loop                  point loop
+ *        0 : 0.w0w1 wide      annulus r^2                cos theta
+ *        1 : 0.w2             annulus angle              phi
+ *        2 : 1.w0w1 wide      aim-disc r^2               bottle inner wall decision
+ *        3 : 1.w2             aim-disc angle             bottle outer wall decision
+ *        4 : 0.w3             L2 flat decision           L2 flat decision
+ *        5 : 1.w3             L2 curved decision         L2 curved decision
+ *    6,7,8 : 2.w0 w1 w2       L3 surfaces 1, 2, 3        L3 surfaces 1, 2, 3       (9: 2.w3 spare)
+ *       10 : 3.w0w1 wide, 11 : 3.w2, 12 : 3.w3          image source: aim r^2, aim angle
+ *       13 : 4.w0w1 wide, 14 : 4.w2, 15 : 4.w3          spare
+ *     16.. : block slot/2, both halves wide              scatter loops / rang, consumed in order
+ * A whole ray needs three blocks (rev 1: five blocks of ten rounds); the ring loop's culling kernel
+ * needs block 1 for every ray and block 0 for the rays that pass L2's aperture.
  * ----------------------------------------------------------------------------------------- */
+#define ORT_PHILOX_ROUNDS 7
 struct OrtRng {
     uint32_t k0, k1;   /* seed */
     const uint32_t* rk; /* optional precomputed key schedule (DevJob.round_keys), or NULL */
@@ -378,11 +392,12 @@ struct OrtRng {
     double override_u; /* >= 0: every draw returns this */
 };
 
-ORT_HD void ort_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
-                              uint32_t k1, uint32_t* o, const uint32_t* rk = nullptr) {
+/* rounds [first, first + n) of Philox4x32; the key of round r is key + r * (W0, W1) */
+ORT_HD void ort_philox4x32_rounds(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                  uint32_t k1, uint32_t* o, const uint32_t* rk, int n) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < n; ++r) {
         uint32_t hi0 = ort_mulhi(M0, c0), lo0 = M0 * c0;
         uint32_t hi1 = ort_mulhi(M1, c2), lo1 = M1 * c2;
         uint32_t ka = rk ? rk[2 * r] : k0, kb = rk ? rk[2 * r + 1] : k1;
@@ -392,24 +407,65 @@ ORT_HD void ort_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3
     }
     o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
 }
+ORT_HD void ort_philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                           uint32_t k1, uint32_t* o, const uint32_t* rk = nullptr) {
+    ort_philox4x32_rounds(c0, c1, c2, c3, k0, k1, o, rk, ORT_PHILOX_ROUNDS);
+}
+/* the four words of block `block` of this ray */
+ORT_HD void ort_block(const OrtRng& g, uint32_t block, uint32_t* w) {
+    ort_philox4x32(g.r0, g.r1, g.phase, block, g.k0, g.k1, w, g.rk);
+}
 
 /* 64 random bits -> uniform in [0,1): 53 bits for double (like gfortran's random_number); the
- * fp32 variant takes the top 24 of the SAME bits, so both variants make the same decisions
- * except within 2^-24 of a threshold */
+ * fp32 variant rounds the SAME number to float, so both variants make the same decisions except
+ * within 2^-24 of a threshold */
 template <typename R> ORT_HD R ort_bits_to_uniform(uint32_t lo, uint32_t hi);
 template <> ORT_HD double ort_bits_to_uniform<double>(uint32_t lo, uint32_t hi) {
     uint64_t bits = (((uint64_t)hi << 32) | lo) >> 11;
     return (double)bits * (1.0 / 9007199254740992.0);
 }
 template <> ORT_HD float ort_bits_to_uniform<float>(uint32_t lo, uint32_t hi) {
-    /* the 53-bit uniform of the fp64 variant, rounded to float: full relative precision for
-     * small draws (an annulus radius is sqrt(u)); never 1.0f */
+    /* full relative precision for small draws (an annulus radius is sqrt(u)); never 1.0f */
     uint64_t bits = (((uint64_t)hi << 32) | lo) >> 11;
     float u = (float)bits * (1.0f / 9007199254740992.0f);
     return fminf(u, 0.99999994f);
 }
+/* one word -> uniform in [0,1): exact in double */
+template <typename R> ORT_HD R ort_word_to_uniform(uint32_t w);
+template <> ORT_HD double ort_word_to_uniform<double>(uint32_t w) { return (double)w * (1.0 / 4294967296.0); }
+template <> ORT_HD float ort_word_to_uniform<float>(uint32_t w) {
+    return fminf((float)w * (1.0f / 4294967296.0f), 0.99999994f);
+}
+/* the same with the known-answer-test override (ort_trace_rays only; folds away in the loops) */
+template <typename R>
+ORT_HD R ort_wide(const OrtRng& g, uint32_t lo, uint32_t hi) {
+    return g.override_u >= 0.0 ? (R)g.override_u : ort_bits_to_uniform<R>(lo, hi);
+}
+template <typename R>
+ORT_HD R ort_narrow(const OrtRng& g, uint32_t w) {
+    return g.override_u >= 0.0 ? (R)g.override_u : ort_word_to_uniform<R>(w);
+}
 
-/* the two uniforms of Philox block `block`: slots 2*block and 2*block+1 */
+/* draw slot -> (block, which words): the table above */
+template <typename R>
+ORT_HD R ort_slot(const OrtRng& g, uint32_t slot) {
+    if (g.override_u >= 0.0) return (R)g.override_u;
+    uint32_t w[4];
+    if (slot >= 16u) {
+        ort_block(g, slot >> 1, w);
+        return (slot & 1u) ? ort_bits_to_uniform<R>(w[2], w[3]) : ort_bits_to_uniform<R>(w[0], w[1]);
+    }
+    /* kind: 0 wide, 1 = w2, 2 = w3, 3..6 = w0..w3 of block 2 */
+    const uint32_t blk = slot < 6u ? ((slot == 4u) ? 0u : (slot == 5u) ? 1u : (slot >> 1)) : slot < 10u ? 2u : slot < 13u ? 3u : 4u;
+    ort_block(g, blk, w);
+    if (slot < 6u) return slot < 4u ? ((slot & 1u) ? ort_word_to_uniform<R>(w[2]) : ort_bits_to_uniform<R>(w[0], w[1]))
+                                    : ort_word_to_uniform<R>(w[3]);
+    if (slot < 10u) return ort_word_to_uniform<R>(w[slot - 6u]);
+    const uint32_t k = (slot - 10u) % 3u;
+    return k == 0u ? ort_bits_to_uniform<R>(w[0], w[1]) : ort_word_to_uniform<R>(w[1u + k]);
+}
+
+/* the two wide uniforms of Philox block `block` (scatter draws: slots 2*block and 2*block+1) */
 template <typename R>
 ORT_HD void ort_draw2(const OrtRng& g, uint32_t block, R* ua, R* ub) {
     if (g.override_u >= 0.0) {
@@ -418,7 +474,7 @@ ORT_HD void ort_draw2(const OrtRng& g, uint32_t block, R* ua, R* ub) {
         return;
     }
     uint32_t w[4];
-    ort_philox4x32_10(g.r0, g.r1, g.phase, block, g.k0, g.k1, w, g.rk);
+    ort_block(g, block, w);
     *ua = ort_bits_to_uniform<R>(w[0], w[1]);
     *ub = ort_bits_to_uniform<R>(w[2], w[3]);
 }
@@ -580,10 +636,21 @@ ORT_HD bool ort_interface(OrtRayT<R>& r, R nx, R ny, R nz, const DevIfaceT<R>& f
  * Sources (src/sourceMod.f90)
  * ----------------------------------------------------------------------------------------- */
 /* point, src/sourceMod.f90:12-47 */
+/* blocks 0 and 1 of a ray: every emitter and the two surfaces after it draw from these, and the
+ * two L2 decisions (a[3], b[3]) travel with the ray to L2 */
+struct OrtDraws01 {
+    uint32_t a[4], b[4];
+};
+ORT_HD void ort_draws01(const OrtRng& g, OrtDraws01& D) {
+    ort_block(g, 0u, D.a);
+    ort_block(g, 1u, D.b);
+}
+
 template <typename R>
-ORT_HD void ort_source_point(const DevSceneT<R>& S, const OrtRng& g, OrtRayT<R>& r) {
-    R u0, u1, sp, cp;
-    ort_draw2(g, 0, &u0, &u1);
+ORT_HD void ort_source_point(const DevSceneT<R>& S, const OrtRng& g, const OrtDraws01& D, OrtRayT<R>& r) {
+    R sp, cp;
+    const R u1 = ort_wide<R>(g, D.a[0], D.a[1]);  /* slot 0: cos theta */
+    const R u0 = ort_narrow<R>(g, D.a[2]);        /* slot 1: phi */
     ort_sincospi(R(2.0) * u0, &sp, &cp);
     R cost = fma(u1, S.cos_theta_max, R(1.0) - u1);
     R sint;
@@ -622,11 +689,9 @@ ORT_HD void ort_source_ring_u(const DevSceneT<R>& S, R u0, R u1, R u2, R u3, Ort
     r.dz = ez * inv;
 }
 template <typename R>
-ORT_HD void ort_source_ring(const DevSceneT<R>& S, const OrtRng& g, OrtRayT<R>& r) {
-    R u0, u1, u2, u3;
-    ort_draw2(g, 0, &u0, &u1);
-    ort_draw2(g, 1, &u2, &u3);
-    ort_source_ring_u(S, u0, u1, u2, u3, r);
+ORT_HD void ort_source_ring(const DevSceneT<R>& S, const OrtRng& g, const OrtDraws01& D, OrtRayT<R>& r) {
+    ort_source_ring_u(S, ort_wide<R>(g, D.a[0], D.a[1]), ort_narrow<R>(g, D.a[2]), ort_wide<R>(g, D.b[0], D.b[1]),
+                      ort_narrow<R>(g, D.b[2]), r);
 }
 /* When L2's flat face lies in the aim plane (DevSceneT<R>.ring_shortcut) the ray meets that face AT
  * its aim point, so the aperture test of src/lens.f90:450-454 is a test on u2 alone: 69 % of the
@@ -656,11 +721,11 @@ ORT_HD void ort_rang(const OrtRng& g, OrtScatterRngT<R>& sr, R sigma, R* x, R* y
 /* point_on_bottle, src/sourceMod.f90:50-89 (crs, ring loop): a Gaussian spot projected along -z
  * onto the cylinder of radius Ra + thickness, emitting into the cone of point() */
 template <typename R>
-ORT_HD bool ort_source_crs(const DevSceneT<R>& S, const OrtRng& g, OrtRayT<R>& r) {
+ORT_HD bool ort_source_crs(const DevSceneT<R>& S, const OrtRng& g, const OrtDraws01& D, OrtRayT<R>& r) {
     OrtScatterRngT<R> sr;
     sr.next = 16;
     sr.spare = R(0.0);
-    ort_source_point(S, g, r); /* same two draws, same direction formulas (:65-77) */
+    ort_source_point(S, g, D, r); /* same two draws, same direction formulas (:65-77) */
     R dx = r.dx, dy = r.dy, dz = r.dz, x, y;
     ort_rang(g, sr, S.spot_size, &x, &y);
     /* the reference drops the point from z = 1 along -z onto the cylinder of radius Ra + thickness
@@ -696,19 +761,30 @@ ORT_HD void ort_source_spot(const DevSceneT<R>& S, long long nrays, long long n,
     r.px = r.py = r.pz = R(0.0);
 }
 
-/* intersect_cone, src/surfaces.f90:179-224, for the axicon of iSORS */
+/* intersect_cone, src/surfaces.f90:179-224, for the axicon of iSORS.  The Gaussian beam is centred
+ * on the apex, where the discriminant b^2 - 4ac = 4 k rho^2 is the difference of two numbers ~1e9
+ * times larger: the reference's own answer is only good to ~1e-7 there, and any other operation
+ * order gives a different one.  So here, as in stokes, the arithmetic keeps the reference's order
+ * and is protected from FMA contraction (a once-per-ray source routine, not a hot spot). */
 template <typename R>
 ORT_HD bool ort_hit_cone(const OrtRayT<R>& r, R k, R height, R* t) {
-    R lz = r.pz - height;
-    R a = fma(r.dx, r.dx, fma(r.dy, r.dy, -k * r.dz * r.dz));
-    R h = fma(r.dx, r.px, fma(r.dy, r.py, -k * r.dz * lz));
-    R c = fma(r.px, r.px, fma(r.py, r.py, -k * lz * lz));
-    /* a < 0 here (steep ray), so the sign logic of ort_pick_root does not apply: both roots */
-    R disc = fma(h, h, -a * c);
+    const R lz = ort_sub_rn(r.pz, height);
+    const R a = ort_sub_rn(ort_add_rn(ort_mul_rn(r.dx, r.dx), ort_mul_rn(r.dy, r.dy)), ort_mul_rn(k, ort_mul_rn(r.dz, r.dz)));
+    const R b = ort_mul_rn(R(2.0), ort_sub_rn(ort_add_rn(ort_mul_rn(r.dx, r.px), ort_mul_rn(r.dy, r.py)),
+                                              ort_mul_rn(ort_mul_rn(k, r.dz), lz)));
+    const R c = ort_sub_rn(ort_add_rn(ort_mul_rn(r.px, r.px), ort_mul_rn(r.py, r.py)), ort_mul_rn(k, ort_mul_rn(lz, lz)));
+    /* solveQuadratic, src/surfaces.f90:227-260, and the root picking of :212-221 */
+    const R disc = ort_sub_rn(ort_mul_rn(b, b), ort_mul_rn(ort_mul_rn(R(4.0), a), c));
     if (disc < R(0.0)) return false;
-    R s = sqrt(disc);
-    R q = (h > R(0.0)) ? -(h + s) : (s - h);
-    R x0 = (disc == R(0.0)) ? -h / a : q / a, x1 = (disc == R(0.0)) ? x0 : c / q;
+    R x0, x1;
+    if (disc == R(0.0)) {
+        x0 = x1 = ort_mul_rn(-R(0.5), b) / a;
+    } else {
+        const R s = sqrt(disc);
+        const R q = ort_mul_rn(-R(0.5), (b > R(0.0)) ? ort_add_rn(b, s) : ort_sub_rn(b, s));
+        x0 = q / a;
+        x1 = c / q;
+    }
     R t0 = fmin(x0, x1), t1 = fmax(x0, x1);
     R tt = (t0 < R(0.0)) ? t1 : t0;
     if (tt < R(0.0)) return false;
@@ -719,16 +795,16 @@ ORT_HD bool ort_hit_cone(const OrtRayT<R>& r, R k, R height, R* t) {
 /* iSORS(ring = .true.), src/sourceMod.f90:162-247 (isors, ring loop).  false = the reference's
  * `error stop "no intersection with bottle!"` (every ray the axicon face reflects, ~2.8 %). */
 template <typename R>
-ORT_HD bool ort_source_isors(const DevSceneT<R>& S, const OrtRng& g, OrtRayT<R>& r) {
+ORT_HD bool ort_source_isors(const DevSceneT<R>& S, const OrtRng& g, const OrtDraws01& D, OrtRayT<R>& r) {
     OrtScatterRngT<R> sr;
     sr.next = 16;
     sr.spare = R(0.0);
-    R x, y, t, u_r, u_th, u_ax, unused;
+    R x, y, t;
     ort_rang(g, sr, S.isors_beam, &x, &y);
     r.px = x; r.py = y; r.pz = R(2.0) * S.isors_h;
     r.dx = R(0.0); r.dy = R(0.0); r.dz = -R(1.0);
-    ort_draw2(g, 0, &u_r, &u_th);
-    ort_draw2(g, 1, &u_ax, &unused);
+    const R u_r = ort_wide<R>(g, D.a[0], D.a[1]), u_th = ort_narrow<R>(g, D.a[2]); /* slots 0, 1 */
+    const R u_ax = ort_wide<R>(g, D.b[0], D.b[1]);                                  /* slot 2 */
     if (ort_hit_cone(r, S.isors_k, S.isors_h, &t)) {
         ort_advance(r, t);
         /* gradient of the cone, inverted (upper nappe), normalised */
@@ -755,9 +831,10 @@ ORT_HD bool ort_source_isors(const DevSceneT<R>& S, const OrtRng& g, OrtRayT<R>&
 /* emit_image + emit, src/sourceMod.f90:303-361 (image source, point loop): ray k leaves the pixel
  * the reference's budget scan reaches after k rays (binary search in the prefix sums), from a
  * uniform point inside it, aimed at a uniform point of L2's aperture disc.
- * Slots: x 0, y 1, aim radius 10, aim angle 11. */
+ * Slots: x 0, y 1, aim radius^2 10, aim angle 11. */
 template <typename R>
-ORT_HD bool ort_source_image(const DevSceneT<R>& S, const DevJob& J, const OrtRng& g, long long k, OrtRayT<R>& r) {
+ORT_HD bool ort_source_image(const DevSceneT<R>& S, const DevJob& J, const OrtRng& g, const OrtDraws01& D, long long k,
+                             OrtRayT<R>& r) {
     const long long npix = (long long)ORT_SRCIMG_N * ORT_SRCIMG_N;
     const long long* cdf = J.image_cdf;
     if (cdf == nullptr || k >= cdf[npix - 1]) return false;
@@ -769,9 +846,11 @@ ORT_HD bool ort_source_image(const DevSceneT<R>& S, const DevJob& J, const OrtRn
     }
     const R dx = R(5000e-6 / 512.);
     const R fj = (R)(lo % ORT_SRCIMG_N), fi = (R)(lo / ORT_SRCIMG_N); /* zero-based pixel */
-    R u0, u1, u2, u3, s, c;
-    ort_draw2(g, 0, &u0, &u1);
-    ort_draw2(g, 5, &u2, &u3);
+    R s, c;
+    uint32_t w3[4];
+    ort_block(g, 3u, w3);
+    const R u0 = ort_wide<R>(g, D.a[0], D.a[1]), u1 = ort_narrow<R>(g, D.a[2]);   /* slots 0, 1 */
+    const R u2 = ort_wide<R>(g, w3[0], w3[1]), u3 = ort_narrow<R>(g, w3[2]);      /* slots 10, 11 */
     R ax = fj * dx, bx = (fj + R(1.0)) * dx, ay = fi * dx, by = (fi + R(1.0)) * dx;
     r.px = fma(u0, bx - ax, ax) - R(2500e-6);
     r.py = fma(u1, by - ay, ay) - R(2500e-6);
@@ -789,15 +868,16 @@ ORT_HD bool ort_source_image(const DevSceneT<R>& S, const DevJob& J, const OrtRn
 /* source dispatch of src/main.f90:95-101 (ring loop) and :132-142 (point loop); SRC is
  * ort_job.source_kind.  Returns 0 or ORT_ST_SOURCE_MISS. */
 template <int PHASE, int SRC, typename R>
-ORT_HD int ort_emit(const DevSceneT<R>& S, const DevJob& J, const OrtRng& g, long long ray, OrtRayT<R>& r) {
+ORT_HD int ort_emit(const DevSceneT<R>& S, const DevJob& J, const OrtRng& g, const OrtDraws01& D, long long ray,
+                    OrtRayT<R>& r) {
     if (PHASE == ORT_PHASE_RING) {
-        if (SRC == ORT_SRC_CRS) return ort_source_crs(S, g, r) ? 0 : ORT_ST_SOURCE_MISS;
-        if (SRC == ORT_SRC_ISORS) return ort_source_isors(S, g, r) ? 0 : ORT_ST_SOURCE_MISS;
-        ort_source_ring(S, g, r);
+        if (SRC == ORT_SRC_CRS) return ort_source_crs(S, g, D, r) ? 0 : ORT_ST_SOURCE_MISS;
+        if (SRC == ORT_SRC_ISORS) return ort_source_isors(S, g, D, r) ? 0 : ORT_ST_SOURCE_MISS;
+        ort_source_ring(S, g, D, r);
     } else {
-        if (SRC == ORT_SRC_IMAGE) return ort_source_image(S, J, g, ray, r) ? 0 : ORT_ST_SOURCE_MISS;
+        if (SRC == ORT_SRC_IMAGE) return ort_source_image(S, J, g, D, ray, r) ? 0 : ORT_ST_SOURCE_MISS;
         if (SRC == ORT_SRC_SPOT) ort_source_spot(S, J.total_rays, ray + 1, r);
-        else ort_source_point(S, g, r);
+        else ort_source_point(S, g, D, r);
     }
     return 0;
 }
@@ -911,8 +991,9 @@ ORT_HD int ort_scatter_loop(const DevSceneT<R>& S, const OrtRng& g, OrtScatterRn
 }
 
 template <bool SCATTER, typename R>
-ORT_HD int ort_bottle_forward(const DevSceneT<R>& S, const OrtRng& g, OrtRayT<R>& r) {
-    R t, u_in, u_out;
+ORT_HD int ort_bottle_forward(const DevSceneT<R>& S, const OrtRng& g, const OrtDraws01& D, OrtRayT<R>& r) {
+    R t;
+    const R u_in = ort_wide<R>(g, D.b[0], D.b[1]), u_out = ort_narrow<R>(g, D.b[2]); /* slots 2, 3 */
     OrtScatterRngT<R> sr;
     sr.next = 16;
     sr.spare = R(0.0);
@@ -925,7 +1006,6 @@ ORT_HD int ort_bottle_forward(const DevSceneT<R>& S, const OrtRng& g, OrtRayT<R>
         if (st) return st;
     }
     ort_advance(r, t);
-    ort_draw2(g, 1, &u_in, &u_out);
     {   /* radial normal in the (y,z) plane, also for the ellipse (src/lens.f90:288-290) */
         R ny = S.bcy - r.py, nz = S.bcz - r.pz;
         /* on a clear cylindrical wall the hit point is on the cylinder: |(ny,nz)| = radius.  After
@@ -962,10 +1042,11 @@ ORT_HD int ort_l2_enter(const DevSceneT<R>& S, OrtRayT<R>& r) { /* :447-454 */
     if (fma(r.px, r.px, r.py * r.py) > S.l2_radius2) return ORT_ST_L2_APERTURE;
     return 0;
 }
+/* w_flat, w_curved: the decision words of slots 4 and 5 (words 3 of blocks 0 and 1) */
 template <typename R>
-ORT_HD int ort_l2_body(const DevSceneT<R>& S, const OrtRng& g, OrtRayT<R>& r) { /* :458-479 */
-    R u_flat, u_curved, t;
-    ort_draw2(g, 2, &u_flat, &u_curved);
+ORT_HD int ort_l2_body(const DevSceneT<R>& S, const OrtRng& g, uint32_t w_flat, uint32_t w_curved, OrtRayT<R>& r) { /* :458-479 */
+    R t;
+    const R u_flat = ort_narrow<R>(g, w_flat), u_curved = ort_narrow<R>(g, w_curved);
     /* a reflection at the flat face is computed but never tested */
     (void)ort_interface(r, S.l2_fnx, S.l2_fny, S.l2_fnz, S.l2_in, u_flat);
     if (!ort_hit_sphere(r, S.l2_cx, S.l2_cy, S.l2_cz, S.l2_R2, &t)) return ORT_ST_L2_SPHERE_MISS;
@@ -997,8 +1078,10 @@ ORT_HD int ort_l3_enter(const DevSceneT<R>& S, bool iris_before, OrtRayT<R>& r) 
 }
 template <typename R>
 ORT_HD int ort_l3_body(const DevSceneT<R>& S, const OrtRng& g, bool iris_after, OrtRayT<R>& r) { /* :582-644 */
-    R u1, u2, u3, unused, t, nx, ny, nz;
-    ort_draw2(g, 3, &u1, &u2);
+    R t, nx, ny, nz;
+    uint32_t w[4];
+    ort_block(g, 2u, w); /* slots 6, 7, 8 */
+    const R u1 = ort_narrow<R>(g, w[0]), u2 = ort_narrow<R>(g, w[1]), u3 = ort_narrow<R>(g, w[2]);
     ort_sphere_normal(r, S.l3_c1x, S.l3_c1y, S.l3_c1z, S.l3_invR1, &nx, &ny, &nz);
     if (ort_interface(r, nx, ny, nz, S.l3_s1, u1)) return ORT_ST_L3_S1_REFLECT;
     if (!ort_hit_sphere(r, S.l3_c2x, S.l3_c2y, S.l3_c2z, S.l3_R2_2, &t)) return ORT_ST_L3_S2_MISS;
@@ -1008,7 +1091,6 @@ ORT_HD int ort_l3_body(const DevSceneT<R>& S, const OrtRng& g, bool iris_after, 
     /* the reference aborts here on a miss (error stop "Help3", :617); we count it */
     if (!ort_hit_sphere(r, S.l3_c3x, S.l3_c3y, S.l3_c3z, S.l3_R3_2, &t)) return ORT_ST_L3_S3_MISS;
     ort_advance(r, t);
-    ort_draw2(g, 4, &u3, &unused);
     ort_sphere_normal(r, S.l3_c3x, S.l3_c3y, S.l3_c3z, S.l3_invR3, &nx, &ny, &nz);
     if (ort_interface(r, nx, ny, nz, S.l3_s3, u3)) return ORT_ST_L3_S3_REFLECT;
     if (iris_after) {
@@ -1117,9 +1199,10 @@ ORT_HD void ortf_sincos_turn(float u, float* s, float* c) {
     *c = cosf(a);
 #endif
 }
-/* the top 24 bits of the 53-bit uniform (the fp64 path's u differs by < 2^-24) */
-ORT_HD float ortf_uniform(uint32_t hi) {
-    return (float)(hi >> 8) * 5.9604644775390625e-8f;
+/* a uniform from one 32-bit word (a narrow draw, or the high word of a wide one), rounded to the
+ * nearest float: off the fp64 path's u by <= 2^-25 (+ 2^-32 for the unseen low word of a wide draw) */
+ORT_HD float ortf_uniform(uint32_t w) {
+    return (float)w * 2.3283064365386963e-10f;
 }
 
 /* The helpers below do not branch on a near-call: they OR it into `unc` and carry on with whatever
@@ -1174,13 +1257,15 @@ ORT_HD bool ortf_interface(OrtRayT<float>& r, float nx, float ny, float nz, cons
     return reflect;
 }
 
-/* (u2, u3): the aim-point uniforms the caller already holds; the other draws are regenerated */
-ORT_HD int ort_ring_filter(const DevSceneT<float>& F, const DevJob& J, const OrtRng& g, float u2, float u3) {
-    /* both Philox blocks up front: four independent multiply chains in flight instead of two */
-    uint32_t w[4], v[4];
-    ort_philox4x32_10(g.r0, g.r1, g.phase, 0u, g.k0, g.k1, w, g.rk);
-    ort_philox4x32_10(g.r0, g.r1, g.phase, 2u, g.k0, g.k1, v, g.rk);
-    float u0 = ortf_uniform(w[1]), u1 = ortf_uniform(w[3]);
+/* (h2, w_aim, w_curved): words 1, 2, 3 of the ray's block 1, which the caller already holds -- the
+ * high word of the aim-disc r^2 draw, the aim angle, L2's curved-face decision; block 0 (annulus
+ * r^2, annulus angle, L2's flat-face decision) is generated here */
+ORT_HD int ort_ring_filter(const DevSceneT<float>& F, const DevJob& J, const OrtRng& g, uint32_t h2, uint32_t w_aim,
+                           uint32_t w_curved) {
+    uint32_t w[4];
+    ort_block(g, 0u, w);
+    const float u0 = ortf_uniform(w[1]), u1 = ortf_uniform(w[2]);
+    const float u2 = ortf_uniform(h2), u3 = ortf_uniform(w_aim);
     /* ring source, ort_source_ring_u */
     OrtRayT<float> r;
     float s, c;
@@ -1207,12 +1292,12 @@ ORT_HD int ort_ring_filter(const DevSceneT<float>& F, const DevJob& J, const Ort
     r.py = ay;
     r.pz = F.l2_flat_z;
     /* L2, ort_l2_body; a reflection at the flat face is not tested by the reference: the ray goes on */
-    (void)ortf_interface(r, F.l2_fnx, F.l2_fny, F.l2_fnz, F.l2_in, ortf_uniform(v[1]), unc);
+    (void)ortf_interface(r, F.l2_fnx, F.l2_fny, F.l2_fnz, F.l2_in, ortf_uniform(w[3]), unc);
     float t;
     if (!ortf_hit_sphere(r, F.l2_cx, F.l2_cy, F.l2_cz, F.l2_R2, &t, unc)) return unc ? 0 : ORT_ST_L2_SPHERE_MISS;
     ort_advance(r, t);
     if (ortf_interface(r, (F.l2_cx - r.px) * F.l2_invR, (F.l2_cy - r.py) * F.l2_invR, (F.l2_cz - r.pz) * F.l2_invR,
-                       F.l2_out, ortf_uniform(v[3]), unc))
+                       F.l2_out, ortf_uniform(w_curved), unc))
         return unc ? 0 : ORT_ST_L2_CURVED_REFLECT;
     /* L3 up to its aperture, ort_l3_enter */
     if (J.iris_before) {
@@ -1240,29 +1325,31 @@ ORT_HD int ort_full_path(const DevSceneT<R>& S, const DevJob& J, const OrtRng& g
                          int* xp, int* yp) {
     const int stop = J.stop_after;
     int st;
+    OrtDraws01 D;
+    ort_draws01(g, D);
     if (!have_input) {
         long long ray = ((long long)g.r1 << 32) | g.r0;
         int es;
         if (J.phase == ORT_PHASE_RING) {
-            es = J.source_kind == ORT_SRC_CRS ? ort_emit<ORT_PHASE_RING, ORT_SRC_CRS>(S, J, g, ray, r)
-               : J.source_kind == ORT_SRC_ISORS ? ort_emit<ORT_PHASE_RING, ORT_SRC_ISORS>(S, J, g, ray, r)
-                                                : ort_emit<ORT_PHASE_RING, ORT_SRC_POINT>(S, J, g, ray, r);
+            es = J.source_kind == ORT_SRC_CRS ? ort_emit<ORT_PHASE_RING, ORT_SRC_CRS>(S, J, g, D, ray, r)
+               : J.source_kind == ORT_SRC_ISORS ? ort_emit<ORT_PHASE_RING, ORT_SRC_ISORS>(S, J, g, D, ray, r)
+                                                : ort_emit<ORT_PHASE_RING, ORT_SRC_POINT>(S, J, g, D, ray, r);
         } else {
-            es = J.source_kind == ORT_SRC_SPOT ? ort_emit<ORT_PHASE_POINT, ORT_SRC_SPOT>(S, J, g, ray, r)
-               : J.source_kind == ORT_SRC_IMAGE ? ort_emit<ORT_PHASE_POINT, ORT_SRC_IMAGE>(S, J, g, ray, r)
-                                                : ort_emit<ORT_PHASE_POINT, ORT_SRC_POINT>(S, J, g, ray, r);
+            es = J.source_kind == ORT_SRC_SPOT ? ort_emit<ORT_PHASE_POINT, ORT_SRC_SPOT>(S, J, g, D, ray, r)
+               : J.source_kind == ORT_SRC_IMAGE ? ort_emit<ORT_PHASE_POINT, ORT_SRC_IMAGE>(S, J, g, D, ray, r)
+                                                : ort_emit<ORT_PHASE_POINT, ORT_SRC_POINT>(S, J, g, D, ray, r);
         }
         if (es) return es;
     }
     if (stop == ORT_STOP_SOURCE) return ORT_ST_STOPPED;
     if (J.phase == ORT_PHASE_POINT && J.use_bottle) {
-        st = (S.scatter_b | S.scatter_c) ? ort_bottle_forward<true>(S, g, r) : ort_bottle_forward<false>(S, g, r);
+        st = (S.scatter_b | S.scatter_c) ? ort_bottle_forward<true>(S, g, D, r) : ort_bottle_forward<false>(S, g, D, r);
         if (st) return st;
     }
     if (stop == ORT_STOP_BOTTLE) return ORT_ST_STOPPED;
     st = ort_l2_enter(S, r);
     if (st) return st;
-    st = ort_l2_body(S, g, r);
+    st = ort_l2_body(S, g, D.a[3], D.b[3], r);
     if (st) return st;
     if (stop == ORT_STOP_L2) return ORT_ST_STOPPED;
     st = ort_l3_enter(S, J.iris_before != 0, r);

@@ -17,7 +17,7 @@
  *
  * The one deliberate difference from the reference: libgfortran's random_number (xoshiro256**,
  * src/random_mod.f90:39-46) is replaced -- as BASELINE.json's north_star prescribes -- by a
- * counter-based generator (Philox4x32-10) whose every uniform is a pure function of
+ * counter-based generator (Philox4x32-7) whose every uniform is a pure function of
  * (seed, phase, ray index, draw slot).  Build: see oracle/Makefile (-O2 -ffp-contract=off).
  */
 #include <cmath>
@@ -59,16 +59,23 @@ const double PI = 3.14159265358979323846;
 const double TWOPI = 2.0 * 3.14159265358979323846;
 
 /* ---------------------------------------------------------------------------------------
- * Counter-based uniforms: Philox4x32-10 (Salmon et al., SC'11; Random123 v1.14 constants).
+ * Counter-based uniforms: Philox4x32-7 (Salmon et al., SC'11; Random123 v1.14 constants; seven
+ * rounds is the variant that paper reports as the fewest that pass BigCrush).
  * Replaces src/random_mod.f90:39-46 (ran2).  counter = (ray_lo, ray_hi, phase, block),
- * key = (seed_lo, seed_hi); block b serves draw slots 2b and 2b+1;
- * u = (64 random bits >> 11) * 2^-53  in [0,1), 53 bits like gfortran's random_number.
+ * key = (seed_lo, seed_hi).  A block of four words w0..w3 serves one WIDE draw
+ * u = ((w1:w0) >> 11) * 2^-53 in [0,1) (53 bits like gfortran's random_number: the radial draws)
+ * and NARROW draws u = w * 2^-32 (angles, reflect-or-refract decisions).  Slot map, rev 2:
+ *    0: 0.w0w1 wide   1: 0.w2   2: 1.w0w1 wide   3: 1.w2   4: 0.w3   5: 1.w3
+ *    6..9: 2.w0..w3   10: 3.w0w1 wide  11: 3.w2  12: 3.w3  13: 4.w0w1 wide  14: 4.w2  15: 4.w3
+ *    16..: block slot/2, (w1:w0) for even and (w3:w2) for odd slots, both wide
  * ------------------------------------------------------------------------------------- */
-inline void philox4x32_10(const uint32_t ctr_in[4], const uint32_t key_in[2], uint32_t out[4]) {
+const int PHILOX_ROUNDS = 7;
+/* rounds [first, first + n) of Philox4x32 (the key of round r is key + r * (W0, W1)) */
+inline void philox4x32_rounds(const uint32_t ctr_in[4], const uint32_t key_in[2], int first, int n, uint32_t out[4]) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
     uint32_t c0 = ctr_in[0], c1 = ctr_in[1], c2 = ctr_in[2], c3 = ctr_in[3];
-    uint32_t k0 = key_in[0], k1 = key_in[1];
-    for (int r = 0; r < 10; ++r) {
+    uint32_t k0 = key_in[0] + (uint32_t)first * W0, k1 = key_in[1] + (uint32_t)first * W1;
+    for (int r = 0; r < n; ++r) {
         uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
         uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
         uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
@@ -81,10 +88,10 @@ inline void philox4x32_10(const uint32_t ctr_in[4], const uint32_t key_in[2], ui
 
 /* draw slots (fixed, independent of control-flow history) */
 enum {
-    SLOT_SRC0 = 0, /* ring: r        | point: phi  */
-    SLOT_SRC1 = 1, /* ring: theta    | point: cost */
-    SLOT_SRC2 = 2, /* ring: r lens   | point: bottle inner reflect_refract */
-    SLOT_SRC3 = 3, /* ring: th lens  | point: bottle outer reflect_refract */
+    SLOT_SRC0 = 0, /* wide.    ring: r^2       | point: cos theta */
+    SLOT_SRC1 = 1, /* narrow.  ring: theta     | point: phi */
+    SLOT_SRC2 = 2, /* wide.    ring: r^2 lens  | point: bottle inner reflect_refract */
+    SLOT_SRC3 = 3, /* narrow.  ring: th lens   | point: bottle outer reflect_refract */
     SLOT_L2_FLAT = 4,
     SLOT_L2_CURVED = 5,
     SLOT_L3_S1 = 6,
@@ -97,26 +104,45 @@ struct Draws {
     uint64_t seed, ray;
     uint32_t phase;
     double override_u;
-    uint32_t cached_block;
+    uint32_t fixed[5][4]; /* blocks 0..4, generated on first use */
+    unsigned have_fixed;
+    uint32_t cached_block; /* the scatter block in use */
     bool have;
     uint32_t w[4];
     uint32_t scatter_next;
     Draws(uint64_t seed_, uint32_t phase_, uint64_t ray_, double ov)
-        : seed(seed_), ray(ray_), phase(phase_), override_u(ov), cached_block(0), have(false),
-          scatter_next(SLOT_SCATTER0) {}
-    double slot(uint32_t k) {
-        if (override_u >= 0.0) return override_u;
-        uint32_t b = k >> 1;
-        if (!have || b != cached_block) {
-            uint32_t ctr[4] = {(uint32_t)ray, (uint32_t)(ray >> 32), phase, b};
-            uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
-            philox4x32_10(ctr, key, w);
-            cached_block = b;
-            have = true;
-        }
-        uint32_t lo = w[2 * (k & 1)], hi = w[2 * (k & 1) + 1];
+        : seed(seed_), ray(ray_), phase(phase_), override_u(ov), fixed{}, have_fixed(0), cached_block(0),
+          have(false), w{}, scatter_next(SLOT_SCATTER0) {}
+    void generate(uint32_t b, uint32_t* out) const {
+        uint32_t ctr[4] = {(uint32_t)ray, (uint32_t)(ray >> 32), phase, b};
+        uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+        philox4x32_rounds(ctr, key, 0, PHILOX_ROUNDS, out);
+    }
+    static double wide(uint32_t lo, uint32_t hi) {
         uint64_t bits = ((uint64_t)hi << 32) | lo;
         return (double)(bits >> 11) * (1.0 / 9007199254740992.0);
+    }
+    static double narrow(uint32_t x) { return (double)x * (1.0 / 4294967296.0); }
+    double slot(uint32_t k) {
+        if (override_u >= 0.0) return override_u;
+        if (k >= 16) {
+            uint32_t b = k >> 1;
+            if (!have || b != cached_block) {
+                generate(b, w);
+                cached_block = b;
+                have = true;
+            }
+            return (k & 1) ? wide(w[2], w[3]) : wide(w[0], w[1]);
+        }
+        static const unsigned char blk[16] = {0, 0, 1, 1, 0, 1, 2, 2, 2, 2, 3, 3, 3, 4, 4, 4};
+        static const signed char word[16] = {-1, 2, -1, 2, 3, 3, 0, 1, 2, 3, -1, 2, 3, -1, 2, 3}; /* -1: wide */
+        const unsigned b = blk[k];
+        if (!(have_fixed & (1u << b))) {
+            generate(b, fixed[b]);
+            have_fixed |= 1u << b;
+        }
+        const uint32_t* f = fixed[b];
+        return word[k] < 0 ? wide(f[0], f[1]) : narrow(f[word[k]]);
     }
     double scatter() { return slot(scatter_next++); }
 };
@@ -388,10 +414,10 @@ L100:
  * ------------------------------------------------------------------------------------- */
 /* point, src/sourceMod.f90:12-47 */
 inline void source_point(vec& pos, vec& dir, double cosThetaMax, double offset, Draws& rng) {
-    double phi = TWOPI * rng.slot(SLOT_SRC0);
+    double phi = TWOPI * rng.slot(SLOT_SRC1);
     double cosp = std::cos(phi);
     double sinp = std::sin(phi);
-    double ran = rng.slot(SLOT_SRC1);
+    double ran = rng.slot(SLOT_SRC0);
     double cost = (1.0 - ran) + ran * cosThetaMax;
     double sint = std::sqrt(1.0 - cost * cost);
     dir = {sint * cosp, sint * sinp, cost};
@@ -448,10 +474,10 @@ inline void rang(double& x, double& y, double avg, double sigma, Draws& rng) {
  * the spot point misses the cylinder (the reference then uses an undefined t). */
 inline bool source_crs(vec& pos, vec& dir, double cosThetaMax, const ort_bottle& B, double spot_radius,
                        Draws& rng) {
-    double phi = TWOPI * rng.slot(SLOT_SRC0);
+    double phi = TWOPI * rng.slot(SLOT_SRC1);
     double cosp = std::cos(phi);
     double sinp = std::sin(phi);
-    double ran = rng.slot(SLOT_SRC1);
+    double ran = rng.slot(SLOT_SRC0);
     double cost = (1.0 - ran) + ran * cosThetaMax;
     double sint = std::sqrt(1.0 - cost * cost);
     double nxp = sint * cosp, nyp = sint * sinp, nzp = cost;
@@ -1016,10 +1042,13 @@ int orc_uniforms(uint64_t seed, int32_t phase, int64_t ray, int32_t first_slot, 
     return 0;
 }
 
-int orc_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
-    philox4x32_10(ctr, key, out);
+/* rounds [first, first + n) of Philox4x32: (0, 10) is Random123's philox4x32-10, (0, 7) the
+ * generator used here, and (7, 3) applied to the latter's output must give the former */
+int orc_philox(const uint32_t* ctr, const uint32_t* key, int32_t first, int32_t n, uint32_t* out) {
+    philox4x32_rounds(ctr, key, first, n, out);
     return 0;
 }
+int orc_philox_rounds(void) { return PHILOX_ROUNDS; }
 
 /* Same contract as ort_trace_rays (include/ort.h). */
 int orc_trace_rays(const ort_job* job, const ort_scene* scene, int64_t n, const double* pos_in,

@@ -40,13 +40,13 @@ def main():
         images["%s/cnt" % cid] = img[0].ravel()[nz].astype(np.int32)
         images["%s/hist" % cid] = hist[0]
         images["%s/lost" % cid] = lost
-    np.savez_compressed(os.path.join(HERE, "rays_v1.npz"), **rays)
-    np.savez_compressed(os.path.join(HERE, "images_v1.npz"), **images)
+    np.savez_compressed(os.path.join(HERE, "rays_v2.npz"), **rays)
+    np.savez_compressed(os.path.join(HERE, "images_v2.npz"), **images)
     # first uniforms of three rays of each phase: freezes the generator + slot map
     u = {"p%d/r%d" % (p, r): O.uniforms(123456789, p, r, 0, 24)
          for p in (1, 2) for r in (0, 1, 2 ** 33 + 5)}
-    np.savez_compressed(os.path.join(HERE, "uniforms_v1.npz"), **u)
-    for f in ("rays_v1.npz", "images_v1.npz", "uniforms_v1.npz"):
+    np.savez_compressed(os.path.join(HERE, "uniforms_v2.npz"), **u)
+    for f in ("rays_v2.npz", "images_v2.npz", "uniforms_v2.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
 
 

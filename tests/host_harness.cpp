@@ -91,9 +91,10 @@ extern "C" int hh_ring_filter(const ort_job* job, const ort_scene* scene, int64_
         g.r0 = (uint32_t)ray; g.r1 = (uint32_t)(ray >> 32);
         g.phase = (uint32_t)J.phase;
         g.override_u = -1.0;
-        double u2, u3;
-        ort_draw2(g, 1, &u2, &u3);
-        verdict[i] = ort_ring_aims_outside_aperture(S, u2) ? -1 : ort_ring_filter(F, J, g, (float)u2, (float)u3);
+        uint32_t w[4];
+        ort_block(g, 1u, w);
+        const double u2 = ort_bits_to_uniform<double>(w[0], w[1]);
+        verdict[i] = ort_ring_aims_outside_aperture(S, u2) ? -1 : ort_ring_filter(F, J, g, w[1], w[2], w[3]);
     }
     return S.ring_shortcut;
 }

@@ -126,9 +126,9 @@ def reflect_refract(I, N, n1, n2, u):   # src/surfaces.f90:262-333 -> (new I, re
 
 
 def source_point(cos_theta_max, offset, u):     # src/sourceMod.f90:12-47
-    phi = TWOPI * u(0)
+    phi = TWOPI * u(1)   # slot 1 (narrow draw); cos theta takes the wide slot 0
     cosp, sinp = math.cos(phi), math.sin(phi)
-    ran = u(1)
+    ran = u(0)
     cost = (1.0 - ran) + ran * cos_theta_max
     sint = math.sqrt(1.0 - cost ** 2)
     return (0.0, 0.0, 0.0 + offset), (sint * cosp, sint * sinp, cost)

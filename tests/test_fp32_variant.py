@@ -17,7 +17,18 @@ TOL32 = 1e-5
 def _check(a, b, n):
     same = a["status"] == b["status"]
     assert np.mean(~same) < 5e-4                       # decisions flip only next to a threshold
-    e = np.maximum(rel_err(a["pos"][:, same], b["pos"][:, same]), rel_err(a["dir"][:, same], b["dir"][:, same]))
+    # a ray rejected by the NA test or flagged FAR was carried to the image plane along a direction
+    # that may be almost parallel to it: its position there is pos + dir * (z / dir.z), arbitrarily
+    # ill-conditioned, so only its direction is compared
+    skew = np.isin(a["status"][same], (21, 22))
+    e_pos = np.where(skew, 0.0, rel_err(a["pos"][:, same], b["pos"][:, same]))
+    e = np.maximum(e_pos, rel_err(a["dir"][:, same], b["dir"][:, same]))
+    # a flipped decision can still end in the same status (reflected at L2's flat face and then at the
+    # back of its sphere, against transmitted and reflected at the curved face: both status 11); such
+    # rays are somewhere else entirely and count as flips, not as numerical error
+    elsewhere = e > 1e-2
+    assert (np.sum(~same) + np.sum(elsewhere)) / n < 5e-4
+    e = e[~elsewhere]
     assert np.nanquantile(e, 0.999) < TOL32, np.nanquantile(e, 0.999)
     assert np.nanmedian(e) < 1e-6
     assert np.nanmax(e) < 1e-3                         # isolated grazing / near-TIR rays

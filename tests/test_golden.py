@@ -18,8 +18,8 @@ NRAYS, NIMG = 96, 200_000
 
 @pytest.fixture(scope="module")
 def gold():
-    return (np.load(os.path.join(HERE, "rays_v1.npz")), np.load(os.path.join(HERE, "images_v1.npz")),
-            np.load(os.path.join(HERE, "uniforms_v1.npz")))
+    return (np.load(os.path.join(HERE, "rays_v2.npz")), np.load(os.path.join(HERE, "images_v2.npz")),
+            np.load(os.path.join(HERE, "uniforms_v2.npz")))
 
 
 def _dense(g, cid):

@@ -12,33 +12,75 @@ from opticalraytrace_b200 import abi
 from tests import cases, pyref
 
 
-def test_philox_random123_vectors(orc):
-    """Random123 kat_vectors, philox4x32-10."""
-    L = orc.lib()
+RANDOM123_KAT = [  # Random123 kat_vectors, philox4x32-10: (counter, key, output)
+    ([0] * 4, [0] * 2, [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+    ([0xffffffff] * 4, [0xffffffff] * 2, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+    ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0],
+     [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]),
+]
 
-    def ph(c, k):
-        c = (C.c_uint32 * 4)(*c)
-        k = (C.c_uint32 * 2)(*k)
-        o = (C.c_uint32 * 4)()
-        L.orc_philox(c, k, o)
-        return list(o)
-    assert ph([0] * 4, [0] * 2) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
-    assert ph([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
-    assert ph([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
-        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+def _philox(L, c, k, first, n):
+    c = (C.c_uint32 * 4)(*c)
+    k = (C.c_uint32 * 2)(*k)
+    o = (C.c_uint32 * 4)()
+    L.orc_philox(c, k, first, n, o)
+    return list(o)
+
+
+def test_philox_random123_vectors(orc):
+    """The round function and key schedule against the published philox4x32-10 vectors, and the
+    7-round generator used here pinned to them: rounds 7..9 applied to its output must give the
+    published 10-round output (a Philox round is a bijection, so this determines the 7-round
+    output uniquely)."""
+    L = orc.lib()
+    assert L.orc_philox_rounds() == 7
+    for c, k, out in RANDOM123_KAT:
+        assert _philox(L, c, k, 0, 10) == out
+        seven = _philox(L, c, k, 0, 7)
+        assert seven != out
+        assert _philox(L, seven, k, 7, 3) == out
+
+
+def test_slot_map_rev2(orc):
+    """the slot -> (block, words) table of the generator, from raw blocks"""
+    L = orc.lib()
+    seed, phase, ray = 0x123456789abcdef0, 2, 0x1_0000_0007
+    key = [seed & 0xffffffff, seed >> 32]
+    blk = [_philox(L, [ray & 0xffffffff, ray >> 32, phase, b], key, 0, 7) for b in range(12)]
+    wide = lambda w, h=0: float((((w[2 * h + 1] << 32) | w[2 * h]) >> 11)) * 2.0 ** -53
+    narrow = lambda x: x * 2.0 ** -32
+    want = [wide(blk[0]), narrow(blk[0][2]), wide(blk[1]), narrow(blk[1][2]), narrow(blk[0][3]), narrow(blk[1][3]),
+            narrow(blk[2][0]), narrow(blk[2][1]), narrow(blk[2][2]), narrow(blk[2][3]),
+            wide(blk[3]), narrow(blk[3][2]), narrow(blk[3][3]), wide(blk[4]), narrow(blk[4][2]), narrow(blk[4][3]),
+            wide(blk[8]), wide(blk[8], 1), wide(blk[9]), wide(blk[9], 1), wide(blk[10]), wide(blk[10], 1)]
+    got = orc.uniforms(seed, phase, ray, 0, len(want))
+    assert list(got) == want
 
 
 def test_uniform_stream_properties(orc):
-    u = np.concatenate([orc.uniforms(123456789, 1, r, 0, 10) for r in range(20000)])
+    u = np.stack([orc.uniforms(123456789, 1, r, 0, 20) for r in range(20000)])
     assert u.min() >= 0.0 and u.max() < 1.0
     assert abs(u.mean() - 0.5) < 5e-3 and abs(u.var() - 1 / 12) < 2e-3
+    # every slot is uniform on its own (chi-square over 64 cells, 20000 samples: mean 63, sd 11.2) ...
+    for k in range(20):
+        h = np.bincount((u[:, k] * 64).astype(int), minlength=64)
+        assert ((h - 312.5) ** 2 / 312.5).sum() < 63 + 5 * 11.2, k
+    # ... uncorrelated with every other slot of the same ray and with the same slot of the next ray
+    cc = np.corrcoef(u.T)
+    assert np.abs(cc - np.eye(20)).max() < 0.04
+    for k in range(20):
+        assert abs(np.corrcoef(u[:-1, k], u[1:, k])[0, 1]) < 0.04
     # pure function of (seed, phase, ray, slot): slots can be fetched in any grouping
-    a = orc.uniforms(5, 2, 77, 0, 12)
-    b = np.concatenate([orc.uniforms(5, 2, 77, 0, 5), orc.uniforms(5, 2, 77, 5, 7)])
+    a = orc.uniforms(5, 2, 77, 0, 24)
+    b = np.concatenate([orc.uniforms(5, 2, 77, 0, 5), orc.uniforms(5, 2, 77, 5, 19)])
     assert np.array_equal(a, b)
     assert not np.array_equal(orc.uniforms(5, 1, 77, 0, 4), orc.uniforms(5, 2, 77, 0, 4))
-    # 53-bit resolution: u * 2^53 is an integer
+    # wide draws have 53-bit resolution, narrow ones 32-bit
     assert np.all(np.mod(a * 2.0 ** 53, 1.0) == 0.0)
+    narrow = [1, 3, 4, 5, 6, 7, 8, 9, 11, 12, 14, 15]
+    assert np.all(np.mod(a[narrow] * 2.0 ** 32, 1.0) == 0.0)
+    assert np.any(np.mod(a[[0, 2, 10, 13, 16, 17]] * 2.0 ** 32, 1.0) != 0.0)
 
 
 def test_dispersion_constants(orc):
