@@ -286,6 +286,15 @@ int ort_measure_fp64_peak(double* tflops, double* sm_clock_mhz);
  * error in units of the last place over n pseudo-random operands (order: rcp, div, sqrt, rsqrt). */
 int ort_math_selftest(int64_t n, uint64_t max_ulp[4]);
 
+/* The ring loop's single-precision filter rests its error bound on the
+ * accuracy of five hardware approximations (rcp, rsqrt, sqrt, sin, cos .approx.ftz.f32).  This runs
+ * all 2^32 fp32 bit patterns through them on device 0 against fp64 references:
+ * worst[0..2] = largest relative error of rcp / rsqrt / sqrt (|x| in [2^-64, 2^64]),
+ * worst[3..4] = largest absolute error of sin / cos (|x| <= 3.1416);  assumed[] (may be NULL) receives
+ * what the filter's bounds assume -- at least twice the measured value, or the proof does not hold
+ * on this device. */
+int ort_mufu_selftest(double worst[5], double assumed[5]);
+
 /* ---- host side of the drop-in surface (no device needed) -------------------------------- */
 int ort_load_plano(const char* path, double wavelength, double offset, ort_plano* out);
 int ort_load_doublet(const char* path, double wavelength, double offset, ort_doublet* out);

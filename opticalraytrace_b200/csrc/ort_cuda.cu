@@ -15,6 +15,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <utility>
 #include <vector>
 
 #include "ort_internal.h"
@@ -118,6 +119,14 @@ struct DeviceCtx {
     cudaEvent_t ev_cull[2] = {nullptr, nullptr}, ev_surv[2] = {nullptr, nullptr};
     unsigned* d_nlist = nullptr;      /* ... and the length of that list, one slot per slice */
     size_t nlist_cap = 0;
+    /* resident blocks per SM of every kernel launched so far (the attribute set-up and the
+     * occupancy query are done once per kernel and device, not once per scene of a batch) */
+    std::vector<std::pair<const void*, int>> occ;
+    /* grow-only device scratch of the entry points beside ort_trace (explicit ray lists, the
+     * volume image, the generator's test entry): kept until ort_finalize instead of a
+     * cudaMalloc / cudaFree pair per call */
+    void* scratch[3] = {nullptr, nullptr, nullptr};
+    size_t scratch_bytes[3] = {0, 0, 0};
 };
 struct LibState {
     bool ready = false;
@@ -158,6 +167,34 @@ static int ctx_open(DeviceCtx& c, int dev) {
     return ORT_OK;
 }
 
+/* resident blocks per SM of `fn` with `smem` bytes of dynamic shared memory (cached) */
+static int ctx_occupancy(DeviceCtx& c, const void* fn, size_t smem, int* occ) {
+    for (auto& e : c.occ)
+        if (e.first == fn) {
+            *occ = e.second;
+            return ORT_OK;
+        }
+    if (smem) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int o = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, fn, ORT_TPB, smem));
+    if (o < 1) o = 1;
+    c.occ.emplace_back(fn, o);
+    *occ = o;
+    return ORT_OK;
+}
+/* grow-only scratch buffer `slot` of at least `bytes` */
+static int ctx_scratch(DeviceCtx& c, int slot, size_t bytes, void** out) {
+    if (c.scratch_bytes[slot] < bytes) {
+        if (c.scratch[slot]) CK(cudaFree(c.scratch[slot]));
+        c.scratch[slot] = nullptr;
+        c.scratch_bytes[slot] = 0;
+        CK(cudaMalloc(&c.scratch[slot], bytes));
+        c.scratch_bytes[slot] = bytes;
+    }
+    *out = c.scratch[slot];
+    return ORT_OK;
+}
+
 extern "C" int ort_finalize(void) {
     for (auto& c : g.devs) {
         if (c.dev < 0) continue;
@@ -167,6 +204,8 @@ extern "C" int ort_finalize(void) {
         if (c.d_image_cdf) cudaFree(c.d_image_cdf);
         if (c.d_list) cudaFree(c.d_list);
         if (c.d_nlist) cudaFree(c.d_nlist);
+        for (void* p : c.scratch)
+            if (p) cudaFree(p);
         if (c.ev_start) cudaEventDestroy(c.ev_start);
         if (c.ev_traced) cudaEventDestroy(c.ev_traced);
         if (c.ev_reduced) cudaEventDestroy(c.ev_reduced);
@@ -374,42 +413,45 @@ static const int64_t ORT_CHUNK = (int64_t)1 << 31; /* rays per scene per launch 
 /* The ring loop's four-stage kernel with the fp32 culling filter (ort_kernels.cuh): fp64 jobs with
  * the default ring source on scenes whose L2 flat face lies in the aim plane. */
 template <typename R>
-static bool ring_filter_applies(const ort_job& job, const DevScene& s, bool flat, unsigned long long* aim_cut) {
-    return sizeof(R) == sizeof(double) && !flat && job.phase == ORT_PHASE_RING && s.ring_shortcut &&
-           (job.source_kind == ORT_SRC_POINT || job.source_kind == ORT_SRC_SPOT) &&
-           !(job.flags & ORT_FLAG_NO_FILTER) && ort_ring_filter_in_range(s, job.iris_before != 0) &&
-           ort_ring_aim_cut(s, aim_cut);
+static bool ring_filter_applies(const ort_job& job, const DevScene& s, bool flat, unsigned long long* aim_cut,
+                                DevFilter* K) {
+    if (!(sizeof(R) == sizeof(double) && !flat && job.phase == ORT_PHASE_RING && s.ring_shortcut &&
+          (job.source_kind == ORT_SRC_POINT || job.source_kind == ORT_SRC_SPOT) && !(job.flags & ORT_FLAG_NO_FILTER)))
+        return false;
+    ort_make_filter(s, job.iris_before != 0, *K);
+    return K->usable == 2 && ort_ring_aim_cut(s, aim_cut);
 }
 /* Slice of the ray range per cull/survivors launch pair: long enough that the tail of a launch
  * is < 1 % of it, short enough that the list of ray indices stays a few hundred MB. */
 static const int64_t ORT_RING_SLICE = (int64_t)1 << 29;
 
-static int enqueue_ring_filter(DeviceCtx& c, const ort_job& job, const DevScene& s, unsigned long long aim_cut,
-                               int nscenes, int64_t first, int64_t n, unsigned long long* d_img,
+static int enqueue_ring_filter(DeviceCtx& c, const ort_job& job, const DevScene& s, const DevFilter& K,
+                               unsigned long long aim_cut, int nscenes, int64_t first, int64_t n, unsigned long long* d_img,
                                unsigned long long* d_cnt, int64_t* launches) {
     const bool verify = (job.flags & ORT_FLAG_VERIFY_FILTER) != 0;
     auto cull = verify ? ort_ring_cull_kernel<true> : ort_ring_cull_kernel<false>;
     auto surv = verify ? ort_ring_survivors_kernel<true> : ort_ring_survivors_kernel<false>;
     const size_t smem_cull = (size_t)ORT_WPB * sizeof(SlimQueue);
     const size_t smem_surv = (size_t)ORT_WPB * sizeof(WarpQueue<double>);
-    CK(cudaFuncSetAttribute(cull, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cull));
-    CK(cudaFuncSetAttribute(surv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_surv));
     int occ_cull = 0, occ_surv = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_cull, cull, ORT_TPB, smem_cull));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_surv, surv, ORT_TPB, smem_surv));
-    if (occ_cull < 1) occ_cull = 1;
-    if (occ_surv < 1) occ_surv = 1;
+    int orc = ctx_occupancy(c, (const void*)cull, smem_cull, &occ_cull);
+    if (orc == ORT_OK) orc = ctx_occupancy(c, (const void*)surv, smem_surv, &occ_surv);
+    if (orc != ORT_OK) return orc;
 
-    /* the list holds the rays that pass stage A at most: Binomial(slice, p), p = aim_cut / 2^64 */
+    /* the list holds at most the rays that pass stage A: Binomial(slice, p), p = aim_cut / 2^64,
+     * standard deviation <= sqrt(slice) / 2.  Capacity = expectation + 8 sqrt(slice) >= 16 sigma. */
     const int64_t slice = n < ORT_RING_SLICE ? n : ORT_RING_SLICE;
     const double p_pass = (double)aim_cut * (1.0 / 18446744073709551616.0);
     double want_cap = (double)slice * p_pass + 8.0 * std::sqrt((double)slice) + 1024.0;
     if (want_cap > (double)slice) want_cap = (double)slice;
     size_t capacity = (size_t)want_cap;
-    if (const char* e = getenv("ORT_TEST_RING_LIST_CAP")) { /* tests only: provoke the overflow report */
+#ifdef ORT_DEBUG
+    /* assert-instrumented build only (libort_debug.so): lets a test provoke the overflow report */
+    if (const char* e = getenv("ORT_TEST_RING_LIST_CAP")) {
         long v = atol(e);
         if (v > 0 && (size_t)v < capacity) capacity = (size_t)v;
     }
+#endif
     const int64_t nslices = (n + ORT_RING_SLICE - 1) / ORT_RING_SLICE;
     if (c.list_cap < capacity) {
         if (c.d_list) CK(cudaFree(c.d_list));
@@ -444,7 +486,7 @@ static int enqueue_ring_filter(DeviceCtx& c, const ort_job& job, const DevScene&
         int grid = c.num_sms * occ_cull;
         int gsz = (int)(want < grid ? (want > 0 ? want : 1) : grid);
         if (k >= 2) CK(cudaStreamWaitEvent(c.stream, c.ev_surv[buf], 0));
-        cull<<<gsz, ORT_TPB, smem_cull, c.stream>>>(sf, dj, aim_cut, list, c.d_nlist + k, (unsigned)capacity, d_cnt);
+        cull<<<gsz, ORT_TPB, smem_cull, c.stream>>>(sf, K, dj, aim_cut, list, c.d_nlist + k, (unsigned)capacity, d_cnt);
         CK(cudaGetLastError());
         CK(cudaEventRecord(c.ev_cull[buf], c.stream));
         /* the list length is only known on the device: size the grid for the longest list there can
@@ -454,7 +496,7 @@ static int enqueue_ring_filter(DeviceCtx& c, const ort_job& job, const DevScene&
         int sgrid = c.num_sms * occ_surv;
         int sgsz = (int)(sb < sgrid ? (sb > 0 ? sb : 1) : sgrid);
         CK(cudaStreamWaitEvent(c.stream2, c.ev_cull[buf], 0));
-        surv<<<sgsz, ORT_TPB, smem_surv, c.stream2>>>(s, sf, dj, list, c.d_nlist + k, (unsigned)capacity, d_img, d_cnt);
+        surv<<<sgsz, ORT_TPB, smem_surv, c.stream2>>>(s, sf, K, dj, list, c.d_nlist + k, (unsigned)capacity, d_img, d_cnt);
         CK(cudaGetLastError());
         CK(cudaEventRecord(c.ev_surv[buf], c.stream2));
         *launches += 2;
@@ -477,17 +519,8 @@ static int enqueue_trace_t(DeviceCtx& c, const ort_job& job, const std::vector<D
         CK(cudaMalloc(&c.d_buf, elems * sizeof(unsigned long long)));
         c.d_elems = elems;
     }
-    bool any_scatter = false;
-    for (auto& s : ds) any_scatter |= (s.scatter_b || s.scatter_c);
-    int bottle_mode = (job.phase == ORT_PHASE_POINT && job.use_bottle) ? (any_scatter ? 2 : 1) : 0;
     bool flat = (job.flags & ORT_FLAG_NO_COMPACTION) != 0 && job.source_kind == ORT_SRC_POINT;
-    typename Kernels<R>::trace_t k = Kernels<R>::pick(job.phase, bottle_mode, job.source_kind, flat);
     size_t smem = flat ? 0 : (size_t)ORT_WPB * sizeof(WarpShared<R>);
-    if (smem) CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, ORT_TPB, smem));
-    if (occ < 1) occ = 1;
-    int grid = c.num_sms * occ;
 
     CK(cudaEventRecord(c.ev_start, c.stream));
     CK(cudaMemsetAsync(c.d_buf, 0, elems * sizeof(unsigned long long), c.stream));
@@ -499,12 +532,23 @@ static int enqueue_trace_t(DeviceCtx& c, const ort_job& job, const std::vector<D
         DevSceneT<R> dsr;
         scene_as(ds[sc], dsr);
         unsigned long long aim_cut = 0;
-        if (ring_filter_applies<R>(job, ds[sc], flat, &aim_cut)) {
-            int rc = enqueue_ring_filter(c, job, ds[sc], aim_cut, nscenes, first, n, d_img + (size_t)sc * ORT_IMG_BINS,
+        DevFilter K;
+        if (ring_filter_applies<R>(job, ds[sc], flat, &aim_cut, &K)) {
+            int rc = enqueue_ring_filter(c, job, ds[sc], K, aim_cut, nscenes, first, n, d_img + (size_t)sc * ORT_IMG_BINS,
                                          d_cnt + (size_t)sc * ORT_NSTATUS, launches);
             if (rc != ORT_OK) return rc;
             continue;
         }
+        /* the kernel is chosen per scene: a clear bottle batched with a scattering one runs exactly
+         * the arithmetic it runs alone (hoisted 1/R wall normals), so a scene's result does not
+         * depend on what it is batched with */
+        const int bottle_mode = (job.phase == ORT_PHASE_POINT && job.use_bottle)
+                                    ? ((ds[sc].scatter_b || ds[sc].scatter_c) ? 2 : 1) : 0;
+        typename Kernels<R>::trace_t k = Kernels<R>::pick(job.phase, bottle_mode, job.source_kind, flat);
+        int occ = 0;
+        int orc = ctx_occupancy(c, (const void*)k, smem, &occ);
+        if (orc != ORT_OK) return orc;
+        const int grid = c.num_sms * occ;
         for (int64_t off = 0; off < n; off += ORT_CHUNK) {
             int64_t m = n - off < ORT_CHUNK ? n - off : ORT_CHUNK;
             DevJob dj;
@@ -696,13 +740,17 @@ extern "C" int ort_trace_rays(const ort_job* job, const ort_scene* scene, int64_
             break;                                                                                 \
         }                                                                                          \
     }
+        void* sp = nullptr;
         if (pos_in) {
-            CKB(cudaMalloc(&d_in, 2 * vb));
+            if ((ret = ctx_scratch(c, 0, 2 * vb, &sp)) != ORT_OK) break;
+            d_in = (double*)sp;
             CKB(cudaMemcpyAsync(d_in, pos_in, vb, cudaMemcpyHostToDevice, c.stream));
             CKB(cudaMemcpyAsync(d_in + 3 * n, dir_in, vb, cudaMemcpyHostToDevice, c.stream));
         }
-        CKB(cudaMalloc(&d_out, 2 * vb));
-        CKB(cudaMalloc(&d_int, (size_t)3 * n * sizeof(int32_t)));
+        if ((ret = ctx_scratch(c, 1, 2 * vb, &sp)) != ORT_OK) break;
+        d_out = (double*)sp;
+        if ((ret = ctx_scratch(c, 2, (size_t)3 * n * sizeof(int32_t), &sp)) != ORT_OK) break;
+        d_int = (int32_t*)sp;
         int grid = (int)((n + ORT_TPB - 1) / ORT_TPB);
         if (job->precision == 32) {
             DevSceneT<float> dsf;
@@ -721,9 +769,6 @@ extern "C" int ort_trace_rays(const ort_job* job, const ort_scene* scene, int64_
         CKB(cudaStreamSynchronize(c.stream));
 #undef CKB
     } while (0);
-    if (d_in) cudaFree(d_in);
-    if (d_out) cudaFree(d_out);
-    if (d_int) cudaFree(d_int);
     return ret;
 }
 
@@ -736,13 +781,14 @@ extern "C" int ort_uniforms(uint64_t seed, int32_t phase, int64_t ray, int32_t f
     if (n <= 0 || !out || first_slot < 0) return ORT_EINVAL;
     DeviceCtx& c = g.devs[0];
     CK(cudaSetDevice(c.dev));
-    double* d = nullptr;
-    CK(cudaMalloc(&d, n * sizeof(double)));
+    void* sp = nullptr;
+    int src = ctx_scratch(c, 1, n * sizeof(double), &sp);
+    if (src != ORT_OK) return src;
+    double* d = (double*)sp;
     ort_uniforms_kernel<<<(n + 127) / 128, 128, 0, c.stream>>>(seed, phase, ray, first_slot, n, d);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, d, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);
-    cudaFree(d);
     if (e != cudaSuccess) {
         ort_set_error("ort_uniforms: %s", cudaGetErrorString(e));
         return ORT_ECUDA;
@@ -813,6 +859,35 @@ extern "C" int ort_math_selftest(int64_t n, uint64_t max_ulp[4]) {
     return ORT_OK;
 }
 
+extern "C" int ort_mufu_selftest(double worst[5], double assumed[5]) {
+    if (!g.ready) {
+        ort_set_error("ort_mufu_selftest: library not initialised");
+        return ORT_ENODEVICE;
+    }
+    if (!worst) return ORT_EINVAL;
+    DeviceCtx& c = g.devs[0];
+    CK(cudaSetDevice(c.dev));
+    unsigned long long* d = nullptr;
+    CK(cudaMalloc(&d, 5 * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(d, 0, 5 * sizeof(unsigned long long), c.stream));
+    ort_mufu_selftest_kernel<<<c.num_sms * 8, 256, 0, c.stream>>>(d);
+    cudaError_t e = cudaGetLastError();
+    unsigned long long h[5] = {0, 0, 0, 0, 0};
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, c.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);
+    cudaFree(d);
+    if (e != cudaSuccess) {
+        ort_set_error("ort_mufu_selftest: %s", cudaGetErrorString(e));
+        return ORT_ECUDA;
+    }
+    for (int i = 0; i < 5; ++i) memcpy(&worst[i], &h[i], sizeof(double));
+    if (assumed) {
+        assumed[0] = ORTF_E_RCP; assumed[1] = ORTF_E_RSQ; assumed[2] = ORTF_E_SQRT;
+        assumed[3] = assumed[4] = ORTF_E_SIN;
+    }
+    return ORT_OK;
+}
+
 /* ------------------------------------------------------------------------------------------
  * tracker files (reference src/stackMod.f90:38-52, src/main.f90:103-107,144-160,
  * src/optics_system.f90:28-50)
@@ -840,9 +915,14 @@ extern "C" int ort_trace_volume(const ort_job* job, const ort_scene* scene, uint
     unsigned* d_vol = nullptr;
     unsigned long long* d_cnt = nullptr;
     unsigned long long h_cnt[ORT_NSTATUS];
-    cudaError_t e = cudaMalloc(&d_vol, nvox * sizeof(unsigned));
-    if (e == cudaSuccess) e = cudaMalloc(&d_cnt, ORT_NSTATUS * sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMemsetAsync(d_vol, 0, nvox * sizeof(unsigned), c.stream);
+    void* sp = nullptr;
+    rc = ctx_scratch(c, 0, nvox * sizeof(unsigned), &sp); /* 128.6 MB, kept for the next call */
+    if (rc != ORT_OK) return rc;
+    d_vol = (unsigned*)sp;
+    rc = ctx_scratch(c, 2, ORT_NSTATUS * sizeof(unsigned long long), &sp);
+    if (rc != ORT_OK) return rc;
+    d_cnt = (unsigned long long*)sp;
+    cudaError_t e = cudaMemsetAsync(d_vol, 0, nvox * sizeof(unsigned), c.stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(d_cnt, 0, ORT_NSTATUS * sizeof(unsigned long long), c.stream);
     for (int64_t off = 0; e == cudaSuccess && off < job->nrays; off += ORT_CHUNK) {
         int64_t m = job->nrays - off < ORT_CHUNK ? job->nrays - off : ORT_CHUNK;
@@ -858,8 +938,6 @@ extern "C" int ort_trace_volume(const ort_job* job, const ort_scene* scene, uint
     if (e == cudaSuccess) e = cudaMemcpyAsync(volume, d_vol, nvox * sizeof(unsigned), cudaMemcpyDeviceToHost, c.stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(h_cnt, d_cnt, sizeof h_cnt, cudaMemcpyDeviceToHost, c.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);
-    if (d_vol) cudaFree(d_vol);
-    if (d_cnt) cudaFree(d_cnt);
     if (e != cudaSuccess) {
         ort_set_error("ort_trace_volume: %s", cudaGetErrorString(e));
         return ORT_ECUDA;

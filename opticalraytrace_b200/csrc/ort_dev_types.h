@@ -80,6 +80,49 @@ struct DevSceneT {
 typedef DevIfaceT<double> DevIface;
 typedef DevSceneT<double> DevScene;
 
+/* ---- the ring loop's single-precision culling filter: error-bound constants ------------------
+ * ort_ring_filter (ort_filter.cuh) carries a bound on the distance between each single-precision
+ * quantity and the value exact arithmetic would give, and calls a ray only when every decision
+ * value is further from zero than its bound.  Everything in those bounds that does not depend on
+ * the ray is computed here, once per launch, in double and rounded up (ort_make_filter,
+ * ort_flatten.h).  The derivation is DESIGN.md section 3.1c; units: lengths in metres, directions and
+ * normals dimensionless. */
+struct DevFilterFlat {    /* L2's flat face: entering the denser medium through a plane whose normal is EXACTLY
+                             (0,0,-1): no total reflection, cos theta_t >= sqrt(1 - eta^2), every bound is
+                             linear in the bound of the incoming direction */
+    float s2_a, s2_b;     /* bound(sin^2 theta_i)  = s2_a * ed + s2_b */
+    float f_a, f_b;       /* bound(lhs - num)      = den * (f_a * ed + f_b) */
+    float d_a, d_b;       /* refraction: bound(dir') = d_a * ed + d_b */
+};
+struct DevFilterIface {   /* a curved interface leaving the denser medium (eta > 1): conditioning ~ 1 / cos theta_t */
+    float ni_0;           /* bound(N.I)            = 1.02 (ed + en) + ni_0 */
+    float ct2_a, ct2_b;   /* bound(cos^2 theta_t)  = ct2_a * bound(N.I) + ct2_b   (already times 1.01) */
+    float cs_0;           /* bound(cos theta_t)    = bound(cos^2) / cos + cs_0 * cos */
+    float f_a, f_b;       /* bound(lhs - num)      = den * (f_a / cos * bound(N.I) + f_b) */
+    float k_a, k_0;       /* bound(k), k = eta cos_i - cos_t:  k_a * bound(N.I) + bound(cos theta_t) + k_0 */
+    float d_d, d_n, d_a, d_0; /* refraction: bound(dir') = d_d (eta cos_i / cos_t) ed + d_n (|k| / cos_t) en + d_a / cos_t + d_0 */
+};
+struct DevFilterSphere {  /* one ray-sphere intersection + the normal at the hit point */
+    float h_d, h_p, h_0;  /* bound(h)    = h_d * ed + h_p * ep + h_0 */
+    float c_p, c_0;       /* bound(c)    = c_p * ep + c_0 */
+    float d_h, d_0;       /* bound(disc) = d_h * bound(h) + 1.01 bound(c) + d_0   (already times 1.01) */
+    float p_0;            /* rounding of the advance to the hit point */
+    float n_p, n_0;       /* bound(normal) = n_p * ep + n_0 */
+};
+struct DevFilter {
+    float ed_a, ed_b;     /* bound(dir) of the emitted ray = ed_a / |aim - source| + ed_b */
+    float ep_flat;        /* bound(pos) on L2's flat face */
+    float ep_max;         /* a bound(pos) above this hands the ray to fp64 */
+    float ap_inv, ap_r, ap_0;       /* L3 aperture: bound(rho^2) = ep (rho^2 * ap_inv + ap_r) + 4u rho^2 + ap_0 */
+    float iris_inv, iris_r, iris_0; /* L3 iris, same form */
+    float iris_z0;                  /* rounding of the iris plane distance */
+    DevFilterFlat flat;
+    DevFilterIface curved;
+    DevFilterSphere s2, s3; /* s2: from the flat face, where ep = ep_flat is inside h_0, c_0 */
+    int32_t usable;       /* 0: a premise fails (see ort_make_filter) or a constant is not finite; 1: valid bounds,
+                             too large to be useful; 2: use the filter (the launcher runs all-fp64 otherwise) */
+};
+
 struct DevJob {
     uint64_t seed;
     int64_t first_ray;   /* ray index of local ray 0 of this launch */

@@ -28,6 +28,7 @@
 #include <cuda_runtime.h>
 
 #include "ort_optics.cuh"
+#include "ort_filter.cuh"
 
 /* `make DEBUG=1` (install.sh -d): own bounds checks on every queue slot and image bin -- the
  * substitute for compute-sanitizer, which is closed on this GPU pool */
@@ -393,8 +394,8 @@ __device__ __forceinline__ void ort_tally(unsigned& c, int st) {
  * ort_trace reports as an error (the launcher sizes the list 16 sigma above its expectation). */
 template <bool VERIFY>
 __global__ void __launch_bounds__(ORT_TPB, ORT_CULL_MIN_BLOCKS)
-ort_ring_cull_kernel(const __grid_constant__ DevSceneT<float> F, const __grid_constant__ DevJob J,
-                     const unsigned long long aim_cut, uint32_t* __restrict__ list, unsigned* __restrict__ nlist,
+ort_ring_cull_kernel(const __grid_constant__ DevSceneT<float> F, const __grid_constant__ DevFilter K,
+                     const __grid_constant__ DevJob J, const unsigned long long aim_cut, uint32_t* __restrict__ list, unsigned* __restrict__ nlist,
                      const unsigned capacity, unsigned long long* __restrict__ counters) {
     extern __shared__ __align__(16) unsigned char ort_smem[];
     SlimQueue& q0 = reinterpret_cast<SlimQueue*>(ort_smem)[threadIdx.x >> 5];
@@ -454,7 +455,7 @@ ort_ring_cull_kernel(const __grid_constant__ DevSceneT<float> F, const __grid_co
             int st = -1;
             if (act) {
                 OrtRng g = ort_make_rng_prod(J, id);
-                st = VERIFY ? 0 : ort_ring_filter(F, J, g, e.x, e.y, e.z);
+                st = VERIFY ? 0 : ort_ring_filter(F, K, J, g, e.x, e.y, e.z);
                 /* one compare + one predicated add per status (left to itself the compiler builds
                  * add / conditional move / move triples here) */
                 ort_tally<ORT_ST_L2_SPHERE_MISS>(c10, st);
@@ -505,7 +506,7 @@ ort_ring_cull_kernel(const __grid_constant__ DevSceneT<float> F, const __grid_co
 template <bool VERIFY>
 __global__ void __launch_bounds__(ORT_TPB, ORT_MIN_BLOCKS)
 ort_ring_survivors_kernel(const __grid_constant__ DevSceneT<double> S, const __grid_constant__ DevSceneT<float> F,
-                          const __grid_constant__ DevJob J, const uint32_t* __restrict__ list,
+                          const __grid_constant__ DevFilter K, const __grid_constant__ DevJob J, const uint32_t* __restrict__ list,
                           const unsigned* __restrict__ nlist, const unsigned capacity,
                           unsigned long long* __restrict__ img, unsigned long long* __restrict__ counters) {
     extern __shared__ __align__(16) unsigned char ort_smem[];
@@ -538,7 +539,7 @@ ort_ring_survivors_kernel(const __grid_constant__ DevSceneT<double> S, const __g
                 r.px = ort_bits_to_uniform<double>(w[0], w[1]);
                 r.py = ort_word_to_uniform<double>(w[2]);
                 /* exactly the words the cull kernel hands the filter */
-                if (VERIFY) verdict = ort_ring_filter(F, J, g, w[1], w[2], w[3]);
+                if (VERIFY) verdict = ort_ring_filter(F, K, J, g, w[1], w[2], w[3]);
                 r.pz = r.dx = r.dy = r.dz = 0.0;
                 st = ort_stage_b<ORT_PHASE_RING, ORT_SRC_POINT>(S, J, g, r, 0u, w[3]);
             }
@@ -715,6 +716,43 @@ __global__ void ort_math_selftest_kernel(long long n, unsigned long long* __rest
     atomicMax(worst + 1, ort_ulp_diff(ort_div(a, x), a / x));
     atomicMax(worst + 2, ort_ulp_diff(ort_sqrt(x), sqrt(x)));
     atomicMax(worst + 3, ort_ulp_diff(ort_rsqrt(x), 1.0 / sqrt(x)));
+}
+
+/* Rule R4 of the ring filter's error bound (ort_filter.cuh): the largest error of the MUFU
+ * approximations it uses, over EVERY fp32 argument -- all 2^32 bit patterns are tried.
+ *   worst[0..2]  relative error of rcp / rsqrt / sqrt.approx.ftz.f32, |x| (x > 0 for the roots) in [2^-64, 2^64]
+ *   worst[3..4]  absolute error of sin / cos.approx.ftz.f32, |x| <= 3.1416 (ortf_sincos_turn folds to [-pi, pi])
+ * as the bit patterns of non-negative doubles (which order like integers), against fp64 references. */
+__global__ void ort_mufu_selftest_kernel(unsigned long long* __restrict__ worst) {
+    double w0 = 0.0, w1 = 0.0, w2 = 0.0, w3 = 0.0, w4 = 0.0;
+    const unsigned long long total = 1ull << 32;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const float x = __uint_as_float((unsigned)i);
+        const float ax = fabsf(x);
+        if (!(ax == ax) || ax == INFINITY) continue;
+        if (ax >= 5.421010862427522e-20f && ax <= 1.8446744073709552e19f) {
+            const double xd = (double)x;
+            w0 = fmax(w0, fabs((double)ortf_rcp(x) * xd - 1.0));
+            if (x > 0.0f) {
+                const double r = sqrt(xd);
+                w1 = fmax(w1, fabs((double)ortf_rsqrt(x) * r - 1.0));
+                w2 = fmax(w2, fabs((double)ortf_sqrt(x) / r - 1.0));
+            }
+        }
+        if (ax <= 3.1416f) {
+            float s, c;
+            asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(x));
+            asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(x));
+            w3 = fmax(w3, fabs((double)s - sin((double)x)));
+            w4 = fmax(w4, fabs((double)c - cos((double)x)));
+        }
+    }
+    atomicMax(worst + 0, (unsigned long long)__double_as_longlong(w0));
+    atomicMax(worst + 1, (unsigned long long)__double_as_longlong(w1));
+    atomicMax(worst + 2, (unsigned long long)__double_as_longlong(w2));
+    atomicMax(worst + 3, (unsigned long long)__double_as_longlong(w3));
+    atomicMax(worst + 4, (unsigned long long)__double_as_longlong(w4));
 }
 
 #endif /* ORT_KERNELS_CUH */

@@ -1127,195 +1127,6 @@ ORT_HD int ort_image(const DevSceneT<R>& S, OrtRayT<R>& r, int* xp, int* yp) {
 }
 
 /* -------------------------------------------------------------------------------------------
- * Single-precision culling filter for the ring loop (no counterpart in the reference).
- *
- * 99.5 % of the ring rays that pass L2's aperture still end between L2's curved face and L3's first
- * surface (total reflection in L2, or no intersection with L3's first sphere), i.e. they only add
- * one to a status counter.  WHICH counter is a chain of sign decisions -- discriminants, aperture
- * radii, the Fresnel draw -- and a decision is safe in single precision whenever its operands are
- * further apart than single precision can blur.  The filter walks source -> L2 -> L3 first
- * surface in fp32 (one issue slot per FFMA instead of a multi-cycle DFMA, one MUFU per
- * rcp/rsqrt/sin/cos) and returns
- *     s > 0 : every decision up to the ray's end had a relative margin > ORT_FILTER_TOL and the ray
- *             ends with status s -- exactly what the fp64 path would count;
- *     0     : the ray survives to L3, or some decision was too close to call -> the caller runs
- *             the ordinary fp64 stage on it (ort_stage_b), which alone moves rays forward.
- * Measured (tools/filter_margin.py, profiles/r01_filter_margin.txt; ORT_FLAG_VERIFY_FILTER runs
- * filter and fp64 on every ray and counts disagreements, over 4 shipped and 8 randomised
- * geometries): with a margin of 1e-6 the filter is wrong ~1e-9 of the time, with 1e-5 ~1e-10, with
- * 5e-5 never in 1.4e11 verdicts; the shipped margin is 5e-4, ten times that again (0 wrong in
- * 5.9e12 verdicts), and costs ~1 % of the rays an unnecessary fp64 pass.  This is an empirical
- * bound, not a proof: an fp32 error analysis that is rigorous for arbitrary scenes would need
- * interval arithmetic.  ORT_FLAG_NO_FILTER switches the filter off.
- * ----------------------------------------------------------------------------------------- */
-#ifndef ORT_FILTER_TOL
-#define ORT_FILTER_TOL 5e-4f /* relative margin of every sign decision */
-#endif
-/* conditioning guard: a ray transmitted just inside the critical angle CONTINUES with a direction
- * computed from sqrt(cos^2 theta_t), which amplifies fp32 rounding by 1 / (2 cos theta_t); every later
- * decision would inherit that, so such rays go to fp64 whatever their own margins say.  (Measured:
- * without this guard the wrong-verdict rate falls only slowly with the margin -- 3 in 6e9 at 5e-5;
- * with it, none in 1.4e11 at 5e-5.  The analogous guard on grazing sphere hits changes nothing.) */
-#ifndef ORT_FILTER_COND_I
-#define ORT_FILTER_COND_I 1e-2f /* smallest cos^2 of the transmitted angle a continuing ray may have */
-#endif
-
-ORT_HD float ortf_rcp(float x) {
-#ifdef __CUDA_ARCH__
-    float y;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-#else
-    return 1.0f / x;
-#endif
-}
-ORT_HD float ortf_rsqrt(float x) {
-#ifdef __CUDA_ARCH__
-    float y;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-#else
-    return 1.0f / sqrtf(x);
-#endif
-}
-ORT_HD float ortf_sqrt(float x) {
-#ifdef __CUDA_ARCH__
-    float y;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-#else
-    return sqrtf(x);
-#endif
-}
-/* sin, cos of 2 pi u, u in [0,1): the argument is folded to [-pi, pi] first, where the MUFU
- * approximations are good to ~5e-7 absolute */
-ORT_HD void ortf_sincos_turn(float u, float* s, float* c) {
-    float a = (u - (u >= 0.5f ? 1.0f : 0.0f)) * 6.2831853071795865f;
-#ifdef __CUDA_ARCH__
-    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(*s) : "f"(a));
-    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(*c) : "f"(a));
-#else
-    *s = sinf(a);
-    *c = cosf(a);
-#endif
-}
-/* a uniform from one 32-bit word (a narrow draw, or the high word of a wide one), rounded to the
- * nearest float: off the fp64 path's u by <= 2^-25 (+ 2^-32 for the unseen low word of a wide draw) */
-ORT_HD float ortf_uniform(uint32_t w) {
-    return (float)w * 2.3283064365386963e-10f;
-}
-
-/* The helpers below do not branch on a near-call: they OR it into `unc` and carry on with whatever
- * fp32 says; the caller leaves at the ray's first definite end and answers 0 (ask fp64) when
- * anything before it was too close.  One exit per possible end, everything else straight-line. */
-
-/* sphere intersection: false = miss.  The outcome hangs on the signs of disc, h and c
- * (ort_pick_root_unit); any of them within the margin of zero sets unc. */
-ORT_HD bool ortf_hit_sphere(const OrtRayT<float>& r, float cx, float cy, float cz, float R2, float* t, bool& unc) {
-    float lx = r.px - cx, ly = r.py - cy, lz = r.pz - cz;
-    float h = fmaf(r.dx, lx, fmaf(r.dy, ly, r.dz * lz));
-    float l2 = fmaf(lx, lx, fmaf(ly, ly, lz * lz));
-    float c = l2 - R2;
-    float disc = fmaf(h, h, -c);
-    float tol = ORT_FILTER_TOL * (l2 + R2);
-    unc |= !(fabsf(disc) > tol) || !(h * h > tol) || !(fabsf(c) > tol); /* each test also catches a NaN */
-    bool hpos = h > 0.0f;
-    if (disc < 0.0f || (hpos && c > 0.0f)) return false;
-    float sq = ortf_sqrt(disc);
-    float q = hpos ? -(h + sq) : (sq - h);
-    *t = (!hpos && c < 0.0f) ? q : c * ortf_rcp(q);
-    return true;
-}
-/* dielectric interface: true = reflected; the new direction is written either way.  Near normal
- * incidence (the reference switches to R = 0 at EXACTLY cos = 1), near the critical angle and a
- * draw within the margin of R set unc. */
-ORT_HD bool ortf_interface(OrtRayT<float>& r, float nx, float ny, float nz, const DevIfaceT<float>& f, float u,
-                           bool& unc) {
-    float c = fmaf(nx, r.dx, fmaf(ny, r.dy, nz * r.dz));
-    float costt = fabsf(c);
-    float s2 = fmaf(-costt, costt, 1.0f);
-    float ct2 = fmaf(-f.eta2, s2, 1.0f);
-    float cost2 = ortf_sqrt(fmaxf(ct2, 0.0f));
-    float ec = f.eta * costt, e2 = f.eta * cost2;
-    float A = ec - cost2, B = ec + cost2, C = e2 - costt, D = e2 + costt;
-    float B2 = B * B, D2 = D * D, den = B2 * D2;
-    float num = fmaf(A * A, D2, (C * C) * B2);
-    float lhs = (u + u) * den;
-    bool tir = !(ct2 > 0.0f);
-    unc |= !(s2 > 1e-4f) || !(fabsf(ct2) > ORT_FILTER_TOL) ||
-           (!tir && !(fabsf(lhs - num) > (2.0f * ORT_FILTER_TOL) * den)); /* |u - R| < tol */
-    /* transmission just inside the critical angle: sqrt(ct2) amplifies the rounding of the
-     * refracted direction, and every later decision would inherit it */
-    unc |= !tir && !(ct2 > ORT_FILTER_COND_I);
-    bool reflect = tir || !(lhs > num);
-    /* reflect: d - 2c n;  refract: eta d + k n, k = +-(eta cos_i - cos_t) opposing the normal */
-    float a = reflect ? 1.0f : f.eta;
-    float k = reflect ? -2.0f * c : ((c < 0.0f) ? A : -A);
-    r.dx = fmaf(a, r.dx, k * nx);
-    r.dy = fmaf(a, r.dy, k * ny);
-    r.dz = fmaf(a, r.dz, k * nz);
-    return reflect;
-}
-
-/* (h2, w_aim, w_curved): words 1, 2, 3 of the ray's block 1, which the caller already holds -- the
- * high word of the aim-disc r^2 draw, the aim angle, L2's curved-face decision; block 0 (annulus
- * r^2, annulus angle, L2's flat-face decision) is generated here */
-ORT_HD int ort_ring_filter(const DevSceneT<float>& F, const DevJob& J, const OrtRng& g, uint32_t h2, uint32_t w_aim,
-                           uint32_t w_curved) {
-    uint32_t w[4];
-    ort_block(g, 0u, w);
-    const float u0 = ortf_uniform(w[1]), u1 = ortf_uniform(w[2]);
-    const float u2 = ortf_uniform(h2), u3 = ortf_uniform(w_aim);
-    /* ring source, ort_source_ring_u */
-    OrtRayT<float> r;
-    float s, c;
-    float rr = ortf_sqrt(fmaf(u0, F.r2_m_r1, F.r1));
-    ortf_sincos_turn(u1, &s, &c);
-    r.px = rr * c;
-    r.py = rr * s;
-    float q = F.ellipse ? r.py * F.ra_over_rb : r.py;
-    r.pz = F.bcz + ortf_sqrt(fmaf(-q, q, F.ra2));
-    float aim2 = u2 * F.lens_r2;
-    /* L2's aperture was decided in stage A on the fp64 u2; the recomputation in ort_l2_enter can
-     * only differ at the very edge */
-    bool unc = !(aim2 < F.l2_radius2 * (1.0f - ORT_FILTER_TOL));
-    float rl = ortf_sqrt(aim2);
-    ortf_sincos_turn(u3, &s, &c);
-    float ax = rl * c, ay = rl * s;
-    float ex = ax - r.px, ey = ay - r.py, ez = F.l2_fb - r.pz;
-    float inv = ortf_rsqrt(fmaf(ex, ex, fmaf(ey, ey, ez * ez)));
-    r.dx = ex * inv;
-    r.dy = ey * inv;
-    r.dz = ez * inv;
-    /* the flat face lies in the aim plane (ring_shortcut): the ray meets it at the aim point */
-    r.px = ax;
-    r.py = ay;
-    r.pz = F.l2_flat_z;
-    /* L2, ort_l2_body; a reflection at the flat face is not tested by the reference: the ray goes on */
-    (void)ortf_interface(r, F.l2_fnx, F.l2_fny, F.l2_fnz, F.l2_in, ortf_uniform(w[3]), unc);
-    float t;
-    if (!ortf_hit_sphere(r, F.l2_cx, F.l2_cy, F.l2_cz, F.l2_R2, &t, unc)) return unc ? 0 : ORT_ST_L2_SPHERE_MISS;
-    ort_advance(r, t);
-    if (ortf_interface(r, (F.l2_cx - r.px) * F.l2_invR, (F.l2_cy - r.py) * F.l2_invR, (F.l2_cz - r.pz) * F.l2_invR,
-                       F.l2_out, ortf_uniform(w_curved), unc))
-        return unc ? 0 : ORT_ST_L2_CURVED_REFLECT;
-    /* L3 up to its aperture, ort_l3_enter */
-    if (J.iris_before) {
-        unc |= !(fabsf(r.dz) > ORT_FILTER_TOL);
-        float ti = (F.l3_iris1_z - r.pz) * ortf_rcp(r.dz);
-        float x = fmaf(r.dx, ti, r.px), y = fmaf(r.dy, ti, r.py);
-        float rho2 = fmaf(x, x, y * y);
-        unc |= !(fabsf(rho2 - F.l3_iris_r2) > ORT_FILTER_TOL * (rho2 + F.l3_iris_r2));
-        if (rho2 > F.l3_iris_r2) return unc ? 0 : ORT_ST_L3_IRIS_BEFORE;
-    }
-    if (!ortf_hit_sphere(r, F.l3_c1x, F.l3_c1y, F.l3_c1z, F.l3_R1_2, &t, unc)) return unc ? 0 : ORT_ST_L3_S1_MISS;
-    ort_advance(r, t);
-    float rho2 = fmaf(r.px, r.px, r.py * r.py);
-    unc |= !(fabsf(rho2 - F.l3_radius2) > ORT_FILTER_TOL * (rho2 + F.l3_radius2));
-    return (!unc && rho2 > F.l3_radius2) ? ORT_ST_L3_APERTURE : 0;
-}
-
-/* -------------------------------------------------------------------------------------------
  * One whole iteration of the reference's ray loops for a single ray (src/main.f90:90-109 /
  * :127-162 incl. telescope, src/optics_system.f90:6-52), with the explicit-ray conveniences of
  * ort_trace_rays: optional caller-supplied start state and ort_job.stop_after.

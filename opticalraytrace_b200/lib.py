@@ -18,7 +18,7 @@ _lib = None
 # every symbol include/ort.h declares (tests/test_abi.py checks the header against this list)
 EXPORTS = [
     "ort_init", "ort_init_rank", "ort_nccl_unique_id", "ort_finalize", "ort_last_error",
-    "ort_device_count", "ort_struct_sizes", "ort_trace", "ort_trace_rays", "ort_uniforms", "ort_measure_fp64_peak", "ort_math_selftest", "ort_write_tracks",
+    "ort_device_count", "ort_struct_sizes", "ort_trace", "ort_trace_rays", "ort_uniforms", "ort_measure_fp64_peak", "ort_math_selftest", "ort_mufu_selftest", "ort_write_tracks",
     "ort_load_image_source", "ort_set_image_source",
     "ort_load_plano", "ort_load_doublet", "ort_load_bottle", "ort_read_settings",
     "ort_build_scene", "ort_job_from_settings", "ort_output_basename", "ort_write_images",
@@ -56,6 +56,7 @@ def load():
     L.ort_uniforms.argtypes = [C.c_uint64, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]
     L.ort_measure_fp64_peak.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.ort_math_selftest.argtypes = [C.c_int64, C.POINTER(C.c_uint64)]
+    L.ort_mufu_selftest.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.ort_write_tracks.argtypes = [C.POINTER(abi.Job), C.POINTER(abi.Scene), C.c_char_p]
     L.ort_load_image_source.argtypes = [C.c_char_p, C.c_int64, C.c_uint64, C.c_void_p]
     L.ort_set_image_source.argtypes = [C.c_void_p]
@@ -276,6 +277,15 @@ def math_selftest(n=1 << 24):
     out = (C.c_uint64 * 4)()
     check(load().ort_math_selftest(n, out))
     return dict(zip(("rcp", "div", "sqrt", "rsqrt"), (int(v) for v in out)))
+
+
+def mufu_selftest():
+    """ort_mufu_selftest: (measured, assumed) largest errors of rcp / rsqrt / sqrt (relative) and
+    sin / cos (absolute) .approx.ftz.f32 over every fp32 argument"""
+    w, a = (C.c_double * 5)(), (C.c_double * 5)()
+    check(load().ort_mufu_selftest(w, a))
+    names = ("rcp", "rsqrt", "sqrt", "sin", "cos")
+    return dict(zip(names, w)), dict(zip(names, a))
 
 
 def measure_fp64_peak():

@@ -57,6 +57,8 @@ int main(int argc, char** argv) {
     int want = std::getenv("ORT_NUM_GPUS") ? std::atoi(std::getenv("ORT_NUM_GPUS")) : 0;
     int ngpu = ort_init(want);
     if (ngpu < 0) return fail("ort_init");
+    if (want > ngpu) /* install.sh -n N with N above the visible device count (its default is 32 = "all") */
+        std::printf(" ORT_NUM_GPUS=%d but %d CUDA device%s visible: using %d\n", want, ngpu, ngpu == 1 ? "" : "s", ngpu);
 
     ort_scene ring_scene, point_scene;
     double pre_guard = 0.0;

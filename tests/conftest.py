@@ -67,6 +67,20 @@ def harness():
         cut = H.hh_ring_aim_cut(C.byref(job), C.byref(scene), C.byref(have))
         return int(cut), bool(have.value)
     run.ring_aim_cut = ring_aim_cut
+    HF = C.CDLL(os.path.join(ROOT, "tests", "libhost_harness_fuzz.so"))
+    for lib in (H, HF):
+        lib.hh_filter_bounds.argtypes = [C.POINTER(abi.Job), C.POINTER(abi.Scene), C.c_int64, C.c_void_p,
+                                         C.c_void_p, C.c_void_p]
+
+    def filter_bounds(job, scene, n, fuzz=False):
+        """-> (usable, {kind: largest |fp32 - exact| / bound}, counts) -- see hh_filter_bounds;
+        usable is None when the scene lacks the filter's premise (no ring_shortcut)"""
+        mr, cnt = np.zeros(16), np.zeros(8, np.int64)
+        ok = (HF if fuzz else H).hh_filter_bounds(C.byref(job), C.byref(scene), n, mr.ctypes.data, cnt.ctypes.data, None)
+        kinds = ["", "pos", "dir", "normal", "n.i", "s2", "ct2", "cos_t", "F", "h", "c", "disc", "t", "rho2"]
+        return (bool(ok & 2) if ok & 1 else None), {kinds[k]: mr[k] for k in range(1, 14)}, dict(
+            records=int(cnt[0]), violations=int(cnt[1]), called=int(cnt[2]), wrong=int(cnt[3]), passed=int(cnt[4]))
+    run.filter_bounds = filter_bounds
     H.hh_ring_filter_in_range.argtypes = [C.POINTER(abi.Job), C.POINTER(abi.Scene)]
     run.ring_filter_in_range = lambda job, scene: bool(H.hh_ring_filter_in_range(C.byref(job), C.byref(scene)))
     run.set_image_source = set_image_source

@@ -6,6 +6,8 @@
   tools/sass_hist.py dynamic prof.ncu-rep [<kernel substring>]
         warp-level executed instruction counts from the SASS source page of an ncu report
         (`ncu --set full --import-source on`): every SASS instruction weighted by how often it ran
+  tools/sass_hist.py lines   prof.ncu-rep file.cubin <kernel substring>
+        the same per CUDA source line (needs the cubin of the profiled build: cuobjdump -xelf all)
 
 Classes follow the pipes of the SM: fp64 (DFMA/DMUL/DADD/DSETP + the 64-bit MUFU seeds), imad
 (integer multiply-add pipe, incl. IMAD used as a move), alu (LOP3/IADD3/SHF/ISETP/SEL/MOV/...),
@@ -29,8 +31,8 @@ CLASSES = [
     ("pred", r"^(PLOP3|P2R|R2P|PSETP)"),
     ("conv", r"^(I2F|F2I|F2F|FRND|I2I|I2FP|F2FP)"),
     ("warp", r"^(VOTE|VOTEU|SHFL|MATCH|REDUX|POPC|FLO|BREV|CREDUX)"),
-    ("lsu", r"^(LDS|STS|LDG|STG|LDL|STL|RED|REDG|ATOM|ATOMS|ATOMG|LD|ST|LDSM|MEMBAR|CCTL|ERRBAR)"),
     ("const", r"^(LDC|LDCU|ULDC)"),
+    ("lsu", r"^(LDS|STS|LDG|STG|LDL|STL|RED|REDG|ATOM|ATOMS|ATOMG|LD|ST|LDSM|MEMBAR|CCTL|ERRBAR)"),
     ("uniform", r"^(U[A-Z0-9]+|R2UR|S2UR)"),
     ("ctrl", r"^(BRA|BRX|JMP|BSSY|BSYNC|WARPSYNC|EXIT|NOP|RET|CALL|BAR|YIELD|ENDCOLLECTIVE|BREAK|BMOV|DEPBAR|NANOSLEEP|KILL|BPT|ACQBULK|ELECT)"),
     ("alu", r"^(LOP3|LOP|IADD3|IADD|VIADD|SHF|SHL|SHR|LEA|ISETP|SEL|MOV|CS2R|S2R|VIMNMX|IMNMX|IABS|PRMT|BMSK|SGXT|VABSDIFF|ISCADD|HADD2|HFMA2|HMUL2)"),
@@ -112,8 +114,46 @@ def dynamic(rep, kern=None):
         print("threads per executed warp instruction: %.2f" % (thr / total))
 
 
+def lines(rep, cubin, kern, top=45):
+    """executed warp instructions per CUDA source line (nvdisasm -g line table of the cubin that was
+    profiled), split by opcode class"""
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr_i = next(i for i, r in enumerate(rows) if "Instructions Executed" in r)
+    ix = {h: i for i, h in enumerate(rows[hdr_i])}
+    data = [r for r in rows[hdr_i + 1:] if len(r) > ix["Instructions Executed"]]
+    base = int(data[0][ix["Address"]], 16)
+    dyn = {int(r[ix["Address"]], 16) - base: (int(r[ix["Instructions Executed"]]), opcode(r[ix["Source"]])) for r in data}
+    dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout
+    line_re = re.compile(r'//## File "([^"]+)", line (\d+)')
+    ins_re = re.compile(r"/\*([0-9a-f]{4,6})\*/\s+(.*?);")
+    per, cur, on, total = collections.defaultdict(collections.Counter), ("?", 0), False, 0
+    for ln in dis.split("\n"):
+        if ln.startswith("//--------------------- .text."):
+            on = kern in ln
+            continue
+        if not on:
+            continue
+        m = line_re.search(ln)
+        if m:
+            cur = (m.group(1).split("/")[-1], int(m.group(2)))
+            continue
+        m = ins_re.search(ln)
+        if m and int(m.group(1), 16) in dyn:
+            n, op = dyn[int(m.group(1), 16)]
+            per[cur][classify(op)] += n
+            total += n
+    print("executed warp instructions per source line, %s (%d total)" % (kern, total))
+    for key, c in sorted(per.items(), key=lambda kv: -sum(kv[1].values()))[:top]:
+        n = sum(c.values())
+        print("  %5.2f %%  %-22s %s" % (100.0 * n / total, "%s:%d" % key,
+                                       " ".join("%s=%.2f" % (k, 100.0 * v / total) for k, v in c.most_common(5))))
+
+
 if __name__ == "__main__":
-    if len(sys.argv) >= 4 and sys.argv[1] == "static":
+    if len(sys.argv) >= 5 and sys.argv[1] == "lines":
+        lines(sys.argv[2], sys.argv[3], sys.argv[4])
+    elif len(sys.argv) >= 4 and sys.argv[1] == "static":
         static(sys.argv[2], sys.argv[3])
     elif len(sys.argv) >= 3 and sys.argv[1] == "dynamic":
         dynamic(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else None)
