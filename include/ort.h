@@ -221,6 +221,9 @@ int ort_init(int ngpus);
 int ort_init_rank(int device, int rank, int nranks, const void* nccl_id);
 int ort_nccl_unique_id(void* out128);
 int ort_finalize(void);
+/* cudaDeviceSynchronize on every device the library drives (ort_trace already returns only when its
+ * own work is done; this is for callers that bracket a timed region) */
+int ort_synchronize(void);
 const char* ort_last_error(void);
 int ort_device_count(void);
 /* sizeof() of {ort_plano, ort_doublet, ort_bottle, ort_scene, ort_job, ort_timing, ort_settings}

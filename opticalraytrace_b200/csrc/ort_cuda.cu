@@ -254,6 +254,15 @@ extern "C" int ort_init(int ngpus) {
     return ngpus;
 }
 
+extern "C" int ort_synchronize(void) {
+    if (!g.ready) return ORT_ENODEVICE;
+    for (auto& c : g.devs) {
+        CK(cudaSetDevice(c.dev));
+        CK(cudaDeviceSynchronize());
+    }
+    return ORT_OK;
+}
+
 extern "C" int ort_nccl_unique_id(void* out128) {
     if (!out128) return ORT_EINVAL;
     int rc = nccl_load();

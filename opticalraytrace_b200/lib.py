@@ -17,7 +17,7 @@ _lib = None
 
 # every symbol include/ort.h declares (tests/test_abi.py checks the header against this list)
 EXPORTS = [
-    "ort_init", "ort_init_rank", "ort_nccl_unique_id", "ort_finalize", "ort_last_error",
+    "ort_init", "ort_init_rank", "ort_nccl_unique_id", "ort_finalize", "ort_synchronize", "ort_last_error",
     "ort_device_count", "ort_struct_sizes", "ort_trace", "ort_trace_rays", "ort_uniforms", "ort_measure_fp64_peak", "ort_math_selftest", "ort_mufu_selftest", "ort_write_tracks",
     "ort_load_image_source", "ort_set_image_source",
     "ort_load_plano", "ort_load_doublet", "ort_load_bottle", "ort_read_settings",
@@ -107,6 +107,10 @@ def nccl_unique_id():
 
 def finalize():
     return check(load().ort_finalize())
+
+
+def synchronize():
+    return check(load().ort_synchronize())
 
 
 def device_count():

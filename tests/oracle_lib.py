@@ -15,6 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 RES = os.path.join(ROOT, "res")
 _lib = None
+_fast = None
 
 DP = C.POINTER(C.c_double)
 IP = C.POINTER(C.c_int32)
@@ -28,6 +29,25 @@ def build():
                                                                os.path.getmtime(hdr)):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "-s"])
     return so
+
+
+def fast_lib():
+    """The timing twin (oracle/Makefile: the reference's -O2 -march=native -flto -mavx -fopenmp): only
+    orc_trace is bound; bench.py's CPU legs use it, the parity tests never do.  It is built on the
+    machine that runs it (-march=native)."""
+    global _fast
+    if _fast is None:
+        so = os.path.join(ORACLE_DIR, "libort_oracle_fast.so")
+        stamp = so + ".host"
+        host = open("/proc/cpuinfo").read().split("model name")[1].split("\n")[0] if os.path.exists("/proc/cpuinfo") else ""
+        if (not os.path.exists(so)) or (not os.path.exists(stamp)) or open(stamp).read() != host:
+            subprocess.check_call(["make", "-C", ORACLE_DIR, "-s", "-B", "libort_oracle_fast.so"])
+            open(stamp, "w").write(host)
+        L = C.CDLL(so)
+        L.orc_trace.argtypes = [C.POINTER(abi.Job), C.POINTER(abi.Scene), C.c_int, C.c_void_p,
+                                C.c_void_p, C.c_void_p, C.c_int]
+        _fast = L
+    return _fast
 
 
 def lib():
@@ -112,8 +132,9 @@ def trace_rays(job, scene, n, pos_in=None, dir_in=None):
     return dict(pos=pos_out, dir=dir_out, status=status, bin=bins)
 
 
-def trace(job, scenes, nthreads=0):
-    """-> image[nscenes,401,401] (uint64, [yp+200, xp+200]), lost[nscenes], hist[nscenes,32]"""
+def trace(job, scenes, nthreads=0, fast=False):
+    """-> image[nscenes,401,401] (uint64, [yp+200, xp+200]), lost[nscenes], hist[nscenes,32];
+    fast=True: the timing twin built with the reference's optimisation flags"""
     if isinstance(scenes, abi.Scene):
         scenes = [scenes]
     ns = len(scenes)
@@ -121,8 +142,8 @@ def trace(job, scenes, nthreads=0):
     image = np.zeros((ns, abi.ORT_IMG_N, abi.ORT_IMG_N), dtype=np.uint64)
     lost = np.zeros(ns, dtype=np.int64)
     hist = np.zeros((ns, abi.ORT_NSTATUS), dtype=np.int64)
-    _chk(lib().orc_trace(C.byref(job), arr, ns, image.ctypes.data, lost.ctypes.data,
-                         hist.ctypes.data, nthreads), "trace")
+    _chk((fast_lib() if fast else lib()).orc_trace(C.byref(job), arr, ns, image.ctypes.data, lost.ctypes.data,
+                                                   hist.ctypes.data, nthreads), "trace")
     return image, lost, hist
 
 
