@@ -441,7 +441,7 @@ static int enqueue_ring_filter(DeviceCtx& c, const ort_job& job, const DevScene&
     auto cull = verify ? ort_ring_cull_kernel<true> : ort_ring_cull_kernel<false>;
     auto surv = verify ? ort_ring_survivors_kernel<true> : ort_ring_survivors_kernel<false>;
     const size_t smem_cull = (size_t)ORT_WPB * sizeof(SlimQueue);
-    const size_t smem_surv = (size_t)ORT_WPB * sizeof(WarpQueue<double>);
+    const size_t smem_surv = (size_t)ORT_WPB * sizeof(SurvShared);
     int occ_cull = 0, occ_surv = 0;
     int orc = ctx_occupancy(c, (const void*)cull, smem_cull, &occ_cull);
     if (orc == ORT_OK) orc = ctx_occupancy(c, (const void*)surv, smem_surv, &occ_surv);

@@ -55,17 +55,38 @@ struct WarpQueue {
     R px[ORT_QCAP], py[ORT_QCAP], pz[ORT_QCAP], dx[ORT_QCAP], dy[ORT_QCAP], dz[ORT_QCAP];
     uint32_t id[ORT_QCAP]; /* ray index relative to DevJob.first_ray */
 };
-/* the queue in front of L2 also carries L2's two decision words (slots 4 and 5: words 3 of the
- * Philox blocks 0 and 1 the emitting stage generated), so that L2 costs no generator call */
+/* The queue in front of L2.  Its rays stand on L2's flat face, the plane z = l2_flat_z, so z is not
+ * stored; it carries L2's two decision words instead (slots 4 and 5: words 3 of the Philox blocks
+ * 0 and 1 the emitting stage generated), so that L2 costs no generator call.  (The ring loop's slim
+ * entries use only px, py = the aim draws, and wc.) */
 template <typename R>
-struct WarpQueueL2 : WarpQueue<R> {
-    uint32_t wf[ORT_QCAP], wc[ORT_QCAP];
+struct WarpQueueL2 {
+    R px[ORT_QCAP], py[ORT_QCAP], dx[ORT_QCAP], dy[ORT_QCAP], dz[ORT_QCAP];
+    uint32_t id[ORT_QCAP], wf[ORT_QCAP], wc[ORT_QCAP];
 };
 template <typename R>
 struct WarpShared {
     WarpQueueL2<R> q0;
     WarpQueue<R> q1;
+    unsigned hist[ORT_NSTATUS]; /* this warp's histogram of final ray statuses */
 };
+#ifndef ORT_COUNT_SMEM
+#define ORT_COUNT_SMEM 1 /* 1: statuses are tallied in the warp's shared-memory histogram (one ATOMS per
+                            stage); 0: in 27 warp-uniform registers (vote + popc + add per status) */
+#endif
+/* one shared-memory increment per ray that ended in this stage */
+__device__ __forceinline__ void ort_tally_smem(unsigned* hist, int st, bool ended) {
+    if (ended) atomicAdd(hist + st, 1u);
+}
+__device__ __forceinline__ void ort_hist_clear(unsigned* hist, unsigned lane) {
+    hist[lane] = 0u;
+    __syncwarp();
+}
+__device__ __forceinline__ void ort_hist_flush(const unsigned* hist, unsigned lane, unsigned long long* __restrict__ counters) {
+    __syncwarp();
+    const unsigned mine = hist[lane];
+    if (mine) atomicAdd(counters + lane, (unsigned long long)mine);
+}
 
 __device__ __forceinline__ OrtRng ort_make_rng(const DevJob& J, uint32_t local_id) {
     OrtRng g;
@@ -87,9 +108,8 @@ __device__ __forceinline__ OrtRng ort_make_rng_prod(const DevJob& J, uint32_t lo
     return g;
 }
 
-/* SLIM: the entry carries only (px, py) -- the ring loop's stage 0 hands on two uniforms.  Returns
- * the slot the entry went to (or -1). */
-template <bool SLIM = false, typename R>
+/* Returns the slot the entry went to (or -1). */
+template <typename R>
 __device__ __forceinline__ int ort_q_push(WarpQueue<R>& q, int& n, bool alive, const OrtRayT<R>& r,
                                           uint32_t id, unsigned lane) {
     unsigned m = __ballot_sync(ORT_FULL, alive);
@@ -97,18 +117,15 @@ __device__ __forceinline__ int ort_q_push(WarpQueue<R>& q, int& n, bool alive, c
     if (alive) {
         p = n + __popc(m & ((1u << lane) - 1u));
         ORT_ASSERT(p >= 0 && p < ORT_QCAP);
-        q.px[p] = r.px; q.py[p] = r.py;
-        if (!SLIM) {
-            q.pz[p] = r.pz;
-            q.dx[p] = r.dx; q.dy[p] = r.dy; q.dz[p] = r.dz;
-        }
+        q.px[p] = r.px; q.py[p] = r.py; q.pz[p] = r.pz;
+        q.dx[p] = r.dx; q.dy[p] = r.dy; q.dz[p] = r.dz;
         q.id[p] = id;
     }
     n += __popc(m);
     return p;
 }
 /* ... and the slot the entry came from (or -1) */
-template <bool SLIM = false, typename R>
+template <typename R>
 __device__ __forceinline__ int ort_q_pop(WarpQueue<R>& q, int& n, OrtRayT<R>& r, uint32_t& id, unsigned lane) {
     int cnt = n < 32 ? n : 32;
     int base = n - cnt;
@@ -116,15 +133,52 @@ __device__ __forceinline__ int ort_q_pop(WarpQueue<R>& q, int& n, OrtRayT<R>& r,
     if ((int)lane < cnt) {
         p = base + lane;
         ORT_ASSERT(p >= 0 && p < ORT_QCAP);
-        r.px = q.px[p]; r.py = q.py[p];
-        if (!SLIM) {
-            r.pz = q.pz[p];
-            r.dx = q.dx[p]; r.dy = q.dy[p]; r.dz = q.dz[p];
-        }
+        r.px = q.px[p]; r.py = q.py[p]; r.pz = q.pz[p];
+        r.dx = q.dx[p]; r.dy = q.dy[p]; r.dz = q.dz[p];
         id = q.id[p];
     }
     n = base;
     return p;
+}
+/* the queue in front of L2.  SLIM: the entry carries only (px, py, wc) -- the ring loop's stage 0 hands
+ * on two uniforms and one decision word */
+template <bool SLIM, typename R>
+__device__ __forceinline__ void ort_q0_push(WarpQueueL2<R>& q, int& n, bool alive, const OrtRayT<R>& r, uint32_t id,
+                                            uint32_t wf, uint32_t wc, unsigned lane) {
+    unsigned m = __ballot_sync(ORT_FULL, alive);
+    if (alive) {
+        const int p = n + __popc(m & ((1u << lane) - 1u));
+        ORT_ASSERT(p >= 0 && p < ORT_QCAP);
+        q.px[p] = r.px; q.py[p] = r.py;
+        if (!SLIM) {
+            q.dx[p] = r.dx; q.dy[p] = r.dy; q.dz[p] = r.dz;
+            q.wf[p] = wf;
+        }
+        q.wc[p] = wc;
+        q.id[p] = id;
+    }
+    n += __popc(m);
+}
+template <bool SLIM, typename R>
+__device__ __forceinline__ bool ort_q0_pop(WarpQueueL2<R>& q, int& n, R flat_z, OrtRayT<R>& r, uint32_t& id, uint32_t& wf,
+                                           uint32_t& wc, unsigned lane) {
+    int cnt = n < 32 ? n : 32;
+    int base = n - cnt;
+    const bool act = (int)lane < cnt;
+    if (act) {
+        const int p = base + lane;
+        ORT_ASSERT(p >= 0 && p < ORT_QCAP);
+        r.px = q.px[p]; r.py = q.py[p];
+        if (!SLIM) {
+            r.pz = flat_z;
+            r.dx = q.dx[p]; r.dy = q.dy[p]; r.dz = q.dz[p];
+            wf = q.wf[p];
+        }
+        wc = q.wc[p];
+        id = q.id[p];
+    }
+    n = base;
+    return act;
 }
 
 /* Histogram of final ray statuses.  Every warp keeps one counter per status it can produce, as
@@ -265,9 +319,13 @@ ort_trace_kernel(const __grid_constant__ DevSceneT<R> S, const __grid_constant__
     const uint32_t nrays = (uint32_t)J.nrays;
     const uint32_t nbatches = (nrays + 31u) >> 5;
 
+#if ORT_COUNT_SMEM
+    ort_hist_clear(ws.hist, lane);
+#else
     OrtCounts cnt;
 #pragma unroll
     for (int k = 0; k < ORT_NSTATUS; ++k) cnt.c[k] = 0;
+#endif
     int n1 = 0, n2 = 0;
     uint32_t b = gwarp;
     /* ring loop with the aim-plane shortcut: stage 0 hands on only (u2, u3) */
@@ -292,25 +350,31 @@ ort_trace_kernel(const __grid_constant__ DevSceneT<R> S, const __grid_constant__
                 OrtRng g = ort_make_rng_prod(J, id);
                 st = ort_stage_a<PHASE, BOTTLE, SRC>(S, J, g, id, r, wf, wc);
             }
-            const int p = slim ? ort_q_push<true>(ws.q0, n1, st == 0, r, id, lane) : ort_q_push(ws.q0, n1, st == 0, r, id, lane);
-            if (p >= 0) {
-                if (!slim) ws.q0.wf[p] = wf;
-                ws.q0.wc[p] = wc;
-            }
+            if (slim) ort_q0_push<true>(ws.q0, n1, st == 0, r, id, wf, wc, lane);
+            else ort_q0_push<false>(ws.q0, n1, st == 0, r, id, wf, wc, lane);
             __syncwarp();
+#if ORT_COUNT_SMEM
+            ort_tally_smem(ws.hist, st, st > 0);
+#else
             ort_count_a<PHASE, BOTTLE, SRC>(cnt, st);
+#endif
         } else if (stage == 1) {
-            const int p = slim ? ort_q_pop<true>(ws.q0, n1, r, id, lane) : ort_q_pop(ws.q0, n1, r, id, lane);
+            uint32_t wf = 0u, wc = 0u;
+            const bool act = slim ? ort_q0_pop<true>(ws.q0, n1, S.l2_flat_z, r, id, wf, wc, lane)
+                                  : ort_q0_pop<false>(ws.q0, n1, S.l2_flat_z, r, id, wf, wc, lane);
             int st = -1;
-            if (p >= 0) {
-                const uint32_t wf = slim ? 0u : ws.q0.wf[p], wc = ws.q0.wc[p];
+            if (act) {
                 OrtRng g = ort_make_rng_prod(J, id);
                 st = ort_stage_b<PHASE, SRC>(S, J, g, r, wf, wc);
             }
             __syncwarp();
             ort_q_push(ws.q1, n2, st == 0, r, id, lane);
             __syncwarp();
+#if ORT_COUNT_SMEM
+            ort_tally_smem(ws.hist, st, st > 0);
+#else
             ort_count_b(cnt, st);
+#endif
         } else {
             const bool act = ort_q_pop(ws.q1, n2, r, id, lane) >= 0;
             __syncwarp();
@@ -320,10 +384,18 @@ ort_trace_kernel(const __grid_constant__ DevSceneT<R> S, const __grid_constant__
                 st = ort_stage_c(S, J, g, r, &xp, &yp);
             }
             ort_bin(img, st == ORT_ST_BINNED, xp, yp, lane);
+#if ORT_COUNT_SMEM
+            ort_tally_smem(ws.hist, st, st >= 0);
+#else
             ort_count_c(cnt, st);
+#endif
         }
     }
+#if ORT_COUNT_SMEM
+    ort_hist_flush(ws.hist, lane, counters);
+#else
     ort_counts_flush(cnt, lane, counters);
+#endif
 }
 
 /* ---- ring loop with the fp32 culling filter (ort_ring_filter) ------------------------------
@@ -503,6 +575,10 @@ ort_ring_cull_kernel(const __grid_constant__ DevSceneT<float> F, const __grid_co
 }
 
 /* fp64 stages B and C over the listed rays */
+struct SurvShared {
+    WarpQueue<double> q;
+    unsigned hist[ORT_NSTATUS];
+};
 template <bool VERIFY>
 __global__ void __launch_bounds__(ORT_TPB, ORT_MIN_BLOCKS)
 ort_ring_survivors_kernel(const __grid_constant__ DevSceneT<double> S, const __grid_constant__ DevSceneT<float> F,
@@ -510,16 +586,15 @@ ort_ring_survivors_kernel(const __grid_constant__ DevSceneT<double> S, const __g
                           const unsigned* __restrict__ nlist, const unsigned capacity,
                           unsigned long long* __restrict__ img, unsigned long long* __restrict__ counters) {
     extern __shared__ __align__(16) unsigned char ort_smem[];
-    WarpQueue<double>& q = reinterpret_cast<WarpQueue<double>*>(ort_smem)[threadIdx.x >> 5];
+    SurvShared& ws = reinterpret_cast<SurvShared*>(ort_smem)[threadIdx.x >> 5];
+    WarpQueue<double>& q = ws.q;
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t nwarps = gridDim.x * ORT_WPB;
     const uint32_t gwarp = blockIdx.x * ORT_WPB + (threadIdx.x >> 5);
     const uint32_t total = *nlist < capacity ? *nlist : capacity;
     const uint32_t nbatches = (total + 31u) >> 5;
 
-    OrtCounts cnt;
-#pragma unroll
-    for (int k = 0; k < ORT_NSTATUS; ++k) cnt.c[k] = 0;
+    ort_hist_clear(ws.hist, lane);
     int n2 = 0;
     uint32_t b = gwarp;
     for (;;) {
@@ -544,12 +619,12 @@ ort_ring_survivors_kernel(const __grid_constant__ DevSceneT<double> S, const __g
                 st = ort_stage_b<ORT_PHASE_RING, ORT_SRC_POINT>(S, J, g, r, 0u, w[3]);
             }
             if (VERIFY) {
-                cnt.c[ORT_FILTER_SLOT_CALLED] += __popc(__ballot_sync(ORT_FULL, verdict > 0));
-                cnt.c[ORT_FILTER_SLOT_WRONG] += __popc(__ballot_sync(ORT_FULL, verdict > 0 && verdict != st));
+                ort_tally_smem(ws.hist, ORT_FILTER_SLOT_CALLED, verdict > 0);
+                ort_tally_smem(ws.hist, ORT_FILTER_SLOT_WRONG, verdict > 0 && verdict != st);
             }
             ort_q_push(q, n2, st == 0, r, id, lane);
             __syncwarp();
-            ort_count_b(cnt, st);
+            ort_tally_smem(ws.hist, st, st > 0);
         } else {
             const bool act = ort_q_pop(q, n2, r, id, lane) >= 0;
             __syncwarp();
@@ -559,10 +634,10 @@ ort_ring_survivors_kernel(const __grid_constant__ DevSceneT<double> S, const __g
                 st = ort_stage_c(S, J, g, r, &xp, &yp);
             }
             ort_bin(img, st == ORT_ST_BINNED, xp, yp, lane);
-            ort_count_c(cnt, st);
+            ort_tally_smem(ws.hist, st, st >= 0);
         }
     }
-    ort_counts_flush(cnt, lane, counters);
+    ort_hist_flush(ws.hist, lane, counters);
 }
 
 /* The same path, one thread per ray from source to detector, no compaction: every early exit

@@ -48,32 +48,31 @@
 /* sin(pi x), cos(pi x) for x in [0, 2) -- all the sources ever ask for (x = 2u).  The library
  * sincospi spends ~75 instructions on arbitrary arguments; here: q = nearest half-integer count,
  * r = x - q/2 in [-1/4, 1/4] (exact), Taylor polynomials of sin(pi r), cos(pi r) in r^2
- * (truncation < 5e-17), quadrant fix-up.  <= 2 ulp, like the library. */
+ * (truncation < 5e-17), quadrant fix-up.  <= 2 ulp, like the library.  The coefficients sit in
+ * constant memory so that each DFMA reads its own as a c[][] operand (as literals the compiler
+ * builds every one of them in a pair of uniform registers first: 38 UMOV per call). */
+#ifdef __CUDACC__
+static __constant__ double ort_sincos_poly[19] = {
+    7.95205400147551261e-07, -2.19153534478302173e-05, 4.66302805767612554e-04, -7.37043094571435044e-03,
+    8.21458866111282326e-02, -5.99264529320792105e-01, 2.55016403987734552e+00, -5.16771278004997026e+00,
+    3.14159265358979312e+00,
+    -1.38789524622137714e-07, 4.30306958703294729e-06, -1.04638104924845705e-04, 1.92957430940392314e-03,
+    -2.58068913900140612e-02, 2.35330630358893206e-01, -1.33526276885458950e+00, 4.05871212641676848e+00,
+    -4.93480220054467900e+00, 1.0};
+#endif
 ORT_HD void ort_sincospi(double x, double* s, double* c) {
 #ifdef __CUDA_ARCH__
     const double q = rint(x + x);
     const double r = fma(q, -0.5, x);
     const double t = r * r;
-    double ps = 7.95205400147551261e-07;
-    ps = fma(ps, t, -2.19153534478302173e-05);
-    ps = fma(ps, t, 4.66302805767612554e-04);
-    ps = fma(ps, t, -7.37043094571435044e-03);
-    ps = fma(ps, t, 8.21458866111282326e-02);
-    ps = fma(ps, t, -5.99264529320792105e-01);
-    ps = fma(ps, t, 2.55016403987734552e+00);
-    ps = fma(ps, t, -5.16771278004997026e+00);
-    ps = fma(ps, t, 3.14159265358979312e+00);
+    const double* P = ort_sincos_poly;
+    double ps = P[0];
+#pragma unroll
+    for (int i = 1; i < 9; ++i) ps = fma(ps, t, P[i]);
     ps *= r;
-    double pc = -1.38789524622137714e-07;
-    pc = fma(pc, t, 4.30306958703294729e-06);
-    pc = fma(pc, t, -1.04638104924845705e-04);
-    pc = fma(pc, t, 1.92957430940392314e-03);
-    pc = fma(pc, t, -2.58068913900140612e-02);
-    pc = fma(pc, t, 2.35330630358893206e-01);
-    pc = fma(pc, t, -1.33526276885458950e+00);
-    pc = fma(pc, t, 4.05871212641676848e+00);
-    pc = fma(pc, t, -4.93480220054467900e+00);
-    pc = fma(pc, t, 1.0);
+    double pc = P[9];
+#pragma unroll
+    for (int i = 10; i < 19; ++i) pc = fma(pc, t, P[i]);
     const int k = (int)q; /* 0..4 */
     const double a = (k & 1) ? pc : ps, b = (k & 1) ? ps : pc; /* odd quadrant: swap */
     *s = (k & 2) ? -a : a;
@@ -446,6 +445,18 @@ ORT_HD R ort_narrow(const OrtRng& g, uint32_t w) {
     return g.override_u >= 0.0 ? (R)g.override_u : ort_word_to_uniform<R>(w);
 }
 
+/* twice the draw, for ort_interface: a scaling by 2^-31 (2^-52) instead of 2^-32 (2^-53), exact */
+template <typename R>
+ORT_HD R ort_narrow2(const OrtRng& g, uint32_t w) {
+    if (g.override_u >= 0.0) return (R)(g.override_u + g.override_u);
+    return sizeof(R) == 8 ? (R)((double)w * (1.0 / 2147483648.0)) : ort_word_to_uniform<R>(w) * R(2.0);
+}
+template <typename R>
+ORT_HD R ort_wide2(const OrtRng& g, uint32_t lo, uint32_t hi) {
+    const R u = ort_wide<R>(g, lo, hi);
+    return u + u;
+}
+
 /* draw slot -> (block, which words): the table above */
 template <typename R>
 ORT_HD R ort_slot(const OrtRng& g, uint32_t slot) {
@@ -597,8 +608,9 @@ ORT_HD void ort_advance(OrtRayT<R>& r, R t) {
  *   its NaN guard turns that into 1);  R = 0 at exactly normal incidence (cos == 1);
  *   reflect when u <= R.
  * ----------------------------------------------------------------------------------------- */
+/* u2 = TWICE the draw (ort_narrow2 / ort_wide2 form it at no extra cost) */
 template <typename R>
-ORT_HD bool ort_interface(OrtRayT<R>& r, R nx, R ny, R nz, const DevIfaceT<R>& f, R u) {
+ORT_HD bool ort_interface(OrtRayT<R>& r, R nx, R ny, R nz, const DevIfaceT<R>& f, R u2) {
     R c = fma(nx, r.dx, fma(ny, r.dy, nz * r.dz)); /* N . I */
     R costt = fabs(c);
     R s2 = fma(-costt, costt, R(1.0)); /* sin^2(theta_i) */
@@ -606,17 +618,17 @@ ORT_HD bool ort_interface(OrtRayT<R>& r, R nx, R ny, R nz, const DevIfaceT<R>& f
     R cost2 = ort_sqrt_nz(ct2); /* NaN under total internal reflection, where it is not used */
     /* Fresnel amplitudes in units of nb (the ratios do not change): A/B = r_s, C/D = r_p.
      * R = (A^2 D^2 + C^2 B^2) / (2 B^2 D^2); the draw is compared without forming the quotient:
-     *   u > R  <=>  2u B^2 D^2 > A^2 D^2 + C^2 B^2.
+     *   u > R  <=>  2u B^2 D^2 > A^2 D^2 + C^2 B^2   (2u is what the caller hands in).
      * 0 <= R <= 1 by construction (|A| <= B, |C| <= D); a NaN fails the comparison and reflects,
      * which is what the reference's NaN guard (R = 1) does. */
     R ec = f.eta * costt, e2 = f.eta * cost2;
     R A = ec - cost2, B = ec + cost2, C = e2 - costt, D = e2 + costt;
     R B2 = B * B, D2 = D * D;
     R num = fma(A * A, D2, (C * C) * B2);
-    R lhs = (u + u) * (B2 * D2);
+    R lhs = u2 * (B2 * D2);
     bool transmit = lhs > num;
     if (ort_either_negative(ct2, s2)) transmit = false; /* TIR, or |N.I| > 1 by rounding (reference: NaN -> R = 1) */
-    else if (ort_is_zero(s2)) transmit = u > R(0.0);      /* exactly normal incidence: the reference returns R = 0 */
+    else if (ort_is_zero(s2)) transmit = u2 > R(0.0);     /* exactly normal incidence: the reference returns R = 0 */
     if (!transmit) { /* reflect, src/surfaces.f90:285-300 */
         R k = -R(2.0) * c;
         r.dx = fma(k, nx, r.dx);
@@ -804,7 +816,7 @@ ORT_HD bool ort_source_isors(const DevSceneT<R>& S, const OrtRng& g, const OrtDr
     r.px = x; r.py = y; r.pz = R(2.0) * S.isors_h;
     r.dx = R(0.0); r.dy = R(0.0); r.dz = -R(1.0);
     const R u_r = ort_wide<R>(g, D.a[0], D.a[1]), u_th = ort_narrow<R>(g, D.a[2]); /* slots 0, 1 */
-    const R u_ax = ort_wide<R>(g, D.b[0], D.b[1]);                                  /* slot 2 */
+    const R u_ax = ort_wide2<R>(g, D.b[0], D.b[1]);                                 /* slot 2, doubled */
     if (ort_hit_cone(r, S.isors_k, S.isors_h, &t)) {
         ort_advance(r, t);
         /* gradient of the cone, inverted (upper nappe), normalised */
@@ -993,7 +1005,7 @@ ORT_HD int ort_scatter_loop(const DevSceneT<R>& S, const OrtRng& g, OrtScatterRn
 template <bool SCATTER, typename R>
 ORT_HD int ort_bottle_forward(const DevSceneT<R>& S, const OrtRng& g, const OrtDraws01& D, OrtRayT<R>& r) {
     R t;
-    const R u_in = ort_wide<R>(g, D.b[0], D.b[1]), u_out = ort_narrow<R>(g, D.b[2]); /* slots 2, 3 */
+    const R u_in = ort_wide2<R>(g, D.b[0], D.b[1]), u_out = ort_narrow2<R>(g, D.b[2]); /* slots 2, 3, doubled */
     OrtScatterRngT<R> sr;
     sr.next = 16;
     sr.spare = R(0.0);
@@ -1046,7 +1058,7 @@ ORT_HD int ort_l2_enter(const DevSceneT<R>& S, OrtRayT<R>& r) { /* :447-454 */
 template <typename R>
 ORT_HD int ort_l2_body(const DevSceneT<R>& S, const OrtRng& g, uint32_t w_flat, uint32_t w_curved, OrtRayT<R>& r) { /* :458-479 */
     R t;
-    const R u_flat = ort_narrow<R>(g, w_flat), u_curved = ort_narrow<R>(g, w_curved);
+    const R u_flat = ort_narrow2<R>(g, w_flat), u_curved = ort_narrow2<R>(g, w_curved); /* doubled */
     /* a reflection at the flat face is computed but never tested */
     (void)ort_interface(r, S.l2_fnx, S.l2_fny, S.l2_fnz, S.l2_in, u_flat);
     if (!ort_hit_sphere(r, S.l2_cx, S.l2_cy, S.l2_cz, S.l2_R2, &t)) return ORT_ST_L2_SPHERE_MISS;
@@ -1081,7 +1093,7 @@ ORT_HD int ort_l3_body(const DevSceneT<R>& S, const OrtRng& g, bool iris_after, 
     R t, nx, ny, nz;
     uint32_t w[4];
     ort_block(g, 2u, w); /* slots 6, 7, 8 */
-    const R u1 = ort_narrow<R>(g, w[0]), u2 = ort_narrow<R>(g, w[1]), u3 = ort_narrow<R>(g, w[2]);
+    const R u1 = ort_narrow2<R>(g, w[0]), u2 = ort_narrow2<R>(g, w[1]), u3 = ort_narrow2<R>(g, w[2]); /* doubled */
     ort_sphere_normal(r, S.l3_c1x, S.l3_c1y, S.l3_c1z, S.l3_invR1, &nx, &ny, &nz);
     if (ort_interface(r, nx, ny, nz, S.l3_s1, u1)) return ORT_ST_L3_S1_REFLECT;
     if (!ort_hit_sphere(r, S.l3_c2x, S.l3_c2y, S.l3_c2z, S.l3_R2_2, &t)) return ORT_ST_L3_S2_MISS;
