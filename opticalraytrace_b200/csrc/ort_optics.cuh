@@ -197,8 +197,10 @@ ORT_HD double ort_sqrt_nz(double x) { /* x > 0: no zero guard (0 would give NaN)
 }
 ORT_HD double ort_sqrt(double x) {
 #ifdef __CUDA_ARCH__
-    /* one Goldschmidt step, then the Newton correction of the root (also quadratic) */
-    double y = ort_mufu_rsq(x);
+    /* one Goldschmidt step, then the Newton correction of the root (also quadratic).  The seed is
+     * taken of x + 1e-300 (== x for every x this path can produce except 0), so that x = 0 gives
+     * g = 0 * 1e150 = 0 straight through instead of 0 * inf and needs no select; x < 0 stays NaN. */
+    double y = ort_mufu_rsq(x + 1e-300);
     double g = x * y, h = 0.5 * y;
 #pragma unroll
     for (int i = 0; i < ORT_NR - 1; ++i) {
@@ -207,8 +209,7 @@ ORT_HD double ort_sqrt(double x) {
         h = fma(h, r, h);
     }
     double d = fma(-g, g, x);
-    g = fma(d, h, g);
-    return (x == 0.0) ? 0.0 : g;
+    return fma(d, h, g);
 #else
     return sqrt(x);
 #endif
@@ -314,6 +315,26 @@ ORT_HD bool ort_both_zero(double x, double y) { /* +-0 */
 #endif
 }
 ORT_HD bool ort_both_zero(float x, float y) { return x == 0.0f && y == 0.0f; }
+
+/* x with its sign flipped when `flip`: one integer op on the high word instead of a negation and
+ * a two-register select */
+ORT_HD double ort_flip_if(double x, bool flip) {
+#ifdef __CUDA_ARCH__
+    return __hiloint2double(__double2hiint(x) ^ (flip ? (int)0x80000000 : 0), __double2loint(x));
+#else
+    return flip ? -x : x;
+#endif
+}
+ORT_HD float ort_flip_if(float x, bool flip) { return flip ? -x : x; }
+/* x if c carries a sign bit, else -x -- (c < 0) ? x : -x wherever c cannot be a negative zero */
+ORT_HD double ort_neg_unless_negative(double x, double c) {
+#ifdef __CUDA_ARCH__
+    return __hiloint2double(__double2hiint(x) ^ (~__double2hiint(c) & (int)0x80000000), __double2loint(x));
+#else
+    return (c < 0.0) ? x : -x;
+#endif
+}
+ORT_HD float ort_neg_unless_negative(float x, float c) { return (c < 0.0f) ? x : -x; }
 
 /* uncontracted arithmetic for stokes (see there) */
 ORT_HD double ort_mul_rn(double a, double b) {
@@ -544,7 +565,7 @@ ORT_HD bool ort_pick_root_unit(R h, R c, R* t) {
     R s = ort_sqrt(disc);
     bool hpos = h > R(0.0);
     if (hpos && c > R(0.0)) return false;
-    R q = hpos ? -(h + s) : (s - h);
+    R q = -(h + ort_flip_if(s, !hpos)); /* hpos ? -(h + s) : (s - h) */
     R x1 = ort_div(c, q);
     R tt = (!hpos && c < R(0.0)) ? q : x1;
     if (q == R(0.0)) tt = R(0.0); /* h = c = 0: the ray starts on the surface, tangent */
@@ -637,7 +658,9 @@ ORT_HD bool ort_interface(OrtRayT<R>& r, R nx, R ny, R nz, const DevIfaceT<R>& f
         return true;
     }
     /* refract, src/surfaces.f90:303-333: T = eta I + (eta c1 - c2) N', N' opposing I */
-    R k = (c < R(0.0)) ? A : -A; /* eta c1 - c2 */
+    /* k = (c < 0) ? A : -A, on the sign bit of c: N.I is a sum of three products and cannot be a negative
+     * zero unless every product is one (a ray in the tangent plane with two vanishing components) */
+    R k = ort_neg_unless_negative(A, c); /* eta c1 - c2, opposing the normal */
     r.dx = fma(f.eta, r.dx, k * nx);
     r.dy = fma(f.eta, r.dy, k * ny);
     r.dz = fma(f.eta, r.dz, k * nz);
