@@ -48,9 +48,17 @@ find "$here/src" -maxdepth 1 -name '*.o' -exec mv {} "$here/build/" \;
 mv "$here/src/raytrace" "$here/bin/raytrace"
 printf '\n*****Install complete*****\n\n'
 
+# --- the unmodified reference, where a Fortran compiler and its tree exist (neither does in the build
+# image): built next to the oracle so that `bench.py --impl reference` / cpu_baseline time the real thing
+ref="${ORT_REFERENCE_DIR:-/root/reference}"
+if command -v gfortran >/dev/null 2>&1 && [ -d "$ref/src" ]; then
+  make -C "$here/oracle" ref REF="$ref" && echo "reference binary: oracle/_ref/raytrace (bench.py --impl reference times it)"
+fi
+
 # --- run, from bin/ like the reference -------------------------------------------------------
 if [ "$gpus" != 32 ]; then
   export ORT_NUM_GPUS="$gpus"      # the reference exports OMP_NUM_THREADS here
+  # (more than the visible devices: raytrace says so and uses what there is)
 fi
 cd "$here/bin"
 exec ./raytrace "$settings"

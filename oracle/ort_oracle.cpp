@@ -281,14 +281,37 @@ inline void reflect_refract(vec& I, vec N, double n1, double n2, bool& rflag, do
     }
 }
 
+/* ---------------------------------------------------------------------------------------
+ * Conditioning probe for the scatter path (tests only; off unless orc_set_jitter(seed != 0)).
+ * The GPU's libm differs from glibc's by up to 2 ulp per call (log, atan2, sin, cos, acos) and
+ * its fused multiply-adds move intersection distances by an ulp; stokes' spherical-triangle
+ * update amplifies such differences by up to ~1/sin^2 of the deflection.  With the probe on,
+ * every one of those results is moved by a pseudo-random -2..+2 ulp, so that running the oracle
+ * against itself measures, ray by ray, how far two correct implementations may be apart.
+ * ------------------------------------------------------------------------------------- */
+static uint64_t g_jitter_seed = 0;
+static thread_local uint64_t t_jitter = 0;
+inline void jitter_begin(int64_t ray) { t_jitter = g_jitter_seed ? (g_jitter_seed ^ ((uint64_t)ray * 0x9E3779B97F4A7C15ull)) | 1ull : 0; }
+inline double jit(double x) {
+    if (!t_jitter || x == 0.0 || !std::isfinite(x)) return x;
+    t_jitter = t_jitter * 6364136223846793005ull + 1442695040888963407ull;
+    int k = (int)((t_jitter >> 33) % 5u) - 2; /* -2 .. +2 ulp */
+    int64_t bits;
+    std::memcpy(&bits, &x, sizeof bits);
+    bits += (x > 0.0) ? k : -k;
+    std::memcpy(&x, &bits, sizeof bits);
+    return x;
+}
+
 /* tauint, src/surfaces.f90:13-50; returns false where the reference does `error stop` */
 inline bool tauint(vec pos, vec dir, double mua, double mus, vec centre, double radius, double& dist,
                    bool& tflag, double u) {
     double mu_tot = mua + mus;
-    double tau = -std::log(u);
+    double tau = -jit(std::log(u));
     tflag = false;
     bool flag = intersect_cylinder(pos, dir, dist, centre, radius);
     if (!flag) return false;
+    dist = jit(dist);
     double tauradius = dist * mu_tot;
     if (tau < tauradius) {
         dist = tau / mu_tot;
@@ -306,7 +329,7 @@ inline void stokes(vec& dir, double hgg, Draws& rng) {
     double cost = dir.z;
     double sint = std::sqrt(1. - cost * cost);
     double g2 = hgg * hgg;
-    double phi = std::atan2(dir.y, dir.x);
+    double phi = jit(std::atan2(dir.y, dir.x));
     double cosp, sinp;
 
     if (hgg == 0.0) { /* :33-48 isotropic */
@@ -318,8 +341,8 @@ inline void stokes(vec& dir, double hgg, Draws& rng) {
             sint = std::sqrt(sint);
         }
         phi = TWOPI * rng.scatter();
-        sinp = std::sin(phi);
-        cosp = std::cos(phi);
+        sinp = jit(std::sin(phi));
+        cosp = jit(std::cos(phi));
         nxp = sint * cosp;
         nyp = sint * sinp;
         nzp = cost;
@@ -345,8 +368,8 @@ inline void stokes(vec& dir, double hgg, Draws& rng) {
 
         if (ri1 > PI) { /* :76-113 */
             double ri3 = TWOPI - ri1;
-            double cosi3 = std::cos(ri3);
-            double sini3 = std::sin(ri3);
+            double cosi3 = jit(std::cos(ri3));
+            double sini3 = jit(std::sin(ri3));
             if (bmu == 1. || bmu == -1.) goto L100; /* :81-87 */
             cost = costp * bmu + sintp * sinbt * cosi3;
             if (std::fabs(cost) < 1.) {
@@ -368,12 +391,12 @@ inline void stokes(vec& dir, double hgg, Draws& rng) {
                     cosdph = -1.;
                 }
             }
-            phi = phip + std::acos(cosdph);
+            phi = phip + jit(std::acos(cosdph));
             if (phi > TWOPI) phi = phi - TWOPI;
             if (phi < 0.) phi = phi + TWOPI;
         } else { /* :116-151 */
-            double cosi1 = std::cos(ri1);
-            double sini1 = std::sin(ri1);
+            double cosi1 = jit(std::cos(ri1));
+            double sini1 = jit(std::sin(ri1));
             if (bmu == 1. || bmu == -1.) goto L100; /* :119-125 */
             cost = costp * bmu + sintp * sinbt * cosi1;
             if (std::fabs(cost) < 1.) {
@@ -395,12 +418,12 @@ inline void stokes(vec& dir, double hgg, Draws& rng) {
                     cosdph = -1.;
                 }
             }
-            phi = phip - std::acos(cosdph);
+            phi = phip - jit(std::acos(cosdph));
             if (phi > TWOPI) phi = phi - TWOPI;
             if (phi < 0.) phi = phi + TWOPI;
         }
-        cosp = std::cos(phi);
-        sinp = std::sin(phi);
+        cosp = jit(std::cos(phi));
+        sinp = jit(std::sin(phi));
         nxp = sint * cosp;
         nyp = sint * sinp;
         nzp = cost;
@@ -782,6 +805,7 @@ struct RayOut {
 inline RayOut trace_one(const ort_job& J, const ort_scene& S, int64_t ray, bool have_input, vec pos,
                         vec dir) {
     Draws rng(J.seed, (uint32_t)J.phase, (uint64_t)ray, J.uniform_override);
+    jitter_begin(ray);
     RayOut o;
     o.xp = o.yp = INT32_MIN;
     int st = 0;
@@ -1033,6 +1057,12 @@ int orc_set_image_source(const int32_t* budget) {
         acc += budget[k] > 0 ? budget[k] : 0;
         g_image_cdf[k] = acc;
     }
+    return 0;
+}
+
+/* conditioning probe of the scatter path (see jit()): 0 = off */
+int orc_set_jitter(uint64_t seed) {
+    g_jitter_seed = seed;
     return 0;
 }
 

@@ -108,6 +108,12 @@ def make_scene(bottle="clearBottle-large.params", l2="planoConvex-f39.9mm.params
     return S
 
 
+def set_jitter(seed):
+    """conditioning probe of the scatter path: every libm result / intersection distance of tauint and
+    stokes moved by a pseudo-random -2..+2 ulp (0 = off)"""
+    lib().orc_set_jitter(C.c_uint64(int(seed)))
+
+
 def uniforms(seed, phase, ray, first_slot, n):
     out = np.zeros(n, dtype=np.float64)
     lib().orc_uniforms(seed, phase, ray, first_slot, n, out.ctypes.data_as(DP))

@@ -1,18 +1,19 @@
 """GPU parity: the CUDA path, called through the C-ABI, against the CPU oracle on the same
 seeded inputs.  Tolerances: 1e-9 relative on exit position / direction (BASELINE.json
-north_star); status codes and detector bins identical; integer images and counters bit-exact."""
+north_star), on the vector and per component (conftest.comp_err); status codes and detector bins
+identical; integer images and counters bit-exact.  The scatter path has no blanket waiver: a ray
+may exceed 1e-9 only as far as +-2 ulp in the libm calls of tauint / stokes move THAT ray in the
+oracle itself (conftest.scatter_conditioning)."""
 import numpy as np
 import pytest
 
 from opticalraytrace_b200 import abi
 from tests import cases
-from tests.conftest import rel_err
+from tests.conftest import both_err, rel_err, scatter_conditioning
 
 pytestmark = pytest.mark.gpu
 
 TOL = 1e-9          # fp64 tolerance stated by BASELINE.json north_star
-TOL_SCATTER = 1e-6  # scatter chains: stokes' spherical-triangle update amplifies 1-ulp input
-                    # differences by ~1/sin^2(deflection); 99.9 % of rays must still meet TOL
 
 
 def test_uniforms_match_oracle(ort, orc):
@@ -32,14 +33,15 @@ def _compare(ort, orc, files, phase, kw, n, tol, stop=0, first_ray=0):
     b = ort.trace_rays(job, scene, n)
     assert np.array_equal(a["status"], b["status"]), np.flatnonzero(a["status"] != b["status"])[:10]
     assert np.array_equal(a["bin"], b["bin"])
-    e = np.maximum(rel_err(a["pos"], b["pos"]), rel_err(a["dir"], b["dir"]))
-    return e, a
+    e, ec = both_err(a, b)
+    return np.maximum(e, ec), a       # vector-relative and per-component, whichever is worse
 
 
 @pytest.mark.parametrize("cid,files,phase,kw", cases.RAY_CASES, ids=[c[0] for c in cases.RAY_CASES])
 def test_rays_match_oracle(ort, orc, cid, files, phase, kw):
     e, a = _compare(ort, orc, files, phase, kw, 200_000, TOL)
     assert np.nanmax(e) < TOL, np.nanmax(e)
+    print("%s: worst of (vector-relative, per-component) error %.3g" % (cid, np.nanmax(e)))
     # unit directions wherever the ray is still a ray
     ok = a["status"] == 0
     if ok.any():
@@ -77,9 +79,21 @@ def test_rays_stage_by_stage(ort, orc, phase, stop):
 
 @pytest.mark.parametrize("cid,files,phase,kw", cases.SCATTER_CASES, ids=[c[0] for c in cases.SCATTER_CASES])
 def test_scatter_rays_match_oracle(ort, orc, cid, files, phase, kw):
-    e, _ = _compare(ort, orc, files, phase, kw, 200_000, TOL_SCATTER)
-    assert np.nanmax(e) < TOL_SCATTER, np.nanmax(e)
-    assert np.quantile(e, 0.999) < TOL
+    n = 200_000
+    scene = cases.scene_for(orc, files, phase, kw)
+    job = abi.default_job(phase, **kw)
+    a, resp, stable = scatter_conditioning(orc, job, scene, n)
+    b = ort.trace_rays(job, scene, n)
+    assert np.array_equal(a["status"], b["status"]), np.flatnonzero(a["status"] != b["status"])[:10]
+    assert np.array_equal(a["bin"], b["bin"])
+    e = np.nan_to_num(np.maximum(rel_err(a["pos"], b["pos"]), rel_err(a["dir"], b["dir"])))
+    # every ray within 1e-9, or within 4x what +-2 ulp in the libm calls does to THIS ray in the oracle
+    allowed = np.maximum(TOL, 4.0 * resp)
+    assert np.all(e[stable] <= allowed[stable]), float((e / allowed)[stable].max())
+    assert np.all(e[resp < TOL / 4] < TOL)
+    print("%s: %d of %d rays above 1e-9 (largest %.3g, its own conditioning bound %.3g); %d rays whose status "
+          "the jitter can flip" % (cid, int((e >= TOL).sum()), n, e.max(), allowed[np.argmax(e)], int((~stable).sum())))
+    assert np.mean(e < TOL) > 0.999
 
 
 def test_explicit_input_rays(ort, orc):

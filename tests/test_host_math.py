@@ -7,9 +7,9 @@ import pytest
 
 from opticalraytrace_b200 import abi
 from tests import cases
-from tests.conftest import rel_err
+from tests.conftest import both_err, rel_err, scatter_conditioning
 
-TOL = 1e-9
+TOL = 1e-9          # north_star: 1e-9 relative, checked on the vector AND per component (conftest.comp_err)
 
 
 _CASES = cases.RAY_CASES + cases.SOURCE_CASES
@@ -24,8 +24,8 @@ def test_reformulated_math_matches_oracle(orc, harness, cid, files, phase, kw):
     b = harness(job, scene, n)
     assert np.array_equal(a["status"], b["status"])
     assert np.array_equal(a["bin"], b["bin"])
-    e = np.maximum(rel_err(a["pos"], b["pos"]), rel_err(a["dir"], b["dir"]))
-    assert np.nanmax(e) < TOL
+    e, ec = both_err(a, b)
+    assert np.nanmax(e) < TOL and np.nanmax(ec) < TOL, (np.nanmax(e), np.nanmax(ec))
 
 
 @pytest.mark.parametrize("cid,files,phase,kw", cases.SCATTER_CASES, ids=[c[0] for c in cases.SCATTER_CASES])
@@ -33,12 +33,15 @@ def test_scatter_math_matches_oracle(orc, harness, cid, files, phase, kw):
     n = 100_000
     scene = cases.scene_for(orc, files, phase, kw)
     job = abi.default_job(phase, **kw)
-    a = orc.trace_rays(job, scene, n)
+    a, resp, stable = scatter_conditioning(orc, job, scene, n)
     b = harness(job, scene, n)
     assert np.array_equal(a["status"], b["status"])
     assert np.array_equal(a["bin"], b["bin"])
-    e = np.maximum(rel_err(a["pos"], b["pos"]), rel_err(a["dir"], b["dir"]))
-    assert np.nanmax(e) < 1e-6 and np.quantile(e, 0.999) < TOL
+    e = np.nan_to_num(np.maximum(rel_err(a["pos"], b["pos"]), rel_err(a["dir"], b["dir"])))
+    # no blanket waiver: every ray within 1e-9, or within 4x what +-2 ulp in the libm calls does to THIS ray
+    assert np.all(e[stable] <= np.maximum(TOL, 4.0 * resp[stable])), float((e / np.maximum(TOL, 4.0 * resp))[stable].max())
+    assert np.all(e[resp < TOL / 4] < TOL)
+    assert np.mean(e < TOL) > 0.999
     assert (a["status"] == 2).any() or (a["status"] == 6).any() or "faithful" in cid  # absorption exercised
 
 
