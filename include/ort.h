@@ -64,6 +64,9 @@ extern "C" {
                                         status_hist[ORT_FILTER_SLOT_WRONG] = calls that disagree with
                                         fp64 (0 expected); image and the other counters as usual */
 
+#define ORT_FLAG_ONE_LANE 32          /* diagnostic: a batched call with few rays per scene runs its scenes back to
+                                        back on one stream instead of overlapping them on several */
+
 /* ort_job.source_kind = settings.params source_type.  Which routine emits, per loop
  * (reference src/main.f90:95-101 and :132-142):
  *                 ring loop (phase 1)                      point loop (phase 2)
@@ -119,6 +122,8 @@ enum ort_status {
                                         with bottle!"`; crs: spot point beside the bottle */
 };
 #define ORT_NSTATUS 32
+#define ORT_SCATTER_EVENTS_SLOT 27   /* not a status: the number of scatter events (stokes calls, src/lens.f90:268,
+                                       319) of the launch, for the roofline's flop count */
 #define ORT_FILTER_SLOT_OVERFLOW 29 /* internal: non-zero makes ort_trace fail with ORT_ECUDA */
 #define ORT_FILTER_SLOT_CALLED 30   /* only with ORT_FLAG_VERIFY_FILTER */
 #define ORT_FILTER_SLOT_WRONG 31

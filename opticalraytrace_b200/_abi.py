@@ -17,7 +17,9 @@ ORT_OK, ORT_EINVAL, ORT_ENODEVICE, ORT_ECUDA, ORT_ENCCL, ORT_EIO, ORT_EPARSE, OR
 PHASE_RING, PHASE_POINT = 1, 2
 FLAG_FIX_OUTER_ELLIPSE, FLAG_NO_REDUCE, FLAG_NO_COMPACTION = 1, 2, 4
 FLAG_NO_FILTER, FLAG_VERIFY_FILTER = 8, 16
+FLAG_ONE_LANE = 32
 FILTER_SLOT_CALLED, FILTER_SLOT_WRONG = 30, 31
+SCATTER_EVENTS_SLOT = 27
 STOP_NONE, STOP_SOURCE, STOP_BOTTLE, STOP_L2, STOP_L3 = 0, 1, 2, 3, 4
 SRC_POINT, SRC_CRS, SRC_ISORS, SRC_SPOT, SRC_IMAGE = 0, 1, 2, 3, 4
 SOURCE_KINDS = {"point": SRC_POINT, "crs": SRC_CRS, "isors": SRC_ISORS, "spot": SRC_SPOT,

@@ -15,6 +15,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -103,22 +104,30 @@ static int nccl_load() {
 /* ------------------------------------------------------------------------------------------
  * library state
  * ---------------------------------------------------------------------------------------- */
+/* One in-order lane of launches.  A batched call with few rays per scene (a quick-look sweep) spreads its
+ * scenes over ORT_LANES lanes so that the tail of one scene's persistent kernel is filled by the next
+ * scene's blocks and launch latencies overlap; large jobs use lane 0 alone. */
+#define ORT_LANES 4
+struct Lane {
+    cudaStream_t stream = nullptr;    /* lane 0: the device's main stream */
+    cudaStream_t stream2 = nullptr;   /* the ring loop's fp64 survivors kernels run here, behind the cull kernels */
+    cudaEvent_t ev_cull[2] = {nullptr, nullptr}, ev_surv[2] = {nullptr, nullptr}, ev_done = nullptr;
+    uint32_t* d_list = nullptr;       /* ring loop: ray indices the fp32 filter hands to fp64, two
+                                         buffers of list_cap entries used alternately */
+    size_t list_cap = 0;
+    unsigned* d_nlist = nullptr;      /* ... and the length of that list, one slot per slice */
+    size_t nlist_cap = 0;
+};
 struct DeviceCtx {
     int dev = -1;
     int num_sms = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev_start = nullptr, ev_traced = nullptr, ev_reduced = nullptr, ev_copied = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_traced = nullptr, ev_reduced = nullptr, ev_copied = nullptr, ev_zeroed = nullptr;
     unsigned long long* d_buf = nullptr; /* [nscenes*BINS image][nscenes*NSTATUS counters] */
     size_t d_elems = 0;
     ncclComm_t comm = nullptr;
     long long* d_image_cdf = nullptr; /* image source: prefix sums of the ray budget */
-    uint32_t* d_list = nullptr;       /* ring loop: ray indices the fp32 filter hands to fp64, two
-                                         buffers of list_cap entries used alternately */
-    size_t list_cap = 0;
-    cudaStream_t stream2 = nullptr;   /* the fp64 survivors kernels run here, behind the cull kernels */
-    cudaEvent_t ev_cull[2] = {nullptr, nullptr}, ev_surv[2] = {nullptr, nullptr};
-    unsigned* d_nlist = nullptr;      /* ... and the length of that list, one slot per slice */
-    size_t nlist_cap = 0;
+    Lane lanes[ORT_LANES];
     /* resident blocks per SM of every kernel launched so far (the attribute set-up and the
      * occupancy query are done once per kernel and device, not once per scene of a batch) */
     std::vector<std::pair<const void*, int>> occ;
@@ -159,10 +168,17 @@ static int ctx_open(DeviceCtx& c, int dev) {
     CK(cudaEventCreate(&c.ev_traced));
     CK(cudaEventCreate(&c.ev_reduced));
     CK(cudaEventCreate(&c.ev_copied));
-    CK(cudaStreamCreateWithFlags(&c.stream2, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
-        CK(cudaEventCreateWithFlags(&c.ev_cull[i], cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&c.ev_surv[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c.ev_zeroed, cudaEventDisableTiming));
+    for (int l = 0; l < ORT_LANES; ++l) {
+        Lane& L = c.lanes[l];
+        if (l == 0) L.stream = c.stream;
+        else CK(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&L.stream2, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CK(cudaEventCreateWithFlags(&L.ev_cull[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&L.ev_surv[i], cudaEventDisableTiming));
+        }
+        CK(cudaEventCreateWithFlags(&L.ev_done, cudaEventDisableTiming));
     }
     return ORT_OK;
 }
@@ -202,19 +218,25 @@ extern "C" int ort_finalize(void) {
         if (c.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c.comm);
         if (c.d_buf) cudaFree(c.d_buf);
         if (c.d_image_cdf) cudaFree(c.d_image_cdf);
-        if (c.d_list) cudaFree(c.d_list);
-        if (c.d_nlist) cudaFree(c.d_nlist);
+        for (int l = 0; l < ORT_LANES; ++l) {
+            Lane& L = c.lanes[l];
+            if (L.d_list) cudaFree(L.d_list);
+            if (L.d_nlist) cudaFree(L.d_nlist);
+            for (int i = 0; i < 2; ++i) {
+                if (L.ev_cull[i]) cudaEventDestroy(L.ev_cull[i]);
+                if (L.ev_surv[i]) cudaEventDestroy(L.ev_surv[i]);
+            }
+            if (L.ev_done) cudaEventDestroy(L.ev_done);
+            if (L.stream2) cudaStreamDestroy(L.stream2);
+            if (l > 0 && L.stream) cudaStreamDestroy(L.stream);
+        }
+        if (c.ev_zeroed) cudaEventDestroy(c.ev_zeroed);
         for (void* p : c.scratch)
             if (p) cudaFree(p);
         if (c.ev_start) cudaEventDestroy(c.ev_start);
         if (c.ev_traced) cudaEventDestroy(c.ev_traced);
         if (c.ev_reduced) cudaEventDestroy(c.ev_reduced);
         if (c.ev_copied) cudaEventDestroy(c.ev_copied);
-        for (int i = 0; i < 2; ++i) {
-            if (c.ev_cull[i]) cudaEventDestroy(c.ev_cull[i]);
-            if (c.ev_surv[i]) cudaEventDestroy(c.ev_surv[i]);
-        }
-        if (c.stream2) cudaStreamDestroy(c.stream2);
         if (c.stream) cudaStreamDestroy(c.stream);
     }
     if (g.h_pinned) cudaFreeHost(g.h_pinned);
@@ -434,7 +456,7 @@ static bool ring_filter_applies(const ort_job& job, const DevScene& s, bool flat
  * is < 1 % of it, short enough that the list of ray indices stays a few hundred MB. */
 static const int64_t ORT_RING_SLICE = (int64_t)1 << 29;
 
-static int enqueue_ring_filter(DeviceCtx& c, const ort_job& job, const DevScene& s, const DevFilter& K,
+static int enqueue_ring_filter(DeviceCtx& c, Lane& L, const ort_job& job, const DevScene& s, const DevFilter& K,
                                unsigned long long aim_cut, int nscenes, int64_t first, int64_t n, unsigned long long* d_img,
                                unsigned long long* d_cnt, int64_t* launches) {
     const bool verify = (job.flags & ORT_FLAG_VERIFY_FILTER) != 0;
@@ -462,56 +484,59 @@ static int enqueue_ring_filter(DeviceCtx& c, const ort_job& job, const DevScene&
     }
 #endif
     const int64_t nslices = (n + ORT_RING_SLICE - 1) / ORT_RING_SLICE;
-    if (c.list_cap < capacity) {
-        if (c.d_list) CK(cudaFree(c.d_list));
-        c.d_list = nullptr;
-        c.list_cap = 0;
-        CK(cudaMalloc(&c.d_list, 2 * capacity * sizeof(uint32_t)));
-        c.list_cap = capacity;
+    if (L.list_cap < capacity) {
+        if (L.d_list) CK(cudaFree(L.d_list)); /* (cudaFree waits for the device: nothing still reads the old list) */
+        L.d_list = nullptr;
+        L.list_cap = 0;
+        CK(cudaMalloc(&L.d_list, 2 * capacity * sizeof(uint32_t)));
+        L.list_cap = capacity;
     }
-    if (c.nlist_cap < (size_t)nslices) {
-        if (c.d_nlist) CK(cudaFree(c.d_nlist));
-        c.d_nlist = nullptr;
-        c.nlist_cap = 0;
-        CK(cudaMalloc(&c.d_nlist, (size_t)nslices * sizeof(unsigned)));
-        c.nlist_cap = (size_t)nslices;
+    if (L.nlist_cap < (size_t)nslices) {
+        if (L.d_nlist) CK(cudaFree(L.d_nlist));
+        L.d_nlist = nullptr;
+        L.nlist_cap = 0;
+        CK(cudaMalloc(&L.d_nlist, (size_t)nslices * sizeof(unsigned)));
+        L.nlist_cap = (size_t)nslices;
     }
-    CK(cudaMemsetAsync(c.d_nlist, 0, (size_t)nslices * sizeof(unsigned), c.stream));
+    /* the previous scene of this lane may still be reading its lists and lengths on stream2 */
+    CK(cudaStreamWaitEvent(L.stream, L.ev_surv[0], 0));
+    CK(cudaStreamWaitEvent(L.stream, L.ev_surv[1], 0));
+    CK(cudaMemsetAsync(L.d_nlist, 0, (size_t)nslices * sizeof(unsigned), L.stream));
 
     DevSceneT<float> sf;
     ort_scene_to_float(s, sf);
-    /* cull(k) runs on the main stream, survivors(k) on the second one behind it, so that the small
+    /* cull(k) runs on the lane's stream, survivors(k) on its second one behind it, so that the small
      * fp64 kernel fills the tail of cull(k+1) instead of standing between two cull kernels; the
      * two list buffers alternate, and cull(k+2) waits until survivors(k) has read its buffer */
     int64_t k = 0;
     for (int64_t off = 0; off < n; off += ORT_RING_SLICE, ++k) {
         int64_t m = n - off < ORT_RING_SLICE ? n - off : ORT_RING_SLICE;
         const int buf = (int)(k & 1);
-        uint32_t* list = c.d_list + (size_t)buf * c.list_cap;
+        uint32_t* list = L.d_list + (size_t)buf * L.list_cap;
         DevJob dj;
         ort_make_dev_job(job, nscenes, first + off, m, dj);
         int64_t batches = (m + 31) / 32;
         int64_t want = (batches + ORT_WPB - 1) / ORT_WPB;
         int grid = c.num_sms * occ_cull;
         int gsz = (int)(want < grid ? (want > 0 ? want : 1) : grid);
-        if (k >= 2) CK(cudaStreamWaitEvent(c.stream, c.ev_surv[buf], 0));
-        cull<<<gsz, ORT_TPB, smem_cull, c.stream>>>(sf, K, dj, aim_cut, list, c.d_nlist + k, (unsigned)capacity, d_cnt);
+        if (k >= 2) CK(cudaStreamWaitEvent(L.stream, L.ev_surv[buf], 0));
+        cull<<<gsz, ORT_TPB, smem_cull, L.stream>>>(sf, K, dj, aim_cut, list, L.d_nlist + k, (unsigned)capacity, d_cnt);
         CK(cudaGetLastError());
-        CK(cudaEventRecord(c.ev_cull[buf], c.stream));
+        CK(cudaEventRecord(L.ev_cull[buf], L.stream));
         /* the list length is only known on the device: size the grid for the longest list there can
          * be (every ray that passes stage A); blocks that find nothing to do leave at once */
         double expect = (double)m * p_pass;
         int64_t sb = ((int64_t)expect / 32 + ORT_WPB) / ORT_WPB;
         int sgrid = c.num_sms * occ_surv;
         int sgsz = (int)(sb < sgrid ? (sb > 0 ? sb : 1) : sgrid);
-        CK(cudaStreamWaitEvent(c.stream2, c.ev_cull[buf], 0));
-        surv<<<sgsz, ORT_TPB, smem_surv, c.stream2>>>(s, sf, K, dj, list, c.d_nlist + k, (unsigned)capacity, d_img, d_cnt);
+        CK(cudaStreamWaitEvent(L.stream2, L.ev_cull[buf], 0));
+        surv<<<sgsz, ORT_TPB, smem_surv, L.stream2>>>(s, sf, K, dj, list, L.d_nlist + k, (unsigned)capacity, d_img, d_cnt);
         CK(cudaGetLastError());
-        CK(cudaEventRecord(c.ev_surv[buf], c.stream2));
+        CK(cudaEventRecord(L.ev_surv[buf], L.stream2));
         *launches += 2;
     }
-    /* join: whatever follows on the main stream (next scene, reduce, read-back) sees every count */
-    for (int64_t j = k > 2 ? k - 2 : 0; j < k; ++j) CK(cudaStreamWaitEvent(c.stream, c.ev_surv[j & 1], 0));
+    /* join: whatever follows on the lane's stream (next scene, reduce, read-back) sees every count */
+    for (int64_t j = k > 2 ? k - 2 : 0; j < k; ++j) CK(cudaStreamWaitEvent(L.stream, L.ev_surv[j & 1], 0));
     return ORT_OK;
 }
 
@@ -535,15 +560,27 @@ static int enqueue_trace_t(DeviceCtx& c, const ort_job& job, const std::vector<D
     CK(cudaMemsetAsync(c.d_buf, 0, elems * sizeof(unsigned long long), c.stream));
     unsigned long long* d_img = c.d_buf;
     unsigned long long* d_cnt = c.d_buf + (size_t)nscenes * ORT_IMG_BINS;
-    /* one launch per scene and per <= 2^31-ray chunk, back to back on the stream; scene and job
-     * travel as kernel parameters, so there is nothing to upload between launches */
+    /* One launch per scene and per <= 2^31-ray chunk; scene and job travel as kernel parameters, so there
+     * is nothing to upload between launches and every scene scalar is an immediate constant-bank operand.
+     * (Indexing the scenes INSIDE one kernel was measured and rejected: a register-indexed LDC per scalar
+     * and a three-register DFMA behind it, ~15 % per ray.)  Large jobs run back to back on the main
+     * stream.  When a batched call has few rays per scene -- a quick-look sweep -- the scenes go round
+     * robin over ORT_LANES streams instead: the tail of one scene's persistent kernel is filled by the
+     * blocks of the next, and the launch latencies overlap. */
+    const int nlanes = (nscenes > 1 && n <= ((int64_t)1 << 26) && !(job.flags & ORT_FLAG_ONE_LANE))
+                           ? (nscenes < ORT_LANES ? nscenes : ORT_LANES) : 1;
+    if (nlanes > 1) {
+        CK(cudaEventRecord(c.ev_zeroed, c.stream));
+        for (int l = 1; l < nlanes; ++l) CK(cudaStreamWaitEvent(c.lanes[l].stream, c.ev_zeroed, 0));
+    }
     for (int sc = 0; sc < nscenes; ++sc) {
+        Lane& L = c.lanes[sc % nlanes];
         DevSceneT<R> dsr;
         scene_as(ds[sc], dsr);
         unsigned long long aim_cut = 0;
         DevFilter K;
         if (ring_filter_applies<R>(job, ds[sc], flat, &aim_cut, &K)) {
-            int rc = enqueue_ring_filter(c, job, ds[sc], K, aim_cut, nscenes, first, n, d_img + (size_t)sc * ORT_IMG_BINS,
+            int rc = enqueue_ring_filter(c, L, job, ds[sc], K, aim_cut, nscenes, first, n, d_img + (size_t)sc * ORT_IMG_BINS,
                                          d_cnt + (size_t)sc * ORT_NSTATUS, launches);
             if (rc != ORT_OK) return rc;
             continue;
@@ -566,11 +603,15 @@ static int enqueue_trace_t(DeviceCtx& c, const ort_job& job, const std::vector<D
             int64_t batches = (m + 31) / 32;
             int64_t want = (batches + ORT_WPB - 1) / ORT_WPB;
             int gsz = (int)(want < grid ? (want > 0 ? want : 1) : grid);
-            k<<<gsz, ORT_TPB, smem, c.stream>>>(dsr, dj, d_img + (size_t)sc * ORT_IMG_BINS,
+            k<<<gsz, ORT_TPB, smem, L.stream>>>(dsr, dj, d_img + (size_t)sc * ORT_IMG_BINS,
                                                 d_cnt + (size_t)sc * ORT_NSTATUS);
             CK(cudaGetLastError());
             ++*launches;
         }
+    }
+    for (int l = 1; l < nlanes; ++l) { /* the main stream continues when every lane is done */
+        CK(cudaEventRecord(c.lanes[l].ev_done, c.lanes[l].stream));
+        CK(cudaStreamWaitEvent(c.stream, c.lanes[l].ev_done, 0));
     }
     CK(cudaEventRecord(c.ev_traced, c.stream));
     return ORT_OK;
@@ -579,6 +620,29 @@ static int enqueue_trace(DeviceCtx& c, const ort_job& job, const std::vector<Dev
                          int64_t n, int64_t* launches) {
     return job.precision == 32 ? enqueue_trace_t<float>(c, job, ds, first, n, launches)
                                : enqueue_trace_t<double>(c, job, ds, first, n, launches);
+}
+
+/* pinned staging buffer -> the caller's (pageable, often untouched) buffer.  A batched call returns
+ * 1.29 MB per scene; above a few MB the copy and the page faults of a fresh destination are spread over
+ * a few threads (a 75-scene sweep: 96 MB, ~18 ms single-threaded -- more than its kernels take) */
+static void host_copy(void* dst, const void* src, size_t bytes) {
+    const size_t chunk = (size_t)4 << 20;
+    unsigned hw = std::thread::hardware_concurrency();
+    size_t nt = bytes / chunk;
+    if (nt > 8) nt = 8;
+    if (hw && nt > hw) nt = hw;
+    if (nt < 2) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    std::vector<std::thread> th;
+    const size_t per = ((bytes / nt) + 4095) & ~(size_t)4095;
+    for (size_t t = 0; t < nt; ++t) {
+        const size_t lo = t * per, hi = (t + 1 == nt || (t + 1) * per > bytes) ? bytes : (t + 1) * per;
+        if (lo >= hi) break;
+        th.emplace_back([=] { memcpy((char*)dst + lo, (const char*)src + lo, hi - lo); });
+    }
+    for (auto& t : th) t.join();
 }
 
 extern "C" int ort_trace(const ort_job* job, const ort_scene* scenes, int nscenes, uint64_t* image,
@@ -660,7 +724,7 @@ extern "C" int ort_trace(const ort_job* job, const ort_scene* scenes, int nscene
         CK(cudaSetDevice(g.devs[d].dev));
         CK(cudaStreamSynchronize(g.devs[d].stream));
     }
-    if (image) memcpy(image, g.h_pinned, img_elems * 8);
+    if (image) host_copy(image, g.h_pinned, img_elems * 8);
     bool trapped = false, list_overflow = false;
     for (int s = 0; s < nscenes; ++s) {
         const unsigned long long* h = g.h_pinned + img_elems + (size_t)s * ORT_NSTATUS;

@@ -232,7 +232,7 @@ __device__ __forceinline__ void ort_bin(unsigned long long* img, bool binned, in
  * C: the three refractions of L3, transfer to the image plane, acceptance + binning. */
 template <int PHASE, int BOTTLE, int SRC, typename R>
 __device__ __forceinline__ int ort_stage_a(const DevSceneT<R>& S, const DevJob& J, const OrtRng& g, uint32_t id,
-                                           OrtRayT<R>& r, uint32_t& wf, uint32_t& wc) {
+                                           OrtRayT<R>& r, uint32_t& wf, uint32_t& wc, int* nevents = nullptr) {
     if (PHASE == ORT_PHASE_RING && SRC == ORT_SRC_POINT && S.ring_shortcut) {
         uint32_t b[4];
         ort_block(g, 1u, b);
@@ -255,7 +255,7 @@ __device__ __forceinline__ int ort_stage_a(const DevSceneT<R>& S, const DevJob& 
             int st = ort_bottle_forward<false>(S, g, D, r);
             if (st) return st;
         } else if (BOTTLE == 2) {
-            int st = ort_bottle_forward<true>(S, g, D, r);
+            int st = ort_bottle_forward<true>(S, g, D, r, nevents);
             if (st) return st;
         }
     }
@@ -348,7 +348,17 @@ ort_trace_kernel(const __grid_constant__ DevSceneT<R> S, const __grid_constant__
             uint32_t wf = 0u, wc = 0u;
             if (id < nrays) {
                 OrtRng g = ort_make_rng_prod(J, id);
-                st = ort_stage_a<PHASE, BOTTLE, SRC>(S, J, g, id, r, wf, wc);
+                if (PHASE == ORT_PHASE_POINT && BOTTLE == 2) { /* scatter events of this ray -> histogram slot 27 */
+                    int nev = 0;
+                    st = ort_stage_a<PHASE, BOTTLE, SRC>(S, J, g, id, r, wf, wc, &nev);
+#if ORT_COUNT_SMEM
+                    if (nev) atomicAdd(ws.hist + ORT_SCATTER_EVENTS_SLOT, (unsigned)nev);
+#else
+                    if (nev) atomicAdd(counters + ORT_SCATTER_EVENTS_SLOT, (unsigned long long)nev);
+#endif
+                } else {
+                    st = ort_stage_a<PHASE, BOTTLE, SRC>(S, J, g, id, r, wf, wc);
+                }
             }
             if (slim) ort_q0_push<true>(ws.q0, n1, st == 0, r, id, wf, wc, lane);
             else ort_q0_push<false>(ws.q0, n1, st == 0, r, id, wf, wc, lane);
@@ -662,7 +672,9 @@ ort_trace_flat_kernel(const __grid_constant__ DevSceneT<R> S, const __grid_const
             OrtRng g = ort_make_rng_prod(J, id);
             OrtRayT<R> r;
             uint32_t wf, wc;
-            st = ort_stage_a<PHASE, BOTTLE, ORT_SRC_POINT>(S, J, g, id, r, wf, wc);
+            int nev = 0;
+            st = ort_stage_a<PHASE, BOTTLE, ORT_SRC_POINT>(S, J, g, id, r, wf, wc, &nev);
+            if (nev) atomicAdd(counters + ORT_SCATTER_EVENTS_SLOT, (unsigned long long)nev);
             if (st == 0) st = ort_stage_b<PHASE, ORT_SRC_POINT>(S, J, g, r, wf, wc);
             if (st == 0) st = ort_stage_c(S, J, g, r, &xp, &yp);
         }

@@ -1005,7 +1005,7 @@ ORT_HD void ort_stokes(OrtRayT<R>& r, R hgg, const OrtRng& g, OrtScatterRngT<R>&
 template <typename R>
 ORT_HD int ort_scatter_loop(const DevSceneT<R>& S, const OrtRng& g, OrtScatterRngT<R>& sr, OrtRayT<R>& r,
                             R mutot, R inv_mutot, R albedo, R hgg, R Rlim,
-                            R Rlim2, int st_absorbed, int st_backward, R* t) {
+                            R Rlim2, int st_absorbed, int st_backward, R* t, int* nevents) {
     bool flag;
     if (!ort_tauint(r, mutot, inv_mutot, S.bcy, S.bcz, Rlim2, ort_scatter_draw(g, sr), t, &flag))
         return ORT_ST_TAUINT_MISS;
@@ -1013,6 +1013,7 @@ ORT_HD int ort_scatter_loop(const DevSceneT<R>& S, const OrtRng& g, OrtScatterRn
         ort_advance(r, *t);
         if (ort_scatter_draw(g, sr) < albedo) {
             ort_stokes(r, hgg, g, sr);
+            ++*nevents;
         } else {
             return st_absorbed;
         }
@@ -1025,8 +1026,11 @@ ORT_HD int ort_scatter_loop(const DevSceneT<R>& S, const OrtRng& g, OrtScatterRn
     return 0;
 }
 
+/* *nevents (SCATTER only) counts the scatter events (stokes calls) of this ray */
 template <bool SCATTER, typename R>
-ORT_HD int ort_bottle_forward(const DevSceneT<R>& S, const OrtRng& g, const OrtDraws01& D, OrtRayT<R>& r) {
+ORT_HD int ort_bottle_forward(const DevSceneT<R>& S, const OrtRng& g, const OrtDraws01& D, OrtRayT<R>& r, int* nevents = nullptr) {
+    int local_events = 0;
+    if (nevents == nullptr) nevents = &local_events;
     R t;
     const R u_in = ort_wide2<R>(g, D.b[0], D.b[1]), u_out = ort_narrow2<R>(g, D.b[2]); /* slots 2, 3, doubled */
     OrtScatterRngT<R> sr;
@@ -1037,7 +1041,7 @@ ORT_HD int ort_bottle_forward(const DevSceneT<R>& S, const OrtRng& g, const OrtD
     if (!hit) return ORT_ST_BOTTLE_INNER_MISS;
     if (SCATTER && S.scatter_c) {
         int st = ort_scatter_loop(S, g, sr, r, S.mutot_c, S.inv_mutot_c, S.albedo_c, R(0.65), S.b_in_r,
-                                  S.b_in_r2, ORT_ST_CONTENTS_ABSORBED, ORT_ST_CONTENTS_BACKWARD, &t);
+                                  S.b_in_r2, ORT_ST_CONTENTS_ABSORBED, ORT_ST_CONTENTS_BACKWARD, &t, nevents);
         if (st) return st;
     }
     ort_advance(r, t);
@@ -1054,7 +1058,7 @@ ORT_HD int ort_bottle_forward(const DevSceneT<R>& S, const OrtRng& g, const OrtD
     if (!hit) return ORT_ST_BOTTLE_OUTER_MISS;
     if (SCATTER && S.scatter_b) {
         int st = ort_scatter_loop(S, g, sr, r, S.mutot_b, S.inv_mutot_b, S.albedo_b, R(0.9), S.b_out_r,
-                                  S.b_out_r2, ORT_ST_WALL_ABSORBED, ORT_ST_WALL_BACKWARD, &t);
+                                  S.b_out_r2, ORT_ST_WALL_ABSORBED, ORT_ST_WALL_BACKWARD, &t, nevents);
         if (st) return st;
     }
     ort_advance(r, t);

@@ -188,7 +188,7 @@ def trace(job, scenes, *, want_image=True, allow_trap=False):
         scenes = [scenes]
     ns = len(scenes)
     arr = (abi.Scene * ns)(*scenes)
-    image = np.zeros((ns, abi.ORT_IMG_N, abi.ORT_IMG_N), dtype=np.uint64) if want_image else None
+    image = np.empty((ns, abi.ORT_IMG_N, abi.ORT_IMG_N), dtype=np.uint64) if want_image else None   # overwritten
     lost = np.zeros(ns, dtype=np.int64)
     hist = np.zeros((ns, abi.ORT_NSTATUS), dtype=np.int64)
     tm = abi.Timing()

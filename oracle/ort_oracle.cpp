@@ -324,7 +324,9 @@ inline bool tauint(vec pos, vec dir, double mua, double mus, vec centre, double 
 /* ---------------------------------------------------------------------------------------
  * stokes, reference src/stokes.f90:7-166 (Henyey-Greenstein direction update)
  * ------------------------------------------------------------------------------------- */
+static thread_local int64_t t_scatter_events = 0; /* stokes() calls of this thread (status_hist slot 27) */
 inline void stokes(vec& dir, double hgg, Draws& rng) {
+    ++t_scatter_events;
     double nxp = dir.x, nyp = dir.y, nzp = dir.z;
     double cost = dir.z;
     double sint = std::sqrt(1. - cost * cost);
@@ -1127,6 +1129,7 @@ int orc_trace(const ort_job* job, const ort_scene* scenes, int nscenes, uint64_t
 #pragma omp parallel
         {
             int64_t h[ORT_NSTATUS] = {0};
+            t_scatter_events = 0;
 #pragma omp for schedule(static)
             for (int64_t i = 0; i < job->nrays; ++i) {
                 RayOut o = trace_one(*job, S, job->first_ray + i, false, {0, 0, 0}, {0, 0, 1});
@@ -1137,6 +1140,7 @@ int orc_trace(const ort_job* job, const ort_scene* scenes, int nscenes, uint64_t
                     img[idx] += 1;
                 }
             }
+            h[ORT_SCATTER_EVENTS_SLOT] = t_scatter_events;
 #pragma omp critical
             for (int k = 0; k < ORT_NSTATUS; ++k) hist[k] += h[k];
         }
