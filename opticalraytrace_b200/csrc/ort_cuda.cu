@@ -405,6 +405,14 @@ extern "C" int ort_set_image_source(const int32_t* budget) {
 template <typename R>
 struct Kernels {
     typedef void (*trace_t)(const DevSceneT<R>, const DevJob, unsigned long long*, unsigned long long*);
+    /* point loop through a scattering bottle: the kernel that queues rays between scatter events */
+    static trace_t pick_scatter(int src) {
+        switch (src) {
+            case ORT_SRC_IMAGE: return ort_trace_scatter_kernel<ORT_SRC_IMAGE, R>;
+            case ORT_SRC_SPOT: return ort_trace_scatter_kernel<ORT_SRC_SPOT, R>;
+            default: return ort_trace_scatter_kernel<ORT_SRC_POINT, R>; /* point, crs, isors: point() */
+        }
+    }
     static trace_t pick(int phase, int bottle_mode, int src, bool flat) {
         if (flat) { /* diagnostic kernel: default sources only */
             if (phase == ORT_PHASE_RING) return ort_trace_flat_kernel<ORT_PHASE_RING, 0, R>;
@@ -554,7 +562,7 @@ static int enqueue_trace_t(DeviceCtx& c, const ort_job& job, const std::vector<D
         c.d_elems = elems;
     }
     bool flat = (job.flags & ORT_FLAG_NO_COMPACTION) != 0 && job.source_kind == ORT_SRC_POINT;
-    size_t smem = flat ? 0 : (size_t)ORT_WPB * sizeof(WarpShared<R>);
+    const size_t smem_trace = flat ? 0 : (size_t)ORT_WPB * sizeof(WarpShared<R>);
 
     CK(cudaEventRecord(c.ev_start, c.stream));
     CK(cudaMemsetAsync(c.d_buf, 0, elems * sizeof(unsigned long long), c.stream));
@@ -590,7 +598,10 @@ static int enqueue_trace_t(DeviceCtx& c, const ort_job& job, const std::vector<D
          * depend on what it is batched with */
         const int bottle_mode = (job.phase == ORT_PHASE_POINT && job.use_bottle)
                                     ? ((ds[sc].scatter_b || ds[sc].scatter_c) ? 2 : 1) : 0;
-        typename Kernels<R>::trace_t k = Kernels<R>::pick(job.phase, bottle_mode, job.source_kind, flat);
+        const bool scatter_kernel = bottle_mode == 2 && !flat;
+        typename Kernels<R>::trace_t k = scatter_kernel ? Kernels<R>::pick_scatter(job.source_kind)
+                                                        : Kernels<R>::pick(job.phase, bottle_mode, job.source_kind, flat);
+        const size_t smem = scatter_kernel ? (size_t)ORT_WPB * sizeof(ScatterShared<R>) : smem_trace;
         int occ = 0;
         int orc = ctx_occupancy(c, (const void*)k, smem, &occ);
         if (orc != ORT_OK) return orc;

@@ -408,6 +408,153 @@ ort_trace_kernel(const __grid_constant__ DevSceneT<R> S, const __grid_constant__
 #endif
 }
 
+/* ---- point loop through a SCATTERING bottle -----------------------------------------------------
+ * The reference's scatter loops (src/lens.f90:262-282, :312-333) have geometric trip counts; a warp that
+ * runs them per lane waits for its longest chain (measured: 9.7 of 32 lanes busy in BASELINE config 4).
+ * Here a scatter EVENT is a stage of its own with its own queue: rays that owe an event wait in qs with
+ * their explicit loop state (ort_bottle_resume / ort_scatter_event), and an event pass always has 32 of
+ * them.  A ray whose loop has ended walks on (the rest of the bottle, possibly into the second loop and
+ * back into qs) inside the same pass; that walk is short.  Stages B and C are those of ort_trace_kernel. */
+template <typename R>
+struct ScatterQueue {
+    R px[ORT_QCAP], py[ORT_QCAP], pz[ORT_QCAP], dx[ORT_QCAP], dy[ORT_QCAP], dz[ORT_QCAP];
+    R t[ORT_QCAP], spare[ORT_QCAP];   /* pending step; odd-slot draw of the last generated block */
+    uint32_t id[ORT_QCAP], next[ORT_QCAP], loop[ORT_QCAP];
+};
+template <typename R>
+struct ScatterShared {
+    ScatterQueue<R> qs;
+    WarpQueueL2<R> q0;
+    WarpQueue<R> q1;
+    unsigned hist[ORT_NSTATUS];
+};
+template <typename R>
+__device__ __forceinline__ void ort_qs_push(ScatterQueue<R>& q, int& n, bool alive, const OrtRayT<R>& r,
+                                            const OrtScatterStateT<R>& ss, uint32_t id, unsigned lane) {
+    unsigned m = __ballot_sync(ORT_FULL, alive);
+    if (alive) {
+        const int p = n + __popc(m & ((1u << lane) - 1u));
+        ORT_ASSERT(p >= 0 && p < ORT_QCAP);
+        q.px[p] = r.px; q.py[p] = r.py; q.pz[p] = r.pz;
+        q.dx[p] = r.dx; q.dy[p] = r.dy; q.dz[p] = r.dz;
+        q.t[p] = ss.t; q.spare[p] = ss.sr.spare;
+        q.id[p] = id; q.next[p] = ss.sr.next; q.loop[p] = (uint32_t)ss.loop;
+    }
+    n += __popc(m);
+}
+template <typename R>
+__device__ __forceinline__ bool ort_qs_pop(ScatterQueue<R>& q, int& n, OrtRayT<R>& r, OrtScatterStateT<R>& ss,
+                                           uint32_t& id, unsigned lane) {
+    int cnt = n < 32 ? n : 32;
+    int base = n - cnt;
+    const bool act = (int)lane < cnt;
+    if (act) {
+        const int p = base + lane;
+        ORT_ASSERT(p >= 0 && p < ORT_QCAP);
+        r.px = q.px[p]; r.py = q.py[p]; r.pz = q.pz[p];
+        r.dx = q.dx[p]; r.dy = q.dy[p]; r.dz = q.dz[p];
+        ss.t = q.t[p]; ss.sr.spare = q.spare[p];
+        id = q.id[p]; ss.sr.next = q.next[p]; ss.loop = (int)q.loop[p];
+    }
+    n = base;
+    return act;
+}
+
+template <int SRC, typename R>
+__global__ void __launch_bounds__(ORT_TPB, 2)
+ort_trace_scatter_kernel(const __grid_constant__ DevSceneT<R> S, const __grid_constant__ DevJob J,
+                         unsigned long long* __restrict__ img, unsigned long long* __restrict__ counters) {
+    extern __shared__ __align__(16) unsigned char ort_smem[];
+    ScatterShared<R>& ws = reinterpret_cast<ScatterShared<R>*>(ort_smem)[threadIdx.x >> 5];
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t nwarps = gridDim.x * ORT_WPB;
+    const uint32_t gwarp = blockIdx.x * ORT_WPB + (threadIdx.x >> 5);
+    const uint32_t nrays = (uint32_t)J.nrays;
+    const uint32_t nbatches = (nrays + 31u) >> 5;
+    ort_hist_clear(ws.hist, lane);
+    int ns = 0, n1 = 0, n2 = 0;
+    uint32_t b = gwarp;
+    for (;;) {
+        /* deepest stage with a full batch first; new rays only when nothing is full; then drain */
+        int stage;
+        if (n2 >= 32) stage = 3;
+        else if (n1 >= 32) stage = 2;
+        else if (ns >= 32) stage = 1;
+        else if (b < nbatches) stage = 0;
+        else if (ns > 0) stage = 1; /* events feed the later stages: drain them first */
+        else if (n2 > 0) stage = 3;
+        else if (n1 > 0) stage = 2;
+        else break;
+
+        OrtRayT<R> r;
+        uint32_t id = 0;
+        if (stage <= 1) {
+            /* 0: emit and walk into the bottle; 1: one scatter event, then walk on if the loop has ended */
+            OrtScatterStateT<R> ss;
+            ss.t = R(0.0); ss.sr.next = 16u; ss.sr.spare = R(0.0); ss.loop = 0;
+            bool act;
+            if (stage == 0) {
+                id = b * 32u + lane;
+                b += nwarps;
+                act = id < nrays;
+            } else {
+                act = ort_qs_pop(ws.qs, ns, r, ss, id, lane);
+            }
+            __syncwarp();
+            int st = -1;
+            uint32_t wf = 0u, wc = 0u;
+            if (act) {
+                OrtRng g = ort_make_rng_prod(J, id);
+                int from = 0;
+                if (stage == 1) {
+                    bool scattered;
+                    st = ort_scatter_event(S, g, r, ss, &scattered);
+                    if (scattered) atomicAdd(ws.hist + ORT_SCATTER_EVENTS_SLOT, 1u);
+                    from = ss.loop + 1;
+                } else {
+                    st = 0;
+                }
+                if (st == 0) {
+                    OrtDraws01 D;
+                    ort_draws01(g, D);
+                    wf = D.a[3];
+                    wc = D.b[3];
+                    if (stage == 0) st = ort_emit<ORT_PHASE_POINT, SRC>(S, J, g, D, J.first_ray + (long long)id, r);
+                    if (st == 0) st = ort_bottle_resume(S, g, D, r, ss, from);
+                    if (st == 0) st = ort_l2_enter(S, r);
+                }
+            }
+            ort_qs_push(ws.qs, ns, st == ORT_BOTTLE_EVENT, r, ss, id, lane);
+            ort_q0_push<false>(ws.q0, n1, st == 0, r, id, wf, wc, lane);
+            __syncwarp();
+            ort_tally_smem(ws.hist, st, st > 0);
+        } else if (stage == 2) {
+            uint32_t wf = 0u, wc = 0u;
+            const bool act = ort_q0_pop<false>(ws.q0, n1, S.l2_flat_z, r, id, wf, wc, lane);
+            int st = -1;
+            if (act) {
+                OrtRng g = ort_make_rng_prod(J, id);
+                st = ort_stage_b<ORT_PHASE_POINT, SRC>(S, J, g, r, wf, wc);
+            }
+            __syncwarp();
+            ort_q_push(ws.q1, n2, st == 0, r, id, lane);
+            __syncwarp();
+            ort_tally_smem(ws.hist, st, st > 0);
+        } else {
+            const bool act = ort_q_pop(ws.q1, n2, r, id, lane) >= 0;
+            __syncwarp();
+            int st = -1, xp = 0, yp = 0;
+            if (act) {
+                OrtRng g = ort_make_rng_prod(J, id);
+                st = ort_stage_c(S, J, g, r, &xp, &yp);
+            }
+            ort_bin(img, st == ORT_ST_BINNED, xp, yp, lane);
+            ort_tally_smem(ws.hist, st, st >= 0);
+        }
+    }
+    ort_hist_flush(ws.hist, lane, counters);
+}
+
 /* ---- ring loop with the fp32 culling filter (ort_ring_filter) ------------------------------
  * Two kernels per slice of the ray range, because 99 % of the ring rays never need fp64 and a
  * kernel that contains the fp64 stages pays their 80 registers on every warp:

@@ -1001,74 +1001,148 @@ ORT_HD void ort_stokes(OrtRayT<R>& r, R hgg, const OrtRng& g, OrtScatterRngT<R>&
 /* -------------------------------------------------------------------------------------------
  * glass_bottle%forward, src/lens.f90:230-350.  Returns 0 or the ort_status that ended the ray.
  * ----------------------------------------------------------------------------------------- */
-/* one scatter loop (contents :262-282, wall :312-333); *t is the step still to be taken */
+/* The clear bottle: straight through. */
 template <typename R>
-ORT_HD int ort_scatter_loop(const DevSceneT<R>& S, const OrtRng& g, OrtScatterRngT<R>& sr, OrtRayT<R>& r,
-                            R mutot, R inv_mutot, R albedo, R hgg, R Rlim,
-                            R Rlim2, int st_absorbed, int st_backward, R* t, int* nevents) {
-    bool flag;
-    if (!ort_tauint(r, mutot, inv_mutot, S.bcy, S.bcz, Rlim2, ort_scatter_draw(g, sr), t, &flag))
-        return ORT_ST_TAUINT_MISS;
-    while (!flag) {
-        ort_advance(r, *t);
-        if (ort_scatter_draw(g, sr) < albedo) {
-            ort_stokes(r, hgg, g, sr);
-            ++*nevents;
-        } else {
-            return st_absorbed;
-        }
-        if (!ort_tauint(r, mutot, inv_mutot, S.bcy, S.bcz, Rlim2, ort_scatter_draw(g, sr), t, &flag))
-            return ORT_ST_TAUINT_MISS;
-        /* the reference's exit test uses (x,z) although the axis is x */
-        if (sqrt(fma(r.px, r.px, r.pz * r.pz)) >= Rlim) break;
-    }
-    if (r.dz < R(0.0)) return st_backward;
-    return 0;
-}
-
-/* *nevents (SCATTER only) counts the scatter events (stokes calls) of this ray */
-template <bool SCATTER, typename R>
-ORT_HD int ort_bottle_forward(const DevSceneT<R>& S, const OrtRng& g, const OrtDraws01& D, OrtRayT<R>& r, int* nevents = nullptr) {
-    int local_events = 0;
-    if (nevents == nullptr) nevents = &local_events;
+ORT_HD int ort_bottle_clear(const DevSceneT<R>& S, const OrtRng& g, const OrtDraws01& D, OrtRayT<R>& r) {
     R t;
     const R u_in = ort_wide2<R>(g, D.b[0], D.b[1]), u_out = ort_narrow2<R>(g, D.b[2]); /* slots 2, 3, doubled */
-    OrtScatterRngT<R> sr;
-    sr.next = 16;
-    sr.spare = R(0.0);
     bool hit = S.ellipse ? ort_hit_ellipse(r, S.bcy, S.bcz, S.b_in_ia2, S.b_in_ib2, &t)
                          : ort_hit_cylinder(r, S.bcy, S.bcz, S.b_in_r2, &t);
     if (!hit) return ORT_ST_BOTTLE_INNER_MISS;
-    if (SCATTER && S.scatter_c) {
-        int st = ort_scatter_loop(S, g, sr, r, S.mutot_c, S.inv_mutot_c, S.albedo_c, R(0.65), S.b_in_r,
-                                  S.b_in_r2, ORT_ST_CONTENTS_ABSORBED, ORT_ST_CONTENTS_BACKWARD, &t, nevents);
-        if (st) return st;
-    }
     ort_advance(r, t);
     {   /* radial normal in the (y,z) plane, also for the ellipse (src/lens.f90:288-290) */
         R ny = S.bcy - r.py, nz = S.bcz - r.pz;
-        /* on a clear cylindrical wall the hit point is on the cylinder: |(ny,nz)| = radius.  After
-         * a scatter loop (quirk 4) or on an ellipse it is not, and the length is computed. */
-        R inv = (SCATTER || S.ellipse) ? ort_rsqrt(fma(ny, ny, nz * nz)) : S.b_in_invr;
+        /* on a clear cylindrical wall the hit point is on the cylinder: |(ny,nz)| = radius; on an
+         * ellipse it is not, and the length is computed */
+        R inv = S.ellipse ? ort_rsqrt(fma(ny, ny, nz * nz)) : S.b_in_invr;
         R nzu = ort_both_zero(ny, R(0.0)) ? copysign(R(1.0), nz) : nz * inv; /* on-axis ray: exactly +-1 */
         if (ort_interface(r, R(0.0), ny * inv, nzu, S.b_in, u_in)) return ORT_ST_BOTTLE_INNER_REFLECT;
     }
     hit = S.ellipse ? ort_hit_ellipse(r, S.bcy, S.bcz, S.b_out_ia2, S.b_out_ib2, &t)
                     : ort_hit_cylinder(r, S.bcy, S.bcz, S.b_out_r2, &t);
     if (!hit) return ORT_ST_BOTTLE_OUTER_MISS;
-    if (SCATTER && S.scatter_b) {
-        int st = ort_scatter_loop(S, g, sr, r, S.mutot_b, S.inv_mutot_b, S.albedo_b, R(0.9), S.b_out_r,
-                                  S.b_out_r2, ORT_ST_WALL_ABSORBED, ORT_ST_WALL_BACKWARD, &t, nevents);
-        if (st) return st;
-    }
     ort_advance(r, t);
     {
         R ny = S.bcy - r.py, nz = S.bcz - r.pz;
-        R inv = (SCATTER || S.ellipse) ? ort_rsqrt(fma(ny, ny, nz * nz)) : S.b_out_invr;
+        R inv = S.ellipse ? ort_rsqrt(fma(ny, ny, nz * nz)) : S.b_out_invr;
         R nzu = ort_both_zero(ny, R(0.0)) ? copysign(R(1.0), nz) : nz * inv;
         if (ort_interface(r, R(0.0), ny * inv, nzu, S.b_out, u_out)) return ORT_ST_BOTTLE_OUTER_REFLECT;
     }
     return 0;
+}
+
+/* The scattering bottle as a RESUMABLE walk.  The reference runs two `do while` loops per ray (contents
+ * src/lens.f90:262-282, wall :312-333) whose trip counts are geometric random numbers: run per lane, a
+ * warp idles on its longest chain (9.7 of 32 lanes busy in BASELINE config 4).  Here one pass of a loop
+ * body is a unit of work of its own (ort_scatter_event), the walk between the loops is ort_bottle_resume,
+ * and the state in between -- the pending step, the position in the sequential draw stream, which loop
+ * -- is explicit, so that the kernel can queue rays between events and always run 32 of them.
+ *   ort_bottle_resume(from): 0 = the ray has just been emitted, 1 = its contents loop has ended,
+ *   2 = its wall loop has ended.  Returns a final status (> 0), 0 (through the bottle), or
+ *   ORT_BOTTLE_EVENT: the ray is inside loop ss.loop and owes one pass of its body. */
+#define ORT_BOTTLE_EVENT (-2)
+template <typename R>
+struct OrtScatterStateT {
+    OrtScatterRngT<R> sr; /* next sequential slot (16, 17, ...) and the spare of the last block */
+    R t;                  /* the step still to be taken */
+    int loop;             /* 0 contents, 1 wall */
+};
+template <typename R>
+ORT_HD int ort_bottle_resume(const DevSceneT<R>& S, const OrtRng& g, const OrtDraws01& D, OrtRayT<R>& r,
+                             OrtScatterStateT<R>& ss, int from) {
+    bool flag;
+    if (from == 0) {
+        ss.sr.next = 16;
+        ss.sr.spare = R(0.0);
+        bool hit = S.ellipse ? ort_hit_ellipse(r, S.bcy, S.bcz, S.b_in_ia2, S.b_in_ib2, &ss.t)
+                             : ort_hit_cylinder(r, S.bcy, S.bcz, S.b_in_r2, &ss.t);
+        if (!hit) return ORT_ST_BOTTLE_INNER_MISS;
+        if (S.scatter_c) { /* :263-265; tauint always uses the cylinder */
+            if (!ort_tauint(r, S.mutot_c, S.inv_mutot_c, S.bcy, S.bcz, S.b_in_r2, ort_scatter_draw(g, ss.sr), &ss.t, &flag))
+                return ORT_ST_TAUINT_MISS;
+            if (!flag) {
+                ss.loop = 0;
+                return ORT_BOTTLE_EVENT;
+            }
+            if (r.dz < R(0.0)) return ORT_ST_CONTENTS_BACKWARD;
+        }
+    } else if (from == 1) {
+        if (r.dz < R(0.0)) return ORT_ST_CONTENTS_BACKWARD; /* :278-281 */
+    }
+    if (from <= 1) {
+        ort_advance(r, ss.t);
+        {   /* radial normal in the (y,z) plane, also for the ellipse (src/lens.f90:288-290); after a scatter
+             * loop (quirk 4) the point need not lie on the cylinder: the length is computed */
+            R ny = S.bcy - r.py, nz = S.bcz - r.pz;
+            R inv = ort_rsqrt(fma(ny, ny, nz * nz));
+            R nzu = ort_both_zero(ny, R(0.0)) ? copysign(R(1.0), nz) : nz * inv; /* on-axis ray: exactly +-1 */
+            if (ort_interface(r, R(0.0), ny * inv, nzu, S.b_in, ort_wide2<R>(g, D.b[0], D.b[1]))) /* slot 2 */
+                return ORT_ST_BOTTLE_INNER_REFLECT;
+        }
+        bool hit = S.ellipse ? ort_hit_ellipse(r, S.bcy, S.bcz, S.b_out_ia2, S.b_out_ib2, &ss.t)
+                             : ort_hit_cylinder(r, S.bcy, S.bcz, S.b_out_r2, &ss.t);
+        if (!hit) return ORT_ST_BOTTLE_OUTER_MISS;
+        if (S.scatter_b) { /* :313-315 */
+            if (!ort_tauint(r, S.mutot_b, S.inv_mutot_b, S.bcy, S.bcz, S.b_out_r2, ort_scatter_draw(g, ss.sr), &ss.t, &flag))
+                return ORT_ST_TAUINT_MISS;
+            if (!flag) {
+                ss.loop = 1;
+                return ORT_BOTTLE_EVENT;
+            }
+            if (r.dz < R(0.0)) return ORT_ST_WALL_BACKWARD;
+        }
+    } else {
+        if (r.dz < R(0.0)) return ORT_ST_WALL_BACKWARD; /* :329-332 */
+    }
+    ort_advance(r, ss.t);
+    {
+        R ny = S.bcy - r.py, nz = S.bcz - r.pz;
+        R inv = ort_rsqrt(fma(ny, ny, nz * nz));
+        R nzu = ort_both_zero(ny, R(0.0)) ? copysign(R(1.0), nz) : nz * inv;
+        if (ort_interface(r, R(0.0), ny * inv, nzu, S.b_out, ort_narrow2<R>(g, D.b[2]))) /* slot 3 */
+            return ORT_ST_BOTTLE_OUTER_REFLECT;
+    }
+    return 0;
+}
+/* One pass of the body of loop ss.loop (:266-277 / :316-328): step, albedo draw, stokes, next tauint, the
+ * reference's exit test.  Returns a final status (> 0), ORT_BOTTLE_EVENT (another pass is owed) or 0 (the
+ * loop has ended: ort_bottle_resume(ss.loop + 1) goes on).  *scattered = stokes was called. */
+template <typename R>
+ORT_HD int ort_scatter_event(const DevSceneT<R>& S, const OrtRng& g, OrtRayT<R>& r, OrtScatterStateT<R>& ss,
+                             bool* scattered) {
+    const bool wall = ss.loop != 0;
+    const R mutot = wall ? S.mutot_b : S.mutot_c, inv_mutot = wall ? S.inv_mutot_b : S.inv_mutot_c;
+    const R albedo = wall ? S.albedo_b : S.albedo_c, hgg = wall ? R(0.9) : R(0.65);
+    const R Rlim = wall ? S.b_out_r : S.b_in_r, Rlim2 = wall ? S.b_out_r2 : S.b_in_r2;
+    *scattered = false;
+    ort_advance(r, ss.t);
+    if (!(ort_scatter_draw(g, ss.sr) < albedo)) return wall ? ORT_ST_WALL_ABSORBED : ORT_ST_CONTENTS_ABSORBED;
+    ort_stokes(r, hgg, g, ss.sr);
+    *scattered = true;
+    bool flag;
+    if (!ort_tauint(r, mutot, inv_mutot, S.bcy, S.bcz, Rlim2, ort_scatter_draw(g, ss.sr), &ss.t, &flag))
+        return ORT_ST_TAUINT_MISS;
+    /* the reference's exit test uses (x,z) although the axis is x */
+    if (sqrt(fma(r.px, r.px, r.pz * r.pz)) >= Rlim) return 0;
+    return flag ? 0 : ORT_BOTTLE_EVENT;
+}
+
+/* glass_bottle%forward for one ray from start to end.  SCATTER: the two functions above driven per ray
+ * (explicit-ray entry point, diagnostic flat kernel, host harness; the production kernel for scattering
+ * bottles, ort_trace_scatter_kernel, queues the rays between events instead).  *nevents counts the
+ * scatter events (stokes calls) of this ray. */
+template <bool SCATTER, typename R>
+ORT_HD int ort_bottle_forward(const DevSceneT<R>& S, const OrtRng& g, const OrtDraws01& D, OrtRayT<R>& r, int* nevents = nullptr) {
+    if (!SCATTER) return ort_bottle_clear(S, g, D, r);
+    OrtScatterStateT<R> ss;
+    int st = ort_bottle_resume(S, g, D, r, ss, 0);
+    while (st == ORT_BOTTLE_EVENT) {
+        bool scattered;
+        st = ort_scatter_event(S, g, r, ss, &scattered);
+        if (scattered && nevents) ++*nevents;
+        if (st == 0) st = ort_bottle_resume(S, g, D, r, ss, ss.loop + 1);
+    }
+    return st;
 }
 
 /* -------------------------------------------------------------------------------------------
