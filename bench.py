@@ -249,7 +249,7 @@ class Rendezvous:
             f.write(data)
         os.rename(tmp, os.path.join(self.dir, name))
 
-    def _get(self, name, timeout=300.0):
+    def _get(self, name, timeout=120.0):
         path, t0 = os.path.join(self.dir, name), time.time()
         while not os.path.exists(path):
             if time.time() - t0 > timeout:
@@ -279,9 +279,15 @@ class Rendezvous:
         return self._get("b%d" % self.seq)
 
     def close(self):
+        """last barrier, then rank 0 removes the directory -- only after every other rank has said that it
+        is done reading"""
         if self.dir:
             self.barrier()
-            if self.rank == 0:
+            if self.rank != 0:
+                self._put("bye.%d" % self.rank, b"")
+            else:
+                for r in range(1, self.world):
+                    self._get("bye.%d" % r, timeout=60.0)
                 shutil.rmtree(self.dir, ignore_errors=True)
 
 
@@ -394,14 +400,23 @@ class Bench:
         self.rdv = Rendezvous(rank, world)
         if lib.device_count() <= 0:
             raise SystemExit("bench.py: no CUDA device -- the trace loop has no CPU fallback")
-        if args.single_process:
-            self.ngpus = lib.init(args.gpus)
-        else:
-            nccl_id = None
-            if world > 1:
-                nccl_id = self.rdv.bcast(lib.nccl_unique_id() if rank == 0 else b"")
-            lib.init_rank(local, rank, world, nccl_id)
-            self.ngpus = world
+        # stdout carries exactly one JSON line: NCCL's banner ("NCCL version ...", printed to stdout when the
+        # environment sets NCCL_DEBUG) goes to stderr with everything else a library may say while it starts
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            if args.single_process:
+                self.ngpus = lib.init(args.gpus)
+            else:
+                nccl_id = None
+                if world > 1:
+                    nccl_id = self.rdv.bcast(lib.nccl_unique_id() if rank == 0 else b"")
+                lib.init_rank(local, rank, world, nccl_id)
+                self.ngpus = world
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
         self.local = local
 
     def sync(self):

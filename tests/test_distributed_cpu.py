@@ -74,3 +74,29 @@ def test_partition_properties():
             assert parts[-1][0] + parts[-1][1] == 5 + n
             sizes = [p[1] for p in parts]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _rdv_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["TORCHELASTIC_RUN_ID"] = "pytest"
+    import bench
+    r = bench.Rendezvous(rank, world)
+    got = r.bcast(b"nccl-unique-id-stand-in" if rank == 0 else b"")
+    rows = [r.allgather([rank, k, 0.5 * rank]) for k in range(40)]
+    r.barrier()
+    r.close()
+    ok = got == b"nccl-unique-id-stand-in" and all(row == [[i, k, 0.5 * i] for i in range(world)] for k, row in enumerate(rows))
+    open(os.path.join(out_dir, "rdv.%d" % rank), "w").write("ok" if ok else "bad")
+
+
+def test_bench_rendezvous_without_torch_distributed(tmp_path):
+    """bench.py's ranks find each other through files (no torch.distributed): broadcast of the NCCL id,
+    all-gather of the timings, barrier, and a teardown in which rank 0 removes the directory only after
+    every rank has finished reading (the race that hung a 2-GPU run once)."""
+    world = 3
+    mp.spawn(_rdv_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert [open(tmp_path / ("rdv.%d" % r)).read() for r in range(world)] == ["ok"] * world
+    import glob
+    import tempfile
+    assert not glob.glob(os.path.join(tempfile.gettempdir(), "ort_bench_*_pytest_%d" % os.getpid()))
