@@ -464,21 +464,11 @@ static bool ring_filter_applies(const ort_job& job, const DevScene& s, bool flat
  * is < 1 % of it, short enough that the list of ray indices stays a few hundred MB. */
 static const int64_t ORT_RING_SLICE = (int64_t)1 << 29;
 
-static int enqueue_ring_filter(DeviceCtx& c, Lane& L, const ort_job& job, const DevScene& s, const DevFilter& K,
-                               unsigned long long aim_cut, int nscenes, int64_t first, int64_t n, unsigned long long* d_img,
-                               unsigned long long* d_cnt, int64_t* launches) {
-    const bool verify = (job.flags & ORT_FLAG_VERIFY_FILTER) != 0;
-    auto cull = verify ? ort_ring_cull_kernel<true> : ort_ring_cull_kernel<false>;
-    auto surv = verify ? ort_ring_survivors_kernel<true> : ort_ring_survivors_kernel<false>;
-    const size_t smem_cull = (size_t)ORT_WPB * sizeof(SlimQueue);
-    const size_t smem_surv = (size_t)ORT_WPB * sizeof(SurvShared);
-    int occ_cull = 0, occ_surv = 0;
-    int orc = ctx_occupancy(c, (const void*)cull, smem_cull, &occ_cull);
-    if (orc == ORT_OK) orc = ctx_occupancy(c, (const void*)surv, smem_surv, &occ_surv);
-    if (orc != ORT_OK) return orc;
-
-    /* the list holds at most the rays that pass stage A: Binomial(slice, p), p = aim_cut / 2^64,
-     * standard deviation <= sqrt(slice) / 2.  Capacity = expectation + 8 sqrt(slice) >= 16 sigma. */
+/* The survivors list of one lane: at most the rays that pass stage A land on it -- Binomial(slice, p),
+ * p = aim_cut / 2^64, standard deviation <= sqrt(slice) / 2; capacity = expectation + 8 sqrt(slice) >= 16
+ * sigma -- two buffers used alternately, plus one length per slice.  Grow-only; called for every scene
+ * BEFORE the timed region starts, so that a first call does not time its own cudaMalloc. */
+static int ring_reserve(Lane& L, unsigned long long aim_cut, int64_t n, size_t* capacity_out, int64_t* nslices_out) {
     const int64_t slice = n < ORT_RING_SLICE ? n : ORT_RING_SLICE;
     const double p_pass = (double)aim_cut * (1.0 / 18446744073709551616.0);
     double want_cap = (double)slice * p_pass + 8.0 * std::sqrt((double)slice) + 1024.0;
@@ -506,6 +496,29 @@ static int enqueue_ring_filter(DeviceCtx& c, Lane& L, const ort_job& job, const 
         CK(cudaMalloc(&L.d_nlist, (size_t)nslices * sizeof(unsigned)));
         L.nlist_cap = (size_t)nslices;
     }
+    *capacity_out = capacity;
+    *nslices_out = nslices;
+    return ORT_OK;
+}
+
+static int enqueue_ring_filter(DeviceCtx& c, Lane& L, const ort_job& job, const DevScene& s, const DevFilter& K,
+                               unsigned long long aim_cut, int nscenes, int64_t first, int64_t n, unsigned long long* d_img,
+                               unsigned long long* d_cnt, int64_t* launches) {
+    const bool verify = (job.flags & ORT_FLAG_VERIFY_FILTER) != 0;
+    auto cull = verify ? ort_ring_cull_kernel<true> : ort_ring_cull_kernel<false>;
+    auto surv = verify ? ort_ring_survivors_kernel<true> : ort_ring_survivors_kernel<false>;
+    const size_t smem_cull = (size_t)ORT_WPB * sizeof(SlimQueue);
+    const size_t smem_surv = (size_t)ORT_WPB * sizeof(SurvShared);
+    int occ_cull = 0, occ_surv = 0;
+    int orc = ctx_occupancy(c, (const void*)cull, smem_cull, &occ_cull);
+    if (orc == ORT_OK) orc = ctx_occupancy(c, (const void*)surv, smem_surv, &occ_surv);
+    if (orc != ORT_OK) return orc;
+
+    size_t capacity = 0;
+    int64_t nslices = 0;
+    const double p_pass = (double)aim_cut * (1.0 / 18446744073709551616.0);
+    int rrc = ring_reserve(L, aim_cut, n, &capacity, &nslices);
+    if (rrc != ORT_OK) return rrc;
     /* the previous scene of this lane may still be reading its lists and lengths on stream2 */
     CK(cudaStreamWaitEvent(L.stream, L.ev_surv[0], 0));
     CK(cudaStreamWaitEvent(L.stream, L.ev_surv[1], 0));
@@ -564,6 +577,19 @@ static int enqueue_trace_t(DeviceCtx& c, const ort_job& job, const std::vector<D
     bool flat = (job.flags & ORT_FLAG_NO_COMPACTION) != 0 && job.source_kind == ORT_SRC_POINT;
     const size_t smem_trace = flat ? 0 : (size_t)ORT_WPB * sizeof(WarpShared<R>);
 
+    const int nlanes = (nscenes > 1 && n <= ((int64_t)1 << 26) && !(job.flags & ORT_FLAG_ONE_LANE))
+                           ? (nscenes < ORT_LANES ? nscenes : ORT_LANES) : 1;
+    for (int sc = 0; sc < nscenes; ++sc) { /* device memory first: the timed region below allocates nothing */
+        unsigned long long aim_cut = 0;
+        DevFilter K;
+        if (ring_filter_applies<R>(job, ds[sc], flat, &aim_cut, &K)) {
+            size_t cap = 0;
+            int64_t nsl = 0;
+            int rrc = ring_reserve(c.lanes[sc % nlanes], aim_cut, n, &cap, &nsl);
+            if (rrc != ORT_OK) return rrc;
+        }
+    }
+
     CK(cudaEventRecord(c.ev_start, c.stream));
     CK(cudaMemsetAsync(c.d_buf, 0, elems * sizeof(unsigned long long), c.stream));
     unsigned long long* d_img = c.d_buf;
@@ -575,8 +601,6 @@ static int enqueue_trace_t(DeviceCtx& c, const ort_job& job, const std::vector<D
      * stream.  When a batched call has few rays per scene -- a quick-look sweep -- the scenes go round
      * robin over ORT_LANES streams instead: the tail of one scene's persistent kernel is filled by the
      * blocks of the next, and the launch latencies overlap. */
-    const int nlanes = (nscenes > 1 && n <= ((int64_t)1 << 26) && !(job.flags & ORT_FLAG_ONE_LANE))
-                           ? (nscenes < ORT_LANES ? nscenes : ORT_LANES) : 1;
     if (nlanes > 1) {
         CK(cudaEventRecord(c.ev_zeroed, c.stream));
         for (int l = 1; l < nlanes; ++l) CK(cudaStreamWaitEvent(c.lanes[l].stream, c.ev_zeroed, 0));

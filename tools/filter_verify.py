@@ -60,7 +60,7 @@ def cpu(nrays):
     print("TOTAL", tot)
 
 
-def gpu(nrays, first_ray=0, only=None):
+def gpu(nrays, first_ray=0, only=None, shipped_factor=1):
     from opticalraytrace_b200 import lib
     lib.init(1)
     try:
@@ -72,12 +72,13 @@ def gpu(nrays, first_ray=0, only=None):
         for name, sc, kw in setups():
             if only and not name.startswith(only):
                 continue
-            job = abi.default_job(1, nrays, first_ray=first_ray, flags=kw.pop("flags", 0) | abi.FLAG_VERIFY_FILTER, **kw)
+            n = nrays * (shipped_factor if name.startswith("shipped") else 1)
+            job = abi.default_job(1, n, first_ray=first_ray, flags=kw.pop("flags", 0) | abi.FLAG_VERIFY_FILTER, **kw)
             _, _, hist, tm = lib.trace(job, sc, want_image=False, allow_trap=True)
             c, w = int(hist[0, abi.FILTER_SLOT_CALLED]), int(hist[0, abi.FILTER_SLOT_WRONG])
             called += c
             wrong += w
-            print("%-40s %.3g rays: filter called %d, wrong %d  (%.1f s)" % (name, nrays, c, w, tm.trace_seconds))
+            print("%-40s %.3g rays: filter called %d, wrong %d  (%.1f s)" % (name, n, c, w, tm.trace_seconds), flush=True)
         print("TOTAL verdicts %d wrong %d" % (called, wrong))
     finally:
         lib.finalize()
@@ -89,5 +90,6 @@ if __name__ == "__main__":
     ap.add_argument("--gpu", type=int, default=0, metavar="RAYS")
     ap.add_argument("--first-ray", type=int, default=0, help="start of the ray-index range (GPU part)")
     ap.add_argument("--only", default=None, help="only the set-ups whose name starts with this (GPU part)")
+    ap.add_argument("--shipped-factor", type=int, default=1, help="the shipped set-ups get this many times RAYS (GPU part)")
     a = ap.parse_args()
-    gpu(a.gpu, a.first_ray, a.only) if a.gpu else cpu(a.rays)
+    gpu(a.gpu, a.first_ray, a.only, a.shipped_factor) if a.gpu else cpu(a.rays)
