@@ -201,9 +201,12 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([time.perf_counter()] + [c.strip() for c in line.split(",")])
 
-    def stop(self):
+    def stop(self, window=None):
+        """`window` = (t0, t1) of the timed region (perf_counter): only the samples taken inside it count
+        (the sampler is started before the warm-up steps, because nvidia-smi needs ~0.3 s to deliver its
+        first line and a timed region of K = 5 steps is only half a second long)"""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -213,7 +216,8 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = [r[1:] for r in self.rows if window is None or window[0] <= r[0] <= window[1] + 0.1]
+        for r in rows:
             if len(r) < 8:
                 continue
             try:
@@ -456,10 +460,10 @@ class Bench:
             job.flags |= flags
             return lib.trace(job, scenes, want_image=True)
 
-        for k in range(warmup):
-            step(k)
         if sampler:
             sampler.start()
+        for k in range(warmup):
+            step(k)
         self.sync()
         t0 = time.perf_counter()
         dev_s = red_s = d2h_s = 0.0
@@ -475,7 +479,7 @@ class Bench:
             hist += h.sum(axis=0)
         self.sync()
         wall_s = time.perf_counter() - t0
-        clocks = sampler.stop() if sampler else None
+        clocks = sampler.stop((t0, t0 + wall_s)) if sampler else None
         every = self.rdv.allgather([dev_s, wall_s, red_s, int(launches), int(mine)])
         if self.rank != 0:
             return None

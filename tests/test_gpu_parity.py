@@ -308,3 +308,22 @@ def test_more_rays_than_one_launch_holds(ort, orc):
     a = orc.trace_rays(abi.default_job(1, first_ray=first + (1 << 32) - 1000), scene, 1005)
     b = ort.trace_rays(abi.default_job(1, first_ray=first + (1 << 32) - 1000), scene, 1005)
     assert np.array_equal(a["status"], b["status"]) and np.array_equal(a["bin"], b["bin"])
+
+
+def test_small_batched_call_is_the_same_on_one_stream_and_on_several(ort, orc):
+    """A batched call with few rays per scene spreads its scenes over several streams (DESIGN.md 3.6);
+    ORT_FLAG_ONE_LANE runs them back to back.  Same images, histograms and loss counters either way,
+    equal to one call per scene, for both loops and for a mix of clear, elliptic and scattering bottles
+    (the kernel is chosen per scene)."""
+    mix = [cases.C1, cases.C2, cases.ELL, cases.OTHER, cases.SCATTER_CASES[0][1], cases.C2, cases.OTHER2]
+    n = 300_007
+    for phase in (1, 2):
+        scenes = [cases.scene_for(orc, f, phase) for f in mix]
+        img, lost, hist, tm = ort.trace(abi.default_job(phase, n), scenes, allow_trap=True)
+        img1, lost1, hist1, _ = ort.trace(abi.default_job(phase, n, flags=abi.FLAG_ONE_LANE), scenes, allow_trap=True)
+        assert np.array_equal(img, img1) and np.array_equal(hist, hist1) and np.array_equal(lost, lost1)
+        for k, sc in enumerate(scenes):
+            i0, l0, h0, _ = ort.trace(abi.default_job(phase, n), sc, allow_trap=True)
+            assert np.array_equal(i0[0], img[k]) and np.array_equal(h0[0], hist[k]) and l0[0] == lost[k], (phase, k)
+        oimg, olost, ohist = orc.trace(abi.default_job(phase, n), scenes)
+        assert np.array_equal(oimg, img) and np.array_equal(ohist, hist)
