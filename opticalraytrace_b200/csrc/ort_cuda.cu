@@ -536,7 +536,8 @@ static int enqueue_ring_filter(DeviceCtx& c, Lane& L, const ort_job& job, const 
         uint32_t* list = L.d_list + (size_t)buf * L.list_cap;
         DevJob dj;
         ort_make_dev_job(job, nscenes, first + off, m, dj);
-        int64_t batches = (m + 31) / 32;
+        dj.aim_cut = aim_cut;
+        int64_t batches = (m + 127) / 128; /* a warp of the cull kernel takes 128 rays per pass */
         int64_t want = (batches + ORT_WPB - 1) / ORT_WPB;
         int grid = c.num_sms * occ_cull;
         int gsz = (int)(want < grid ? (want > 0 ? want : 1) : grid);
@@ -622,6 +623,8 @@ static int enqueue_trace_t(DeviceCtx& c, const ort_job& job, const std::vector<D
          * depend on what it is batched with */
         const int bottle_mode = (job.phase == ORT_PHASE_POINT && job.use_bottle)
                                     ? ((ds[sc].scatter_b || ds[sc].scatter_c) ? 2 : 1) : 0;
+        unsigned long long ring_cut = 0; /* the ring loop's stage A decides on the high word of the aim draw */
+        if (job.phase == ORT_PHASE_RING && ds[sc].ring_shortcut && !ort_ring_aim_cut(ds[sc], &ring_cut, sizeof(R) == 4)) ring_cut = 0;
         const bool scatter_kernel = bottle_mode == 2 && !flat;
         typename Kernels<R>::trace_t k = scatter_kernel ? Kernels<R>::pick_scatter(job.source_kind)
                                                         : Kernels<R>::pick(job.phase, bottle_mode, job.source_kind, flat);
@@ -635,6 +638,7 @@ static int enqueue_trace_t(DeviceCtx& c, const ort_job& job, const std::vector<D
             DevJob dj;
             ort_make_dev_job(job, nscenes, first + off, m, dj);
             dj.image_cdf = c.d_image_cdf;
+            dj.aim_cut = ring_cut;
             int64_t batches = (m + 31) / 32;
             int64_t want = (batches + ORT_WPB - 1) / ORT_WPB;
             int gsz = (int)(want < grid ? (want > 0 ? want : 1) : grid);

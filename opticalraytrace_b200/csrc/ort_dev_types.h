@@ -133,6 +133,8 @@ struct DevJob {
     int64_t total_rays;  /* nphotons of the whole job (create_spot) */
     uint32_t round_keys[20];    /* Philox key schedule seed + r * (W0, W1), r = 0..9: launch constants,
                                    so the rounds read them straight from the constant bank */
+    uint64_t aim_cut;           /* ring loop: the smallest 64-bit slot-2 draw that fails L2's aperture test
+                                   (ort_ring_aim_cut), or 0 when the test is not a test on that draw */
     const long long* image_cdf; /* image source: inclusive prefix sums of the 512x512 ray budget in
                                    emit_image's scan order (device memory), or NULL */
 };

@@ -297,13 +297,14 @@ ORT_HD bool ortf_outside(float x, float y, float r2, float inv_r, float rr, floa
     return rho2 > r2;
 }
 
-/* (h2, w_aim, w_curved): words 1, 2, 3 of the ray's block 1, which the caller already holds -- the
- * high word of the aim-disc r^2 draw, the aim angle, L2's curved-face decision; block 0 (annulus
- * r^2, annulus angle, L2's flat-face decision) is generated here */
+/* h2: the high word of the aim-disc r^2 draw, which stage A has tested; the ray's blocks 0 (annulus r^2,
+ * annulus angle, L2's flat-face decision) and 1 (aim angle, L2's curved-face decision) are generated here */
 ORT_HD int ort_ring_filter(const DevSceneT<float>& F, const DevFilter& K, const DevJob& J, const OrtRng& g, uint32_t h2,
-                           uint32_t w_aim, uint32_t w_curved, OrtFilterTrace* tr = nullptr) {
-    uint32_t w[4];
+                           OrtFilterTrace* tr = nullptr) {
+    uint32_t w[4], v[4];
     ort_block(g, 0u, w);
+    ort_block(g, 1u, v);
+    const uint32_t w_aim = v[2], w_curved = v[3];
     const float u0 = ortf_uniform(w[1]), u1 = ortf_uniform(w[2]);
     const float u2 = ortf_uniform(h2), u3 = ortf_uniform(w_aim);
     /* ring source, ort_source_ring_u.  Its position error is a scene constant (inside K.ed_a) */

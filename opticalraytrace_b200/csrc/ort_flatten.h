@@ -115,8 +115,12 @@ inline void ort_flatten_scene(const ort_scene& s, const ort_job& j, DevScene& d)
  * u2 * lens_r2 > l2_radius2 (ort_ring_aims_outside_aperture).  The expression is monotone in w,
  * so a bisection finds it.  Returns false when no draw fails (then the caller does not use the
  * integer test). */
-inline bool ort_ring_aim_cut(const DevScene& d, unsigned long long* cut) {
+inline bool ort_ring_aim_cut(const DevScene& d, unsigned long long* cut, bool fp32 = false) {
     auto outside = [&](unsigned long long bits) {
+        if (fp32) { /* the fp32 variant's own expression (ort_bits_to_uniform<float>, float scene): also monotone */
+            float u2 = fminf((float)bits * (1.0f / 9007199254740992.0f), 0.99999994f);
+            return u2 * (float)d.lens_r2 > (float)d.l2_radius2;
+        }
         double u2 = (double)bits * (1.0 / 9007199254740992.0);
         return u2 * d.lens_r2 > d.l2_radius2;
     };

@@ -234,18 +234,20 @@ template <int PHASE, int BOTTLE, int SRC, typename R>
 __device__ __forceinline__ int ort_stage_a(const DevSceneT<R>& S, const DevJob& J, const OrtRng& g, uint32_t id,
                                            OrtRayT<R>& r, uint32_t& wf, uint32_t& wc, int* nevents = nullptr) {
     if (PHASE == ORT_PHASE_RING && SRC == ORT_SRC_POINT && S.ring_shortcut) {
-        uint32_t b[4];
-        ort_block(g, 1u, b);
-        const R u2 = ort_bits_to_uniform<R>(b[0], b[1]);
-        r.px = u2;
-        r.py = ort_word_to_uniform<R>(b[2]);
-        r.pz = r.dx = r.dy = r.dz = R(0.0);
+        /* only the high word of the aim-disc r^2 draw: it decides L2's aperture unless it EQUALS the cut's
+         * (2^-32 of the rays), and the survivor carries nothing else -- stage B regenerates its blocks */
+        const uint32_t hi = ort_aim_hi(g);
+        r.px = r.py = r.pz = r.dx = r.dy = r.dz = R(0.0);
         wf = 0u;
-        wc = b[3];
-        return ort_ring_aims_outside_aperture(S, u2) ? ORT_ST_L2_APERTURE : 0;
+        wc = hi;
+        const uint32_t cut_hi = (uint32_t)(J.aim_cut >> 32);
+        if (J.aim_cut != 0ull && hi != cut_hi) return hi > cut_hi ? ORT_ST_L2_APERTURE : 0;
+        uint32_t b[4]; /* on the edge: the expression itself */
+        ort_block(g, 1u, b);
+        return ort_ring_aims_outside_aperture(S, ort_bits_to_uniform<R>(b[0], hi)) ? ORT_ST_L2_APERTURE : 0;
     }
     OrtDraws01 D;
-    ort_draws01(g, D);
+    ort_draws01<PHASE>(g, D);
     wf = D.a[3];
     wc = D.b[3];
     int es = ort_emit<PHASE, SRC>(S, J, g, D, J.first_ray + (long long)id, r);
@@ -265,10 +267,12 @@ template <int PHASE, int SRC, typename R>
 __device__ __forceinline__ int ort_stage_b(const DevSceneT<R>& S, const DevJob& J, const OrtRng& g, OrtRayT<R>& r,
                                            uint32_t wf, uint32_t wc) {
     if (PHASE == ORT_PHASE_RING && SRC == ORT_SRC_POINT && S.ring_shortcut) {
-        uint32_t a[4];
+        uint32_t a[4], b[4];
         ort_block(g, 0u, a);
-        R u2 = r.px, u3 = r.py;
+        ort_block(g, 1u, b);
+        const R u2 = ort_bits_to_uniform<R>(b[0], wc), u3 = ort_word_to_uniform<R>(b[2]); /* wc: the high word stage A tested */
         wf = a[3];
+        wc = b[3];
         ort_source_ring_u(S, ort_bits_to_uniform<R>(a[0], a[1]), ort_word_to_uniform<R>(a[2]), u2, u3, r);
         int st0 = ort_l2_enter(S, r); /* same arithmetic as the general path; cannot fail except
                                          within rounding of the aperture edge */
@@ -516,7 +520,7 @@ ort_trace_scatter_kernel(const __grid_constant__ DevSceneT<R> S, const __grid_co
                 }
                 if (st == 0) {
                     OrtDraws01 D;
-                    ort_draws01(g, D);
+                    ort_draws01<ORT_PHASE_POINT>(g, D);
                     wf = D.a[3];
                     wc = D.b[3];
                     if (stage == 0) st = ort_emit<ORT_PHASE_POINT, SRC>(S, J, g, D, J.first_ray + (long long)id, r);
@@ -573,17 +577,13 @@ ort_trace_scatter_kernel(const __grid_constant__ DevSceneT<R> S, const __grid_co
  * and the survivors kernel compares the filter's verdict with what fp64 finds:
  * counters[ORT_FILTER_SLOT_CALLED] = rays the filter called, counters[ORT_FILTER_SLOT_WRONG] =
  * calls that disagree with fp64 (must stay 0). */
-#ifndef ORT_CULL_UNROLL
-#define ORT_CULL_UNROLL 2 /* batches of 32 rays per stage-A pass */
-#endif
-#define ORT_CULL_QCAP (32 + 32 * ORT_CULL_UNROLL) /* < 32 leftovers + the survivors of one pass */
+#define ORT_CULL_QUAD 4 /* rays per lane and stage-A pass: the four that share one block (ort_shared_block) */
+#define ORT_CULL_QCAP (32 + 32 * ORT_CULL_QUAD) /* < 32 leftovers + the survivors of one pass */
 struct SlimQueue {
-    uint4 e[ORT_CULL_QCAP]; /* x: high word of the aim-disc r^2 draw, y: aim angle word, z: L2 curved-face
-                               decision word (words 1, 2, 3 of the ray's block 1 -- all the filter
-                               needs of it; fp64 regenerates the block), w: ray index */
+    uint2 e[ORT_CULL_QCAP]; /* x: high word of the aim-disc r^2 draw (what stage A tested), y: ray index */
     uint32_t hb[64];        /* ray indices on their way to the survivors list */
 };
-__device__ __forceinline__ bool ort_slim_pop(SlimQueue& q, int& n, uint4& e, unsigned lane) {
+__device__ __forceinline__ bool ort_slim_pop(SlimQueue& q, int& n, uint2& e, unsigned lane) {
     int cnt = n < 32 ? n : 32;
     int base = n - cnt;
     bool act = (int)lane < cnt;
@@ -632,59 +632,66 @@ ort_ring_cull_kernel(const __grid_constant__ DevSceneT<float> F, const __grid_co
     const uint32_t nwarps = gridDim.x * ORT_WPB;
     const uint32_t gwarp = blockIdx.x * ORT_WPB + (threadIdx.x >> 5);
     const uint32_t nrays = (uint32_t)J.nrays;
-    const uint32_t nbatches = (nrays + 31u) >> 5;
+    /* Stage A works on QUADS: the four rays 4q .. 4q+3 (global ray index) share the block that holds the
+     * high words of their aim-disc draws, so one lane decides four rays with one Philox block.  Local ray
+     * ids are offsets from J.first_ray; `mis` is how far that is from a multiple of four. */
+    const uint32_t mis = (uint32_t)(J.first_ray & 3);
+    const uint32_t nquads = (nrays + mis + 3u) >> 2;
+    const uint32_t npasses = (nquads + 31u) >> 5; /* 32 quads = 128 rays per warp and pass */
 
     const uint32_t cut_hi = (uint32_t)(aim_cut >> 32);
-    unsigned c10 = 0, c11 = 0, c12 = 0, c13 = 0, c14 = 0;
-    unsigned npassed = 0; /* warp-uniform: rays of this warp that passed stage A */
+    unsigned c9 = 0, c10 = 0, c11 = 0, c12 = 0, c13 = 0, c14 = 0;
     int nh = 0;           /* entries parked in q0.hb */
     unsigned below;       /* lanes below this one */
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(below));
     int n0 = 0;
     uint32_t b = gwarp;
     for (;;) {
-        const bool emit = n0 < 32 && b < nbatches;
+        const bool emit = n0 < 32 && b < npasses;
         if (!emit && n0 == 0) break;
         if (emit) {
-            /* ORT_CULL_UNROLL batches per pass: that many pairs of independent Philox multiply
-             * chains in flight, and the loop / queue bookkeeping is paid once per pass.  Lanes
-             * past the end of the slice compute a draw nobody uses. */
-            uint4 ent[ORT_CULL_UNROLL];
-            bool pass[ORT_CULL_UNROLL];
+            const uint32_t quad = b * 32u + lane;
+            /* a pass at either end of the slice can hold ids outside it: counted exactly there, 128 elsewhere */
+            const bool edge = (b == 0u && mis != 0u) || (b * 32u + 32u >= nquads);
+            b += nwarps;
+            OrtRng g = ort_make_rng_prod(J, 0u); /* any ray of the quad names the shared block */
+            {
+                const unsigned long long ray = ((unsigned long long)J.first_ray & ~3ull) + 4ull * quad;
+                g.r0 = (uint32_t)ray;
+                g.r1 = (uint32_t)(ray >> 32);
+            }
+            uint32_t w[4];
+            ort_shared_block(g, w);
+            const int before = n0;
+            unsigned nvalid = 128u;
+            if (edge) nvalid = 0u;
 #pragma unroll
-            for (int k = 0; k < ORT_CULL_UNROLL; ++k) {
-                const uint32_t id = (b + (uint32_t)k * nwarps) * 32u + lane;
-                OrtRng g = ort_make_rng_prod(J, id);
-                uint32_t w[4];
-                ort_block(g, 1u, w); /* w[0], the low word of the r^2 draw, is never formed */
-                ent[k] = make_uint4(w[1], w[2], w[3], id);
+            for (int k = 0; k < ORT_CULL_QUAD; ++k) {
+                const uint32_t id = quad * 4u + (uint32_t)k - mis; /* wraps above nrays when it is before the slice */
+                const bool valid = id < nrays;
                 /* decided on the high word alone; a draw whose high word EQUALS the cut's (2^-32 of
                  * the rays) goes on: it sits on the aperture edge, where the filter hands it to
                  * fp64, and ort_l2_enter there makes the exact call */
-                pass[k] = id < nrays && w[1] <= cut_hi;
-            }
-            b += (uint32_t)ORT_CULL_UNROLL * nwarps;
-            const int before = n0;
-#pragma unroll
-            for (int k = 0; k < ORT_CULL_UNROLL; ++k) {
-                const unsigned m = __ballot_sync(ORT_FULL, pass[k]);
-                if (pass[k]) {
+                const bool pass = valid && w[k] <= cut_hi;
+                const unsigned m = __ballot_sync(ORT_FULL, pass);
+                if (edge) nvalid += __popc(__ballot_sync(ORT_FULL, valid));
+                if (pass) {
                     int p = n0 + __popc(m & below);
                     ORT_ASSERT(p >= 0 && p < ORT_CULL_QCAP);
-                    q0.e[p] = ent[k];
+                    q0.e[p] = make_uint2(w[k], id);
                 }
                 n0 += __popc(m);
             }
-            npassed += (unsigned)(n0 - before);
+            c9 += nvalid - (unsigned)(n0 - before); /* warp-uniform: rays that ended in stage A */
             __syncwarp();
         } else {
-            uint4 e = make_uint4(0u, 0u, 0u, 0u);
+            uint2 e = make_uint2(0u, 0u);
             bool act = ort_slim_pop(q0, n0, e, lane);
-            const uint32_t id = e.w;
+            const uint32_t id = e.y;
             int st = -1;
             if (act) {
                 OrtRng g = ort_make_rng_prod(J, id);
-                st = VERIFY ? 0 : ort_ring_filter(F, K, J, g, e.x, e.y, e.z);
+                st = VERIFY ? 0 : ort_ring_filter(F, K, J, g, e.x);
                 /* one compare + one predicated add per status (left to itself the compiler builds
                  * add / conditional move / move triples here) */
                 ort_tally<ORT_ST_L2_SPHERE_MISS>(c10, st);
@@ -711,16 +718,6 @@ ort_ring_cull_kernel(const __grid_constant__ DevSceneT<float> F, const __grid_co
         }
     }
     if (nh > 0) ort_list_append(list, nlist, capacity, counters, (int)lane < nh ? q0.hb[lane] : 0u, (unsigned)nh, lane);
-    /* rays that ended in stage A = rays this warp drew - rays that passed.  The warp drew the
-     * batches gwarp, gwarp + nwarps, ... below nbatches; only the last batch of the slice can be
-     * ragged */
-    unsigned c9 = 0;
-    if (gwarp < nbatches) {
-        const uint32_t mine_batches = (nbatches - 1u - gwarp) / nwarps + 1u;
-        unsigned drew = mine_batches * 32u;
-        if ((nbatches - 1u - gwarp) % nwarps == 0u) drew -= nbatches * 32u - nrays; /* owns the last batch */
-        c9 = drew - npassed;
-    }
     /* per-lane tallies -> one atomic per status and warp */
     c10 = __reduce_add_sync(ORT_FULL, c10);
     c11 = __reduce_add_sync(ORT_FULL, c11);
@@ -766,14 +763,11 @@ ort_ring_survivors_kernel(const __grid_constant__ DevSceneT<double> S, const __g
             if (i < total) {
                 id = list[i];
                 OrtRng g = ort_make_rng_prod(J, id);
-                uint32_t w[4];
-                ort_block(g, 1u, w);
-                r.px = ort_bits_to_uniform<double>(w[0], w[1]);
-                r.py = ort_word_to_uniform<double>(w[2]);
-                /* exactly the words the cull kernel hands the filter */
-                if (VERIFY) verdict = ort_ring_filter(F, K, J, g, w[1], w[2], w[3]);
-                r.pz = r.dx = r.dy = r.dz = 0.0;
-                st = ort_stage_b<ORT_PHASE_RING, ORT_SRC_POINT>(S, J, g, r, 0u, w[3]);
+                const uint32_t hi = ort_aim_hi(g);
+                /* exactly the word the cull kernel hands the filter */
+                if (VERIFY) verdict = ort_ring_filter(F, K, J, g, hi);
+                r.px = r.py = r.pz = r.dx = r.dy = r.dz = 0.0;
+                st = ort_stage_b<ORT_PHASE_RING, ORT_SRC_POINT>(S, J, g, r, 0u, hi);
             }
             if (VERIFY) {
                 ort_tally_smem(ws.hist, ORT_FILTER_SLOT_CALLED, verdict > 0);

@@ -392,7 +392,7 @@ ORT_HD float ort_sub_rn(float a, float b) {
  *     slot : block.words      ring loop                  point loop
  *        0 : 0.w0w1 wide      annulus r^2                cos theta
  *        1 : 0.w2             annulus angle              phi
- *        2 : 1.w0w1 wide      aim-disc r^2               bottle inner wall decision
+ *        2 : 1.w0w1 wide      aim-disc r^2 (*)           bottle inner wall decision
  *        3 : 1.w2             aim-disc angle             bottle outer wall decision
  *        4 : 0.w3             L2 flat decision           L2 flat decision
  *        5 : 1.w3             L2 curved decision         L2 curved decision
@@ -400,6 +400,10 @@ ORT_HD float ort_sub_rn(float a, float b) {
  *       10 : 3.w0w1 wide, 11 : 3.w2, 12 : 3.w3          image source: aim r^2, aim angle
  *       13 : 4.w0w1 wide, 14 : 4.w2, 15 : 4.w3          spare
  *     16.. : block slot/2, both halves wide              scatter loops / rang, consumed in order
+ * (*) in the ring loop the HIGH word of slot 2 is not 1.w1 but word (ray & 3) of a block that four
+ *     consecutive rays share -- counter (ray >> 2, 0, 16 + phase, 0): that word alone decides L2's
+ *     aperture for 69 % of the ring rays, and this way one Philox block decides it for four of them
+ *     (words of one block are as independent as words of different blocks); the low word stays 1.w0.
  * A whole ray needs three blocks (rev 1: five blocks of ten rounds); the ring loop's culling kernel
  * needs block 1 for every ray and block 0 for the rays that pass L2's aperture.
  * ----------------------------------------------------------------------------------------- */
@@ -434,6 +438,21 @@ ORT_HD void ort_philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, u
 /* the four words of block `block` of this ray */
 ORT_HD void ort_block(const OrtRng& g, uint32_t block, uint32_t* w) {
     ort_philox4x32(g.r0, g.r1, g.phase, block, g.k0, g.k1, w, g.rk);
+}
+/* the block the four rays 4q .. 4q+3 share (ring loop: the high words of their slot-2 draws) */
+#define ORT_SHARED_PHASE 16u
+ORT_HD void ort_shared_block(const OrtRng& g, uint32_t* w) {
+    const uint32_t q0 = (g.r0 >> 2) | (g.r1 << 30), q1 = g.r1 >> 2;
+    ort_philox4x32(q0, q1, ORT_SHARED_PHASE + g.phase, 0u, g.k0, g.k1, w, g.rk);
+}
+ORT_HD uint32_t ort_pick_word(const uint32_t* w, uint32_t k) {
+    return k == 0u ? w[0] : k == 1u ? w[1] : k == 2u ? w[2] : w[3];
+}
+/* the high word of this ray's slot-2 draw in the ring loop */
+ORT_HD uint32_t ort_aim_hi(const OrtRng& g) {
+    uint32_t w[4];
+    ort_shared_block(g, w);
+    return ort_pick_word(w, g.r0 & 3u);
 }
 
 /* 64 random bits -> uniform in [0,1): 53 bits for double (like gfortran's random_number); the
@@ -490,6 +509,7 @@ ORT_HD R ort_slot(const OrtRng& g, uint32_t slot) {
     /* kind: 0 wide, 1 = w2, 2 = w3, 3..6 = w0..w3 of block 2 */
     const uint32_t blk = slot < 6u ? ((slot == 4u) ? 0u : (slot == 5u) ? 1u : (slot >> 1)) : slot < 10u ? 2u : slot < 13u ? 3u : 4u;
     ort_block(g, blk, w);
+    if (slot == 2u && g.phase == (uint32_t)ORT_PHASE_RING) return ort_bits_to_uniform<R>(w[0], ort_aim_hi(g));
     if (slot < 6u) return slot < 4u ? ((slot & 1u) ? ort_word_to_uniform<R>(w[2]) : ort_bits_to_uniform<R>(w[0], w[1]))
                                     : ort_word_to_uniform<R>(w[3]);
     if (slot < 10u) return ort_word_to_uniform<R>(w[slot - 6u]);
@@ -675,10 +695,16 @@ ORT_HD bool ort_interface(OrtRayT<R>& r, R nx, R ny, R nz, const DevIfaceT<R>& f
  * two L2 decisions (a[3], b[3]) travel with the ray to L2 */
 struct OrtDraws01 {
     uint32_t a[4], b[4];
+    uint32_t hi2; /* high word of slot 2: b[1], in the ring loop the word of the shared block */
 };
+/* PHASE: ORT_PHASE_RING / ORT_PHASE_POINT where the caller knows it at compile time (the kernels), 0 =
+ * look at g.phase */
+template <int PHASE = 0>
 ORT_HD void ort_draws01(const OrtRng& g, OrtDraws01& D) {
     ort_block(g, 0u, D.a);
     ort_block(g, 1u, D.b);
+    const bool ring = PHASE ? PHASE == ORT_PHASE_RING : g.phase == (uint32_t)ORT_PHASE_RING;
+    D.hi2 = ring ? ort_aim_hi(g) : D.b[1];
 }
 
 template <typename R>
@@ -725,7 +751,7 @@ ORT_HD void ort_source_ring_u(const DevSceneT<R>& S, R u0, R u1, R u2, R u3, Ort
 }
 template <typename R>
 ORT_HD void ort_source_ring(const DevSceneT<R>& S, const OrtRng& g, const OrtDraws01& D, OrtRayT<R>& r) {
-    ort_source_ring_u(S, ort_wide<R>(g, D.a[0], D.a[1]), ort_narrow<R>(g, D.a[2]), ort_wide<R>(g, D.b[0], D.b[1]),
+    ort_source_ring_u(S, ort_wide<R>(g, D.a[0], D.a[1]), ort_narrow<R>(g, D.a[2]), ort_wide<R>(g, D.b[0], D.hi2),
                       ort_narrow<R>(g, D.b[2]), r);
 }
 /* When L2's flat face lies in the aim plane (DevSceneT<R>.ring_shortcut) the ray meets that face AT
@@ -839,7 +865,7 @@ ORT_HD bool ort_source_isors(const DevSceneT<R>& S, const OrtRng& g, const OrtDr
     r.px = x; r.py = y; r.pz = R(2.0) * S.isors_h;
     r.dx = R(0.0); r.dy = R(0.0); r.dz = -R(1.0);
     const R u_r = ort_wide<R>(g, D.a[0], D.a[1]), u_th = ort_narrow<R>(g, D.a[2]); /* slots 0, 1 */
-    const R u_ax = ort_wide2<R>(g, D.b[0], D.b[1]);                                 /* slot 2, doubled */
+    const R u_ax = ort_wide2<R>(g, D.b[0], D.hi2);                                 /* slot 2, doubled */
     if (ort_hit_cone(r, S.isors_k, S.isors_h, &t)) {
         ort_advance(r, t);
         /* gradient of the cone, inverted (upper nappe), normalised */
@@ -1005,7 +1031,7 @@ ORT_HD void ort_stokes(OrtRayT<R>& r, R hgg, const OrtRng& g, OrtScatterRngT<R>&
 template <typename R>
 ORT_HD int ort_bottle_clear(const DevSceneT<R>& S, const OrtRng& g, const OrtDraws01& D, OrtRayT<R>& r) {
     R t;
-    const R u_in = ort_wide2<R>(g, D.b[0], D.b[1]), u_out = ort_narrow2<R>(g, D.b[2]); /* slots 2, 3, doubled */
+    const R u_in = ort_wide2<R>(g, D.b[0], D.hi2), u_out = ort_narrow2<R>(g, D.b[2]); /* slots 2, 3, doubled */
     bool hit = S.ellipse ? ort_hit_ellipse(r, S.bcy, S.bcz, S.b_in_ia2, S.b_in_ib2, &t)
                          : ort_hit_cylinder(r, S.bcy, S.bcz, S.b_in_r2, &t);
     if (!hit) return ORT_ST_BOTTLE_INNER_MISS;
@@ -1076,7 +1102,7 @@ ORT_HD int ort_bottle_resume(const DevSceneT<R>& S, const OrtRng& g, const OrtDr
             R ny = S.bcy - r.py, nz = S.bcz - r.pz;
             R inv = ort_rsqrt(fma(ny, ny, nz * nz));
             R nzu = ort_both_zero(ny, R(0.0)) ? copysign(R(1.0), nz) : nz * inv; /* on-axis ray: exactly +-1 */
-            if (ort_interface(r, R(0.0), ny * inv, nzu, S.b_in, ort_wide2<R>(g, D.b[0], D.b[1]))) /* slot 2 */
+            if (ort_interface(r, R(0.0), ny * inv, nzu, S.b_in, ort_wide2<R>(g, D.b[0], D.hi2))) /* slot 2 */
                 return ORT_ST_BOTTLE_INNER_REFLECT;
         }
         bool hit = S.ellipse ? ort_hit_ellipse(r, S.bcy, S.bcz, S.b_out_ia2, S.b_out_ib2, &ss.t)

@@ -68,6 +68,8 @@ const double TWOPI = 2.0 * 3.14159265358979323846;
  *    0: 0.w0w1 wide   1: 0.w2   2: 1.w0w1 wide   3: 1.w2   4: 0.w3   5: 1.w3
  *    6..9: 2.w0..w3   10: 3.w0w1 wide  11: 3.w2  12: 3.w3  13: 4.w0w1 wide  14: 4.w2  15: 4.w3
  *    16..: block slot/2, (w1:w0) for even and (w3:w2) for odd slots, both wide
+ * In the ring loop (phase 1) the HIGH word of slot 2 is word (ray & 3) of a block four consecutive rays
+ * share, counter (ray >> 2, 16 + phase, 0): that word decides L2's aperture for 69 % of the ring rays.
  * ------------------------------------------------------------------------------------- */
 const int PHILOX_ROUNDS = 7;
 /* rounds [first, first + n) of Philox4x32 (the key of round r is key + r * (W0, W1)) */
@@ -142,6 +144,16 @@ struct Draws {
             have_fixed |= 1u << b;
         }
         const uint32_t* f = fixed[b];
+        if (k == 2 && phase == ORT_PHASE_RING) {
+            /* ring loop: the high word of slot 2 is word (ray & 3) of the block rays 4q .. 4q+3 share,
+             * counter (ray >> 2, 16 + phase, 0) */
+            uint64_t q = ray >> 2;
+            uint32_t ctr[4] = {(uint32_t)q, (uint32_t)(q >> 32), 16u + phase, 0u};
+            uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+            uint32_t sh[4];
+            philox4x32_rounds(ctr, key, 0, PHILOX_ROUNDS, sh);
+            return wide(f[0], sh[ray & 3]);
+        }
         return word[k] < 0 ? wide(f[0], f[1]) : narrow(f[word[k]]);
     }
     double scatter() { return slot(scatter_next++); }
@@ -576,7 +588,7 @@ inline bool source_isors(vec& pos, vec& dir, const ort_bottle& B, const ort_plan
     double k = (radius / height) * (radius / height);
     double base_pos = (seperation + beam_width) / std::tan(alpha * (axicon_n - 1.));
     vec centre = {0., 0., 0.};
-    double posx, posy, t;
+    double posx = 0., posy = 0., t;
     rang(posx, posy, 0., beam_width, rng);
     pos = centre + vec{posx, posy, 2 * height};
     dir = {0., 0., -1.};

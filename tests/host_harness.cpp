@@ -114,8 +114,9 @@ extern "C" int hh_ring_filter(const ort_job* job, const ort_scene* scene, int64_
         OrtRng g = harness_rng(J, i);
         uint32_t w[4];
         ort_block(g, 1u, w);
-        const double u2 = ort_bits_to_uniform<double>(w[0], w[1]);
-        verdict[i] = ort_ring_aims_outside_aperture(S, u2) ? -1 : ort_ring_filter(F, K, J, g, w[1], w[2], w[3]);
+        const uint32_t hi = ort_aim_hi(g);
+        const double u2 = ort_bits_to_uniform<double>(w[0], hi);
+        verdict[i] = ort_ring_aims_outside_aperture(S, u2) ? -1 : ort_ring_filter(F, K, J, g, hi);
     }
     return (S.ring_shortcut && K.usable == 2) ? 1 : 0;
 }
@@ -172,12 +173,13 @@ static bool twin_interface(DRay& r, double nx, double ny, double nz, const DevIf
     trec(T, surf + ORTF_T_DIR, r.dx, r.dy, r.dz);
     return reflect;
 }
-static int twin_filter(const DevScene& S, const DevJob& J, const OrtRng& g, const uint32_t* b, TwinTrace& T) {
-    uint32_t a[4];
+static int twin_filter(const DevScene& S, const DevJob& J, const OrtRng& g, uint32_t hi, TwinTrace& T) {
+    uint32_t a[4], b[4];
     ort_block(g, 0u, a);
+    ort_block(g, 1u, b);
     const double PI2 = 6.283185307179586476925286766559;
     const double u0 = ort_bits_to_uniform<double>(a[0], a[1]), u1 = ort_word_to_uniform<double>(a[2]);
-    const double u2 = ort_bits_to_uniform<double>(b[0], b[1]), u3 = ort_word_to_uniform<double>(b[2]);
+    const double u2 = ort_bits_to_uniform<double>(b[0], hi), u3 = ort_word_to_uniform<double>(b[2]);
     double rr = std::sqrt(S.r1 + u0 * S.r2_m_r1);
     DRay r;
     double sx = rr * std::cos(PI2 * u1), sy = rr * std::sin(PI2 * u1);
@@ -245,13 +247,14 @@ extern "C" int hh_filter_bounds(const ort_job* job, const ort_scene* scene, int6
 #endif
             uint32_t w[4];
             ort_block(g, 1u, w);
-            if (ort_ring_aims_outside_aperture(S, ort_bits_to_uniform<double>(w[0], w[1]))) continue;
+            const uint32_t hi = ort_aim_hi(g);
+            if (ort_ring_aims_outside_aperture(S, ort_bits_to_uniform<double>(w[0], hi))) continue;
             ++lpass;
             OrtFilterTrace tr;
             tr.n = 0;
-            int verdict = ort_ring_filter(F, K, J, g, w[1], w[2], w[3], &tr);
+            int verdict = ort_ring_filter(F, K, J, g, hi, &tr);
             TwinTrace T;
-            int exact = twin_filter(S, J, g, w, T);
+            int exact = twin_filter(S, J, g, hi, T);
             if (verdict > 0) {
                 ++lcalled;
                 if (verdict != exact) ++lwrong;
@@ -314,11 +317,9 @@ extern "C" int hh_filter_trace(const ort_job* job, const ort_scene* scene, int64
     DevFilter K;
     ort_make_filter(S, job->iris_before != 0, K);
     OrtRng g = harness_rng(J, i);
-    uint32_t w[4];
-    ort_block(g, 1u, w);
     OrtFilterTrace tr;
     tr.n = 0;
-    int verdict = ort_ring_filter(F, K, J, g, w[1], w[2], w[3], &tr);
+    int verdict = ort_ring_filter(F, K, J, g, ort_aim_hi(g), &tr);
     for (int k = 0; k < tr.n; ++k) {
         tags[2 * k] = tr.rec[k].tag; tags[2 * k + 1] = tr.rec[k].valid;
         for (int c = 0; c < 3; ++c) vals[4 * k + c] = tr.rec[k].v[c];

@@ -56,6 +56,17 @@ def test_slot_map_rev2(orc):
             wide(blk[8]), wide(blk[8], 1), wide(blk[9]), wide(blk[9], 1), wide(blk[10]), wide(blk[10], 1)]
     got = orc.uniforms(seed, phase, ray, 0, len(want))
     assert list(got) == want
+    # ring loop (phase 1): the high word of slot 2 is word (ray & 3) of the block rays 4q .. 4q+3 share,
+    # counter (ray >> 2, 16 + phase, 0); everything else as in the table
+    blk1 = [_philox(L, [ray & 0xffffffff, ray >> 32, 1, b], key, 0, 7) for b in range(5)]
+    q = ray >> 2
+    shared = _philox(L, [q & 0xffffffff, q >> 32, 17, 0], key, 0, 7)
+    got1 = orc.uniforms(seed, 1, ray, 0, 6)
+    assert got1[2] == float((((shared[ray & 3] << 32) | blk1[1][0]) >> 11)) * 2.0 ** -53
+    assert list(got1[[0, 1, 3, 4, 5]]) == [wide(blk1[0]), narrow(blk1[0][2]), narrow(blk1[1][2]), narrow(blk1[0][3]), narrow(blk1[1][3])]
+    # the four rays of a quad take the four different words
+    his = [int(orc.uniforms(seed, 1, 4 * q + k, 2, 1)[0] * 2.0 ** 32) for k in range(4)]
+    assert his == shared
 
 
 def test_uniform_stream_properties(orc):
