@@ -542,7 +542,7 @@ static int enqueue_ring_filter(DeviceCtx& c, Lane& L, const ort_job& job, const 
         int grid = c.num_sms * occ_cull;
         int gsz = (int)(want < grid ? (want > 0 ? want : 1) : grid);
         if (k >= 2) CK(cudaStreamWaitEvent(L.stream, L.ev_surv[buf], 0));
-        cull<<<gsz, ORT_TPB, smem_cull, L.stream>>>(sf, K, dj, aim_cut, list, L.d_nlist + k, (unsigned)capacity, d_cnt);
+        cull<<<gsz, ORT_TPB, smem_cull, L.stream>>>(sf, K, dj, list, L.d_nlist + k, (unsigned)capacity, d_cnt);
         CK(cudaGetLastError());
         CK(cudaEventRecord(L.ev_cull[buf], L.stream));
         /* the list length is only known on the device: size the grid for the longest list there can
@@ -624,7 +624,8 @@ static int enqueue_trace_t(DeviceCtx& c, const ort_job& job, const std::vector<D
         const int bottle_mode = (job.phase == ORT_PHASE_POINT && job.use_bottle)
                                     ? ((ds[sc].scatter_b || ds[sc].scatter_c) ? 2 : 1) : 0;
         unsigned long long ring_cut = 0; /* the ring loop's stage A decides on the high word of the aim draw */
-        if (job.phase == ORT_PHASE_RING && ds[sc].ring_shortcut && !ort_ring_aim_cut(ds[sc], &ring_cut, sizeof(R) == 4)) ring_cut = 0;
+        if (job.phase == ORT_PHASE_RING && ds[sc].ring_shortcut && !ort_ring_aim_cut(ds[sc], &ring_cut, sizeof(R) == 4))
+            ring_cut = ~0ull; /* no draw fails L2's aperture: every word is below the cut, the all-ones word is re-tested */
         const bool scatter_kernel = bottle_mode == 2 && !flat;
         typename Kernels<R>::trace_t k = scatter_kernel ? Kernels<R>::pick_scatter(job.source_kind)
                                                         : Kernels<R>::pick(job.phase, bottle_mode, job.source_kind, flat);

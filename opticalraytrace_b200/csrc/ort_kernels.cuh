@@ -140,9 +140,8 @@ __device__ __forceinline__ int ort_q_pop(WarpQueue<R>& q, int& n, OrtRayT<R>& r,
     n = base;
     return p;
 }
-/* the queue in front of L2.  SLIM: the entry carries only (px, py, wc) -- the ring loop's stage 0 hands
- * on two uniforms and one decision word */
-template <bool SLIM, typename R>
+/* the queue in front of L2 (the start point is on its flat face: no pz) */
+template <typename R>
 __device__ __forceinline__ void ort_q0_push(WarpQueueL2<R>& q, int& n, bool alive, const OrtRayT<R>& r, uint32_t id,
                                             uint32_t wf, uint32_t wc, unsigned lane) {
     unsigned m = __ballot_sync(ORT_FULL, alive);
@@ -150,16 +149,14 @@ __device__ __forceinline__ void ort_q0_push(WarpQueueL2<R>& q, int& n, bool aliv
         const int p = n + __popc(m & ((1u << lane) - 1u));
         ORT_ASSERT(p >= 0 && p < ORT_QCAP);
         q.px[p] = r.px; q.py[p] = r.py;
-        if (!SLIM) {
-            q.dx[p] = r.dx; q.dy[p] = r.dy; q.dz[p] = r.dz;
-            q.wf[p] = wf;
-        }
+        q.dx[p] = r.dx; q.dy[p] = r.dy; q.dz[p] = r.dz;
+        q.wf[p] = wf;
         q.wc[p] = wc;
         q.id[p] = id;
     }
     n += __popc(m);
 }
-template <bool SLIM, typename R>
+template <typename R>
 __device__ __forceinline__ bool ort_q0_pop(WarpQueueL2<R>& q, int& n, R flat_z, OrtRayT<R>& r, uint32_t& id, uint32_t& wf,
                                            uint32_t& wc, unsigned lane) {
     int cnt = n < 32 ? n : 32;
@@ -169,11 +166,9 @@ __device__ __forceinline__ bool ort_q0_pop(WarpQueueL2<R>& q, int& n, R flat_z, 
         const int p = base + lane;
         ORT_ASSERT(p >= 0 && p < ORT_QCAP);
         r.px = q.px[p]; r.py = q.py[p];
-        if (!SLIM) {
-            r.pz = flat_z;
-            r.dx = q.dx[p]; r.dy = q.dy[p]; r.dz = q.dz[p];
-            wf = q.wf[p];
-        }
+        r.pz = flat_z;
+        r.dx = q.dx[p]; r.dy = q.dy[p]; r.dz = q.dz[p];
+        wf = q.wf[p];
         wc = q.wc[p];
         id = q.id[p];
     }
@@ -223,9 +218,97 @@ __device__ __forceinline__ void ort_bin(unsigned long long* img, bool binned, in
     if (binned && (int)lane == __ffs(m) - 1) atomicAdd(img + key, (unsigned long long)__popc(m));
 }
 
+/* ---- ring loop, stage A on QUADS -------------------------------------------------------------
+ * The four rays 4q .. 4q+3 (global ray index) share the block that holds the high words of their aim-disc
+ * draws (ort_shared_block), so one lane decides L2's aperture for four rays with one Philox block: a pass
+ * takes the 32 quads [32 b, 32 b + 32) -- 128 rays -- and appends the survivors as (high word, ray id) to
+ * the warp's queue q (room for 32 leftovers + 128).  Ray ids are offsets from J.first_ray; `mis` is how
+ * far that is from a multiple of four.  on_edge(id, word) makes the call for a draw whose high word
+ * EQUALS the cut's (2^-32 of the rays).  Returns the number of rays that ended here (warp-uniform). */
+#define ORT_QUAD 4
+#define ORT_QUAD_QCAP (32 + 32 * ORT_QUAD)
+struct OrtQuadRange {
+    uint32_t mis, nquads, npasses, nrays, cut_hi;
+};
+__device__ __forceinline__ OrtQuadRange ort_quad_range(const DevJob& J) {
+    OrtQuadRange q;
+    q.nrays = (uint32_t)J.nrays;
+    q.mis = (uint32_t)(J.first_ray & 3);
+    q.nquads = (q.nrays + q.mis + 3u) >> 2;
+    q.npasses = (q.nquads + 31u) >> 5;
+    q.cut_hi = (uint32_t)(J.aim_cut >> 32);
+    return q;
+}
+template <typename EdgeFn>
+__device__ __forceinline__ unsigned ort_ring_quads_pass(const DevJob& J, const OrtQuadRange& Q, uint32_t b, uint2* q, int& n0,
+                                                        unsigned lane, EdgeFn on_edge) {
+    unsigned below;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(below));
+    const uint32_t quad = b * 32u + lane;
+    /* a pass at either end of the slice can hold ids outside it: counted exactly there, 128 elsewhere */
+    const bool edge = (b == 0u && Q.mis != 0u) || (b * 32u + 32u >= Q.nquads);
+    OrtRng g = ort_make_rng_prod(J, 0u); /* any ray of the quad names the shared block */
+    {
+        const unsigned long long ray = ((unsigned long long)J.first_ray & ~3ull) + 4ull * quad;
+        g.r0 = (uint32_t)ray;
+        g.r1 = (uint32_t)(ray >> 32);
+    }
+    uint32_t w[4];
+    ort_shared_block(g, w);
+    const int before = n0;
+    unsigned nvalid = 128u;
+    if (!edge) { /* every id of the pass is inside the slice */
+#pragma unroll
+        for (int k = 0; k < ORT_QUAD; ++k) {
+            bool pass = w[k] <= Q.cut_hi;
+            if (pass && w[k] == Q.cut_hi) pass = on_edge(quad * 4u + (uint32_t)k - Q.mis, w[k]);
+            const unsigned m = __ballot_sync(ORT_FULL, pass);
+            if (pass) {
+                int p = n0 + __popc(m & below);
+                ORT_ASSERT(p >= 0 && p < ORT_QUAD_QCAP);
+                q[p] = make_uint2(w[k], quad * 4u + (uint32_t)k - Q.mis);
+            }
+            n0 += __popc(m);
+        }
+    } else {
+        nvalid = 0u;
+#pragma unroll
+        for (int k = 0; k < ORT_QUAD; ++k) {
+            const uint32_t id = quad * 4u + (uint32_t)k - Q.mis; /* wraps above nrays when it is before the slice */
+            const bool valid = id < Q.nrays;
+            bool pass = valid && w[k] <= Q.cut_hi;
+            if (pass && w[k] == Q.cut_hi) pass = on_edge(id, w[k]);
+            const unsigned m = __ballot_sync(ORT_FULL, pass);
+            nvalid += __popc(__ballot_sync(ORT_FULL, valid));
+            if (pass) {
+                int p = n0 + __popc(m & below);
+                ORT_ASSERT(p >= 0 && p < ORT_QUAD_QCAP);
+                q[p] = make_uint2(w[k], id);
+            }
+            n0 += __popc(m);
+        }
+    }
+    __syncwarp();
+    return nvalid - (unsigned)(n0 - before);
+}
+/* up to 32 entries off the end of the queue, one per lane */
+__device__ __forceinline__ bool ort_quads_pop(const uint2* q, int& n, uint2& e, unsigned lane) {
+    int cnt = n < 32 ? n : 32;
+    int base = n - cnt;
+    bool act = (int)lane < cnt;
+    if (act) {
+        int p = base + lane;
+        ORT_ASSERT(p >= 0 && p < ORT_QUAD_QCAP);
+        e = q[p];
+    }
+    n = base;
+    __syncwarp();
+    return act;
+}
+
 /* ---- stages ------------------------------------------------------------------------------
- * A: emit.  Ring phase with the aim-plane shortcut: draw the aim point only and drop the 69 % of
- *    rays aimed outside L2's aperture (the survivors carry (u2,u3) in the queue).  Otherwise:
+ * A: emit.  Ring phase with the aim-plane shortcut: ort_ring_quads_pass above (69 % of the rays are aimed
+ *    outside L2's aperture; the survivors carry the tested word in the queue).  Otherwise:
  *    full source, (point phase) both bottle walls, carry to L2's flat face, aperture test.
  * B: (ring shortcut: the rest of the source, then) through L2, up to and including the aperture
  *    test on L3's first surface.
@@ -233,19 +316,6 @@ __device__ __forceinline__ void ort_bin(unsigned long long* img, bool binned, in
 template <int PHASE, int BOTTLE, int SRC, typename R>
 __device__ __forceinline__ int ort_stage_a(const DevSceneT<R>& S, const DevJob& J, const OrtRng& g, uint32_t id,
                                            OrtRayT<R>& r, uint32_t& wf, uint32_t& wc, int* nevents = nullptr) {
-    if (PHASE == ORT_PHASE_RING && SRC == ORT_SRC_POINT && S.ring_shortcut) {
-        /* only the high word of the aim-disc r^2 draw: it decides L2's aperture unless it EQUALS the cut's
-         * (2^-32 of the rays), and the survivor carries nothing else -- stage B regenerates its blocks */
-        const uint32_t hi = ort_aim_hi(g);
-        r.px = r.py = r.pz = r.dx = r.dy = r.dz = R(0.0);
-        wf = 0u;
-        wc = hi;
-        const uint32_t cut_hi = (uint32_t)(J.aim_cut >> 32);
-        if (J.aim_cut != 0ull && hi != cut_hi) return hi > cut_hi ? ORT_ST_L2_APERTURE : 0;
-        uint32_t b[4]; /* on the edge: the expression itself */
-        ort_block(g, 1u, b);
-        return ort_ring_aims_outside_aperture(S, ort_bits_to_uniform<R>(b[0], hi)) ? ORT_ST_L2_APERTURE : 0;
-    }
     OrtDraws01 D;
     ort_draws01<PHASE>(g, D);
     wf = D.a[3];
@@ -263,10 +333,11 @@ __device__ __forceinline__ int ort_stage_a(const DevSceneT<R>& S, const DevJob& 
     }
     return ort_l2_enter(S, r);
 }
-template <int PHASE, int SRC, typename R>
+/* FROM_WORD: in the ring loop with the aim-plane shortcut the ray arrives as the word stage A tested (in wc) */
+template <int PHASE, int SRC, bool FROM_WORD = true, typename R>
 __device__ __forceinline__ int ort_stage_b(const DevSceneT<R>& S, const DevJob& J, const OrtRng& g, OrtRayT<R>& r,
                                            uint32_t wf, uint32_t wc) {
-    if (PHASE == ORT_PHASE_RING && SRC == ORT_SRC_POINT && S.ring_shortcut) {
+    if (FROM_WORD && PHASE == ORT_PHASE_RING && SRC == ORT_SRC_POINT && S.ring_shortcut) {
         uint32_t a[4], b[4];
         ort_block(g, 0u, a);
         ort_block(g, 1u, b);
@@ -332,20 +403,39 @@ ort_trace_kernel(const __grid_constant__ DevSceneT<R> S, const __grid_constant__
 #endif
     int n1 = 0, n2 = 0;
     uint32_t b = gwarp;
-    /* ring loop with the aim-plane shortcut: stage 0 hands on only (u2, u3) */
+    /* ring loop with the aim-plane shortcut: stage 0 works on quads and hands on (tested word, ray id);
+     * these entries live in q0's memory */
     const bool slim = PHASE == ORT_PHASE_RING && SRC == ORT_SRC_POINT && S.ring_shortcut;
+    static_assert(sizeof(WarpQueueL2<R>) >= ORT_QUAD_QCAP * sizeof(uint2), "q0 too small for the quad queue");
+    uint2* const qq = reinterpret_cast<uint2*>(&ws.q0);
+    const OrtQuadRange Q = ort_quad_range(J);
+    const uint32_t nemit = slim ? Q.npasses : nbatches;
     for (;;) {
         int stage;
         if (n2 >= 32) stage = 2;
         else if (n1 >= 32) stage = 1;
-        else if (b < nbatches) stage = 0;
+        else if (b < nemit) stage = 0;
         else if (n2 > 0) stage = 2;
         else if (n1 > 0) stage = 1;
         else break;
 
         OrtRayT<R> r;
         uint32_t id = 0;
-        if (stage == 0) {
+        if (PHASE == ORT_PHASE_RING && SRC == ORT_SRC_POINT && stage == 0 && slim) {
+            const unsigned ended = ort_ring_quads_pass(J, Q, b, qq, n1, lane, [&](uint32_t eid, uint32_t hi) {
+                /* the expression itself (ort_ring_aims_outside_aperture on the whole draw) */
+                OrtRng g = ort_make_rng_prod(J, eid);
+                uint32_t v[4];
+                ort_block(g, 1u, v);
+                return !ort_ring_aims_outside_aperture(S, ort_bits_to_uniform<R>(v[0], hi));
+            });
+            b += nwarps;
+#if ORT_COUNT_SMEM
+            if (lane == 0 && ended) atomicAdd(ws.hist + ORT_ST_L2_APERTURE, ended);
+#else
+            cnt.c[ORT_ST_L2_APERTURE] += ended;
+#endif
+        } else if (stage == 0) {
             id = b * 32u + lane;
             b += nwarps;
             int st = -1;
@@ -364,8 +454,7 @@ ort_trace_kernel(const __grid_constant__ DevSceneT<R> S, const __grid_constant__
                     st = ort_stage_a<PHASE, BOTTLE, SRC>(S, J, g, id, r, wf, wc);
                 }
             }
-            if (slim) ort_q0_push<true>(ws.q0, n1, st == 0, r, id, wf, wc, lane);
-            else ort_q0_push<false>(ws.q0, n1, st == 0, r, id, wf, wc, lane);
+            ort_q0_push(ws.q0, n1, st == 0, r, id, wf, wc, lane);
             __syncwarp();
 #if ORT_COUNT_SMEM
             ort_tally_smem(ws.hist, st, st > 0);
@@ -374,8 +463,15 @@ ort_trace_kernel(const __grid_constant__ DevSceneT<R> S, const __grid_constant__
 #endif
         } else if (stage == 1) {
             uint32_t wf = 0u, wc = 0u;
-            const bool act = slim ? ort_q0_pop<true>(ws.q0, n1, S.l2_flat_z, r, id, wf, wc, lane)
-                                  : ort_q0_pop<false>(ws.q0, n1, S.l2_flat_z, r, id, wf, wc, lane);
+            bool act;
+            if (slim) {
+                uint2 e = make_uint2(0u, 0u);
+                act = ort_quads_pop(qq, n1, e, lane);
+                wc = e.x; /* the word stage A tested */
+                id = e.y;
+            } else {
+                act = ort_q0_pop(ws.q0, n1, S.l2_flat_z, r, id, wf, wc, lane);
+            }
             int st = -1;
             if (act) {
                 OrtRng g = ort_make_rng_prod(J, id);
@@ -529,12 +625,12 @@ ort_trace_scatter_kernel(const __grid_constant__ DevSceneT<R> S, const __grid_co
                 }
             }
             ort_qs_push(ws.qs, ns, st == ORT_BOTTLE_EVENT, r, ss, id, lane);
-            ort_q0_push<false>(ws.q0, n1, st == 0, r, id, wf, wc, lane);
+            ort_q0_push(ws.q0, n1, st == 0, r, id, wf, wc, lane);
             __syncwarp();
             ort_tally_smem(ws.hist, st, st > 0);
         } else if (stage == 2) {
             uint32_t wf = 0u, wc = 0u;
-            const bool act = ort_q0_pop<false>(ws.q0, n1, S.l2_flat_z, r, id, wf, wc, lane);
+            const bool act = ort_q0_pop(ws.q0, n1, S.l2_flat_z, r, id, wf, wc, lane);
             int st = -1;
             if (act) {
                 OrtRng g = ort_make_rng_prod(J, id);
@@ -577,25 +673,10 @@ ort_trace_scatter_kernel(const __grid_constant__ DevSceneT<R> S, const __grid_co
  * and the survivors kernel compares the filter's verdict with what fp64 finds:
  * counters[ORT_FILTER_SLOT_CALLED] = rays the filter called, counters[ORT_FILTER_SLOT_WRONG] =
  * calls that disagree with fp64 (must stay 0). */
-#define ORT_CULL_QUAD 4 /* rays per lane and stage-A pass: the four that share one block (ort_shared_block) */
-#define ORT_CULL_QCAP (32 + 32 * ORT_CULL_QUAD) /* < 32 leftovers + the survivors of one pass */
 struct SlimQueue {
-    uint2 e[ORT_CULL_QCAP]; /* x: high word of the aim-disc r^2 draw (what stage A tested), y: ray index */
+    uint2 e[ORT_QUAD_QCAP]; /* x: high word of the aim-disc r^2 draw (what stage A tested), y: ray index */
     uint32_t hb[64];        /* ray indices on their way to the survivors list */
 };
-__device__ __forceinline__ bool ort_slim_pop(SlimQueue& q, int& n, uint2& e, unsigned lane) {
-    int cnt = n < 32 ? n : 32;
-    int base = n - cnt;
-    bool act = (int)lane < cnt;
-    if (act) {
-        int p = base + lane;
-        ORT_ASSERT(p >= 0 && p < ORT_CULL_QCAP);
-        e = q.e[p];
-    }
-    n = base;
-    __syncwarp();
-    return act;
-}
 
 /* `count` (<= 32, warp-uniform) entries, one per lane, to the end of the global list */
 __device__ __forceinline__ void ort_list_append(uint32_t* __restrict__ list, unsigned* __restrict__ nlist,
@@ -624,22 +705,14 @@ __device__ __forceinline__ void ort_tally(unsigned& c, int st) {
 template <bool VERIFY>
 __global__ void __launch_bounds__(ORT_TPB, ORT_CULL_MIN_BLOCKS)
 ort_ring_cull_kernel(const __grid_constant__ DevSceneT<float> F, const __grid_constant__ DevFilter K,
-                     const __grid_constant__ DevJob J, const unsigned long long aim_cut, uint32_t* __restrict__ list, unsigned* __restrict__ nlist,
+                     const __grid_constant__ DevJob J, uint32_t* __restrict__ list, unsigned* __restrict__ nlist,
                      const unsigned capacity, unsigned long long* __restrict__ counters) {
     extern __shared__ __align__(16) unsigned char ort_smem[];
     SlimQueue& q0 = reinterpret_cast<SlimQueue*>(ort_smem)[threadIdx.x >> 5];
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t nwarps = gridDim.x * ORT_WPB;
     const uint32_t gwarp = blockIdx.x * ORT_WPB + (threadIdx.x >> 5);
-    const uint32_t nrays = (uint32_t)J.nrays;
-    /* Stage A works on QUADS: the four rays 4q .. 4q+3 (global ray index) share the block that holds the
-     * high words of their aim-disc draws, so one lane decides four rays with one Philox block.  Local ray
-     * ids are offsets from J.first_ray; `mis` is how far that is from a multiple of four. */
-    const uint32_t mis = (uint32_t)(J.first_ray & 3);
-    const uint32_t nquads = (nrays + mis + 3u) >> 2;
-    const uint32_t npasses = (nquads + 31u) >> 5; /* 32 quads = 128 rays per warp and pass */
-
-    const uint32_t cut_hi = (uint32_t)(aim_cut >> 32);
+    const OrtQuadRange Q = ort_quad_range(J);
     unsigned c9 = 0, c10 = 0, c11 = 0, c12 = 0, c13 = 0, c14 = 0;
     int nh = 0;           /* entries parked in q0.hb */
     unsigned below;       /* lanes below this one */
@@ -647,46 +720,16 @@ ort_ring_cull_kernel(const __grid_constant__ DevSceneT<float> F, const __grid_co
     int n0 = 0;
     uint32_t b = gwarp;
     for (;;) {
-        const bool emit = n0 < 32 && b < npasses;
+        const bool emit = n0 < 32 && b < Q.npasses;
         if (!emit && n0 == 0) break;
         if (emit) {
-            const uint32_t quad = b * 32u + lane;
-            /* a pass at either end of the slice can hold ids outside it: counted exactly there, 128 elsewhere */
-            const bool edge = (b == 0u && mis != 0u) || (b * 32u + 32u >= nquads);
+            /* a draw whose high word EQUALS the cut's goes on: it sits on the aperture edge, where the
+             * filter hands it to fp64, and ort_l2_enter there makes the exact call */
+            c9 += ort_ring_quads_pass(J, Q, b, q0.e, n0, lane, [](uint32_t, uint32_t) { return true; });
             b += nwarps;
-            OrtRng g = ort_make_rng_prod(J, 0u); /* any ray of the quad names the shared block */
-            {
-                const unsigned long long ray = ((unsigned long long)J.first_ray & ~3ull) + 4ull * quad;
-                g.r0 = (uint32_t)ray;
-                g.r1 = (uint32_t)(ray >> 32);
-            }
-            uint32_t w[4];
-            ort_shared_block(g, w);
-            const int before = n0;
-            unsigned nvalid = 128u;
-            if (edge) nvalid = 0u;
-#pragma unroll
-            for (int k = 0; k < ORT_CULL_QUAD; ++k) {
-                const uint32_t id = quad * 4u + (uint32_t)k - mis; /* wraps above nrays when it is before the slice */
-                const bool valid = id < nrays;
-                /* decided on the high word alone; a draw whose high word EQUALS the cut's (2^-32 of
-                 * the rays) goes on: it sits on the aperture edge, where the filter hands it to
-                 * fp64, and ort_l2_enter there makes the exact call */
-                const bool pass = valid && w[k] <= cut_hi;
-                const unsigned m = __ballot_sync(ORT_FULL, pass);
-                if (edge) nvalid += __popc(__ballot_sync(ORT_FULL, valid));
-                if (pass) {
-                    int p = n0 + __popc(m & below);
-                    ORT_ASSERT(p >= 0 && p < ORT_CULL_QCAP);
-                    q0.e[p] = make_uint2(w[k], id);
-                }
-                n0 += __popc(m);
-            }
-            c9 += nvalid - (unsigned)(n0 - before); /* warp-uniform: rays that ended in stage A */
-            __syncwarp();
         } else {
             uint2 e = make_uint2(0u, 0u);
-            bool act = ort_slim_pop(q0, n0, e, lane);
+            bool act = ort_quads_pop(q0.e, n0, e, lane);
             const uint32_t id = e.y;
             int st = -1;
             if (act) {
@@ -816,7 +859,7 @@ ort_trace_flat_kernel(const __grid_constant__ DevSceneT<R> S, const __grid_const
             int nev = 0;
             st = ort_stage_a<PHASE, BOTTLE, ORT_SRC_POINT>(S, J, g, id, r, wf, wc, &nev);
             if (nev) atomicAdd(counters + ORT_SCATTER_EVENTS_SLOT, (unsigned long long)nev);
-            if (st == 0) st = ort_stage_b<PHASE, ORT_SRC_POINT>(S, J, g, r, wf, wc);
+            if (st == 0) st = ort_stage_b<PHASE, ORT_SRC_POINT, false>(S, J, g, r, wf, wc);
             if (st == 0) st = ort_stage_c(S, J, g, r, &xp, &yp);
         }
         ort_bin(img, st == ORT_ST_BINNED, xp, yp, lane);
