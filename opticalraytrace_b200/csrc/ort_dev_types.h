@@ -116,6 +116,7 @@ struct DevFilter {
     float ap_inv, ap_r, ap_0;       /* L3 aperture: bound(rho^2) = ep (rho^2 * ap_inv + ap_r) + 4u rho^2 + ap_0 */
     float iris_inv, iris_r, iris_0; /* L3 iris, same form */
     float iris_z0;                  /* rounding of the iris plane distance */
+    float r2m_s, lens_r2_s;         /* the fp32 scene's r2_m_r1 and lens_r2 times 2^-32 (they multiply raw 32-bit words) */
     DevFilterFlat flat;
     DevFilterIface curved;
     DevFilterSphere s2, s3; /* s2: from the flat face, where ep = ep_flat is inside h_0, c_0 */

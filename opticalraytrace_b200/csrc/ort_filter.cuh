@@ -86,9 +86,11 @@ ORT_HD float ortf_sqrt(float x) {
     return ORTF_PERTURB_REL(sqrtf(x), 0.5f * ORTF_E_SQRT);
 #endif
 }
-/* sin, cos of 2 pi u, u in [0,1]: the argument is folded to [-pi, pi] first */
-ORT_HD void ortf_sincos_turn(float u, float* s, float* c) {
-    float a = (u - (u >= 0.5f ? 1.0f : 0.0f)) * 6.2831853071795865f;
+/* sin, cos of 2 pi u for the narrow draw u = w 2^-32.  Read as a SIGNED integer the word is 2^32 (u - [u >= 1/2]):
+ * the same angle, folded to [-pi, pi), from one conversion and one product.  The conversion is off by
+ * <= 2^-25 |w_s| <= 2^-26 of a turn (less than the 2^-25 the bound allows for an unsigned word). */
+ORT_HD void ortf_sincos_word(uint32_t w, float* s, float* c) {
+    float a = (float)(int32_t)w * 1.4629180792671596e-9f; /* 2 pi 2^-32 */
 #ifdef __CUDA_ARCH__
     asm("sin.approx.ftz.f32 %0, %1;" : "=f"(*s) : "f"(a));
     asm("cos.approx.ftz.f32 %0, %1;" : "=f"(*c) : "f"(a));
@@ -97,10 +99,11 @@ ORT_HD void ortf_sincos_turn(float u, float* s, float* c) {
     *c = ORTF_PERTURB_ABS(cosf(a), 0.5f * ORTF_E_SIN);
 #endif
 }
-/* a uniform from one 32-bit word (a narrow draw, or the high word of a wide one), rounded to the
- * nearest float: off the exact draw by <= 2^-25 (+ 2^-32 for the unseen low word of a wide draw) */
-ORT_HD float ortf_uniform(uint32_t w) {
-    return (float)w * 2.3283064365386963e-10f;
+/* A 32-bit word (a narrow draw, or the high word of a wide one) as a float: 2^32 times a uniform that is
+ * off the exact draw by <= 2^-25 (+ 2^-32 for the unseen low word of a wide draw).  The factor 2^-32 is
+ * folded into whatever the draw multiplies (powers of two: the products are the same floats). */
+ORT_HD float ortf_word(uint32_t w) {
+    return (float)w;
 }
 
 /* what the bound test in tests/test_filter_bound.py reads back (host harness only) */
@@ -139,9 +142,9 @@ ORT_HD void ortf_trace(OrtFilterTrace* tr, int tag, bool unc, float a, float b, 
 /* Ray-sphere intersection, ort_hit_sphere / ort_pick_root_unit: false = miss.  The outcome hangs on
  * the signs of disc, h and c.  In: ep, ed.  Out: *t and *et >= |t~ - t*|. */
 template <bool FROM_FLAT> /* the start point is on L2's flat face: its bound ep_flat is inside h_0, c_0, d_0 */
-ORT_HD bool ortf_hit_sphere(const OrtRayT<float>& r, float cx, float cy, float cz, float R2, const DevFilterSphere& k,
+ORT_HD bool ortf_hit_sphere(const OrtRayT<float>& r, float cz, float R2, const DevFilterSphere& k,
                             float ep, float ed, float* t, float* et, bool& unc, OrtFilterTrace* tr, int surf) {
-    float lx = r.px - cx, ly = r.py - cy, lz = r.pz - cz;
+    float lx = r.px, ly = r.py, lz = r.pz - cz; /* the centre is on the axis (ort_make_filter checks) */
     float h = fmaf(r.dx, lx, fmaf(r.dy, ly, r.dz * lz));
     float l2 = fmaf(lx, lx, fmaf(ly, ly, lz * lz));
     float c = l2 - R2;
@@ -188,7 +191,7 @@ ORT_HD bool ortf_hit_sphere(const OrtRayT<float>& r, float cx, float cy, float c
 /* L2's flat face (ort_interface with the normal (0,0,-1) and eta < 1; ort_make_filter checks both):
  * N.I = -dz exactly, no total reflection, T = (eta dx, eta dy, cos theta_t).  true = reflected
  * (the reference does not test that flag: the ray goes on either way, quirk 1). */
-ORT_HD bool ortf_flat_face(OrtRayT<float>& r, const DevIfaceT<float>& f, const DevFilterFlat& k, float u, float& ed,
+ORT_HD bool ortf_flat_face(OrtRayT<float>& r, const DevIfaceT<float>& f, const DevFilterFlat& k, float uw, float& ed,
                            bool& unc, OrtFilterTrace* tr, int surf) {
     float costt = r.dz; /* > 0: the aim plane lies beyond the bottle (Dmin > 0) */
     float s2 = fmaf(-costt, costt, 1.0f);
@@ -206,7 +209,7 @@ ORT_HD bool ortf_flat_face(OrtRayT<float>& r, const DevIfaceT<float>& f, const D
     float A = ec - cost2, B = ec + cost2, C = e2 - costt, D = e2 + costt;
     float B2 = B * B, D2 = D * D, den = B2 * D2;
     float num = fmaf(A * A, D2, (C * C) * B2);
-    float lhs = (u + u) * den;
+    float lhs = (uw * den) * 4.656612873077393e-10f; /* 2 u den, u = uw 2^-32 */
     /* lhs - num = 2 den (u - R(cos_i)):  |dR / dcos_i| = 2 eta (1 - eta^2) / cos_t |A / B^3 - C / D^3|, bounded
      * over the whole face by a scene constant, so  ef = den (f_a ed + f_b)  (f_b: the draw and the rounding) */
     float ef = den * fmaf(k.f_a, ed, k.f_b);
@@ -229,7 +232,7 @@ ORT_HD bool ortf_flat_face(OrtRayT<float>& r, const DevIfaceT<float>& f, const D
  * then the ray ends (its direction is not updated).  In: en (normal), ed (direction); out: ed of the
  * refracted direction. */
 ORT_HD bool ortf_exit_face(OrtRayT<float>& r, float nx, float ny, float nz, const DevIfaceT<float>& f,
-                           const DevFilterIface& k, float u, float en, float& ed, bool& unc, OrtFilterTrace* tr,
+                           const DevFilterIface& k, float uw, float en, float& ed, bool& unc, OrtFilterTrace* tr,
                            int surf) {
     float c = fmaf(nx, r.dx, fmaf(ny, r.dy, nz * r.dz));
     float costt = fabsf(c);
@@ -259,7 +262,7 @@ ORT_HD bool ortf_exit_face(OrtRayT<float>& r, float nx, float ny, float nz, cons
     float A = ec - cost2, B = ec + cost2, C = e2 - costt, D = e2 + costt;
     float B2 = B * B, D2 = D * D, den = B2 * D2;
     float num = fmaf(A * A, D2, (C * C) * B2);
-    float lhs = (u + u) * den;
+    float lhs = (uw * den) * 4.656612873077393e-10f; /* 2 u den, u = uw 2^-32 */
     /* lhs - num = 2 den (u - R(cos_i)),  |dR / dcos_i| <= 2 eta |1 - eta^2| / cos_t (1 / B^2 + 1 / D^2), and B, D
      * are bounded below without total reflection:  ef = den (f_a eni / cos_t + f_b);  G6, G7 keep cos_i, cos_t
      * within the 1.07 inside f_a (and d_d, d_n below) over the segment between fp32 and exact arguments */
@@ -305,24 +308,22 @@ ORT_HD int ort_ring_filter(const DevSceneT<float>& F, const DevFilter& K, const 
     ort_block(g, 0u, w);
     ort_block(g, 1u, v);
     const uint32_t w_aim = v[2], w_curved = v[3];
-    const float u0 = ortf_uniform(w[1]), u1 = ortf_uniform(w[2]);
-    const float u2 = ortf_uniform(h2), u3 = ortf_uniform(w_aim);
     /* ring source, ort_source_ring_u.  Its position error is a scene constant (inside K.ed_a) */
     OrtRayT<float> r;
     float s, c;
-    float rr = ortf_sqrt(fmaf(u0, F.r2_m_r1, F.r1));
-    ortf_sincos_turn(u1, &s, &c);
+    float rr = ortf_sqrt(fmaf(ortf_word(w[1]), K.r2m_s, F.r1)); /* r1 + u0 (r2 - r1) */
+    ortf_sincos_word(w[2], &s, &c);
     r.px = rr * c;
     r.py = rr * s;
     float q = F.ellipse ? r.py * F.ra_over_rb : r.py;
     r.pz = F.bcz + ortf_sqrt(fmaf(-q, q, F.ra2));
-    float aim2 = u2 * F.lens_r2;
+    float aim2 = ortf_word(h2) * K.lens_r2_s; /* u2 lens_r2 */
     /* G5;  and L2's aperture: stage A decided it on the exact draw, but the fp64 path re-tests the
      * computed aim point (ort_l2_enter), which can differ within its rounding of the edge -- those
      * rays are fp64's */
     bool unc = h2 < 65536u || !(aim2 < F.l2_radius2 * 0.999996f);
     float rl = aim2 * ortf_rsqrt(aim2);
-    ortf_sincos_turn(u3, &s, &c);
+    ortf_sincos_word(w_aim, &s, &c);
     float ax = rl * c, ay = rl * s;
     float ex = ax - r.px, ey = ay - r.py, ez = F.l2_fb - r.pz;
     float inv = ortf_rsqrt(fmaf(ex, ex, fmaf(ey, ey, ez * ez)));
@@ -338,19 +339,19 @@ ORT_HD int ort_ring_filter(const DevSceneT<float>& F, const DevFilter& K, const 
     ortf_trace(tr, 0 + ORTF_T_POS, unc, r.px, r.py, r.pz, K.ep_flat);
     ortf_trace(tr, 0 + ORTF_T_DIR, unc, r.dx, r.dy, r.dz, ed);
     /* L2, ort_l2_body; a reflection at the flat face is not tested by the reference: the ray goes on */
-    (void)ortf_flat_face(r, F.l2_in, K.flat, ortf_uniform(w[3]), ed, unc, tr, 100);
+    (void)ortf_flat_face(r, F.l2_in, K.flat, ortf_word(w[3]), ed, unc, tr, 100);
     float t, et;
-    if (!ortf_hit_sphere<true>(r, F.l2_cx, F.l2_cy, F.l2_cz, F.l2_R2, K.s2, 0.0f, ed, &t, &et, unc, tr, 200))
+    if (!ortf_hit_sphere<true>(r, F.l2_cz, F.l2_R2, K.s2, 0.0f, ed, &t, &et, unc, tr, 200))
         return unc ? 0 : ORT_ST_L2_SPHERE_MISS;
     ort_advance(r, t);
     /* (R2) the hit point: ep' = ep + |t| ed + 1.02 et + rounding (|t*| <= |t~| + et, |dir~| <= 1.01);  G2 */
     float ep = fmaf(fabsf(t), ed, fmaf(1.02f, et, K.s2.p_0));
     float en = fmaf(K.s2.n_p, ep, K.s2.n_0);
-    float nx = (F.l2_cx - r.px) * F.l2_invR, ny = (F.l2_cy - r.py) * F.l2_invR, nz = (F.l2_cz - r.pz) * F.l2_invR;
+    float nx = r.px * -F.l2_invR, ny = r.py * -F.l2_invR, nz = (F.l2_cz - r.pz) * F.l2_invR; /* centre on the axis */
     ortf_trace(tr, 200 + ORTF_T_POS, unc, r.px, r.py, r.pz, ep);
     ortf_trace(tr, 200 + ORTF_T_NORMAL, unc, nx, ny, nz, en);
     unc |= !(ep < K.ep_max);
-    if (ortf_exit_face(r, nx, ny, nz, F.l2_out, K.curved, ortf_uniform(w_curved), en, ed, unc, tr, 300))
+    if (ortf_exit_face(r, nx, ny, nz, F.l2_out, K.curved, ortf_word(w_curved), en, ed, unc, tr, 300))
         return unc ? 0 : ORT_ST_L2_CURVED_REFLECT;
     /* L3 up to its aperture, ort_l3_enter */
     if (J.iris_before) {
@@ -369,7 +370,7 @@ ORT_HD int ort_ring_filter(const DevSceneT<float>& F, const DevFilter& K, const 
         if (ortf_outside(x, y, F.l3_iris_r2, K.iris_inv, K.iris_r, K.iris_0, epi, unc, tr, 400))
             return unc ? 0 : ORT_ST_L3_IRIS_BEFORE;
     }
-    if (!ortf_hit_sphere<false>(r, F.l3_c1x, F.l3_c1y, F.l3_c1z, F.l3_R1_2, K.s3, ep, ed, &t, &et, unc, tr, 500))
+    if (!ortf_hit_sphere<false>(r, F.l3_c1z, F.l3_R1_2, K.s3, ep, ed, &t, &et, unc, tr, 500))
         return unc ? 0 : ORT_ST_L3_S1_MISS;
     ort_advance(r, t);
     ep = fmaf(fabsf(t), ed, fmaf(1.02f, et, ep + K.s3.p_0));

@@ -259,9 +259,14 @@ inline void ort_make_filter(const DevScene& d, bool iris_before, DevFilter& K) {
     const double EE = EA + EP0 + U * std::fabs(d.l2_fb) + 2.0 * u * Emax;
     K.ed_a = ort_up(2.02 * EE);
     K.ed_b = ort_up(1.01 * (5.0 * u + E_RSQ));
+    /* scene constants that multiply a raw word: the fp32 scene's value (rounded once from double, as
+     * ort_scene_to_float does) times 2^-32, exact */
+    K.r2m_s = (float)d.r2_m_r1 * 2.3283064365386963e-10f;
+    K.lens_r2_s = (float)d.lens_r2 * 2.3283064365386963e-10f;
     /* ---- L2's two faces: premises of the specialised code */
     bool ok = ort_filter_flat(d.l2_in, K.flat) && ort_filter_exit(d.l2_out, K.curved);
     ok = ok && d.l2_fnx == 0.0 && d.l2_fny == 0.0 && d.l2_fnz == -1.0 && d.l2_cx == 0.0 && d.l2_cy == 0.0;
+    ok = ok && d.l3_c1x == 0.0 && d.l3_c1y == 0.0; /* both sphere centres on the axis */
     /* ---- spheres.  L2: from the flat face inside the aperture.  L3 surface 1: from L2's sphere. */
     const double R2 = std::sqrt(d.l2_R2), R1 = std::sqrt(d.l3_R1_2);
     const double c2n = std::fabs(d.l2_cz);

@@ -992,7 +992,7 @@ __global__ void ort_math_selftest_kernel(long long n, unsigned long long* __rest
 /* Rule R4 of the ring filter's error bound (ort_filter.cuh): the largest error of the MUFU
  * approximations it uses, over EVERY fp32 argument -- all 2^32 bit patterns are tried.
  *   worst[0..2]  relative error of rcp / rsqrt / sqrt.approx.ftz.f32, |x| (x > 0 for the roots) in [2^-64, 2^64]
- *   worst[3..4]  absolute error of sin / cos.approx.ftz.f32, |x| <= 3.1416 (ortf_sincos_turn folds to [-pi, pi])
+ *   worst[3..4]  absolute error of sin / cos.approx.ftz.f32, |x| <= 3.1416 (ortf_sincos_word: the angle is in [-pi, pi))
  * as the bit patterns of non-negative doubles (which order like integers), against fp64 references. */
 __global__ void ort_mufu_selftest_kernel(unsigned long long* __restrict__ worst) {
     double w0 = 0.0, w1 = 0.0, w2 = 0.0, w3 = 0.0, w4 = 0.0;
