@@ -204,7 +204,7 @@ ORT_HD bool ortf_flat_face(OrtRayT<float>& r, const DevIfaceT<float>& f, const D
     unc |= !(ed < 0.0078125f) || !(s2 > es2) || !(costt > 0.0f); /* G1 */
     ortf_trace(tr, surf + 24, !(ed < 0.0078125f), 0.f, 0.f, 0.f, 0.f);
     ortf_trace(tr, surf + 25, !(s2 > es2), 0.f, 0.f, 0.f, 0.f);
-    float cost2 = ct2 * ortf_rsqrt(ct2);
+    float cost2 = ortf_sqrt(ct2); /* E_SQRT <= E_RSQ + u, what d_b and f_b allow for it */
     float ec = f.eta * costt, e2 = f.eta * cost2;
     float A = ec - cost2, B = ec + cost2, C = e2 - costt, D = e2 + costt;
     float B2 = B * B, D2 = D * D, den = B2 * D2;
@@ -322,7 +322,7 @@ ORT_HD int ort_ring_filter(const DevSceneT<float>& F, const DevFilter& K, const 
      * computed aim point (ort_l2_enter), which can differ within its rounding of the edge -- those
      * rays are fp64's */
     bool unc = h2 < 65536u || !(aim2 < F.l2_radius2 * 0.999996f);
-    float rl = aim2 * ortf_rsqrt(aim2);
+    float rl = ortf_sqrt(aim2); /* E_SQRT <= E_RSQ + 2.5u, what E_rl allows */
     ortf_sincos_word(w_aim, &s, &c);
     float ax = rl * c, ay = rl * s;
     float ex = ax - r.px, ey = ay - r.py, ez = F.l2_fb - r.pz;
