@@ -1094,6 +1094,30 @@ int orc_philox(const uint32_t* ctr, const uint32_t* key, int32_t first, int32_t 
 }
 int orc_philox_rounds(void) { return PHILOX_ROUNDS; }
 
+/* Ray indices in [first, first + n) whose ring-loop aim word (the high word of slot 2, see Draws::slot) equals
+ * `word`: the rays that sit on the integer aperture cut of the CUDA kernels' stage A (2^-32 of all rays),
+ * found by brute force for tests/golden/make_edge_rays.py.  Returns how many were found (at most `cap` stored). */
+int64_t orc_find_aim_word(uint64_t seed, int32_t phase, uint32_t word, int64_t first, int64_t n, int64_t* out, int64_t cap) {
+    const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    const uint64_t q0 = (uint64_t)first >> 2, q1 = ((uint64_t)(first + n) + 3) >> 2;
+    int64_t found = 0;
+#pragma omp parallel for schedule(static)
+    for (uint64_t q = q0; q < q1; ++q) {
+        uint32_t ctr[4] = {(uint32_t)q, (uint32_t)(q >> 32), 16u + (uint32_t)phase, 0u}, sh[4];
+        philox4x32_rounds(ctr, key, 0, PHILOX_ROUNDS, sh);
+        for (int k = 0; k < 4; ++k) {
+            const int64_t ray = (int64_t)(4 * q + k);
+            if (sh[k] == word && ray >= first && ray < first + n) {
+                int64_t slot;
+#pragma omp atomic capture
+                slot = found++;
+                if (slot < cap) out[slot] = ray;
+            }
+        }
+    }
+    return found;
+}
+
 /* Same contract as ort_trace_rays (include/ort.h). */
 int orc_trace_rays(const ort_job* job, const ort_scene* scene, int64_t n, const double* pos_in,
                    const double* dir_in, double* pos_out, double* dir_out, int32_t* status,

@@ -4,6 +4,8 @@ A verdict s > 0 claims "this ray ends with status s, no need to trace it in fp64
 with the oracle on EVERY ray; a verdict 0 hands the ray to the fp64 stage and is always safe.  On
 CPU the filter is the host-compiled header; on the GPU box ORT_FLAG_VERIFY_FILTER makes the kernel
 run both paths on every ray and count disagreements."""
+import os
+
 import numpy as np
 import pytest
 
@@ -226,3 +228,45 @@ def test_high_word_rule_of_stage_a(orc, harness):
             continue
         u2 = float(((hi << 32) | lo) >> 11) * 2.0 ** -53
         assert (u2 * lens_r2 > rad2) == (hi > cut_hi)
+
+
+def _edge_cases():
+    import json
+    d = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "edge_rays_v2.json")))
+    return [(name, c["cut_hi"], ray) for name, c in sorted(d["cases"].items()) for ray in c["rays"]]
+
+
+def test_edge_ray_fixture_matches_the_generator(orc, harness):
+    """tests/golden/edge_rays_v2.json (make_edge_rays.py): rays whose aim word EQUALS the cut's high word, the
+    one case stage A cannot decide on the word.  Checked against the oracle's own draw: slot 2 of each
+    listed ray, as 53 bits, has exactly that high word."""
+    for name, cut_hi, ray in _edge_cases():
+        files = cases.C1 if name == "c1" else cases.C2
+        scene = cases.scene_for(orc, files, 1)
+        cut, have = harness.ring_aim_cut(abi.default_job(1), scene)
+        assert have and cut >> 32 == cut_hi
+        u2 = orc.uniforms(abi.default_job(1).seed, 1, ray, 2, 1)[0]
+        assert (int(u2 * 2.0 ** 53) << 11) >> 32 == cut_hi, (name, ray)
+
+
+@pytest.mark.gpu
+def test_cuda_rays_on_the_aperture_cut(ort, orc):
+    """A few rays around every listed edge ray through the culling kernel (the ray goes on to fp64), the
+    all-fp64 kernel (it evaluates the whole aperture expression) and the oracle: identical counts and images;
+    the fp32 kernel takes the same branch and must at least account for every ray.  The windows start off a
+    multiple of four, so the first and last quad of the launch are partial."""
+    for name, cut_hi, ray in _edge_cases():
+        files = cases.C1 if name == "c1" else cases.C2
+        scene = cases.scene_for(orc, files, 1)
+        for first, n in ((ray - 3, 9), (ray, 1), (ray - 130, 263)):
+            job = abi.default_job(1, n, first_ray=first)
+            oimg, olost, ohist = orc.trace(job, scene)
+            img, lost, hist, _ = ort.trace(job, scene)
+            assert np.array_equal(hist, ohist) and np.array_equal(img, oimg) and np.array_equal(lost, olost), (name, ray, first, n)
+            job.flags = abi.FLAG_NO_FILTER
+            img0, lost0, hist0, _ = ort.trace(job, scene)
+            assert np.array_equal(hist0, ohist) and np.array_equal(img0, oimg), (name, ray, first, n)
+            job32 = abi.default_job(1, n, first_ray=first)
+            job32.precision = 32
+            _, _, hist32, _ = ort.trace(job32, scene)
+            assert int(hist32[..., :27].sum()) == n
