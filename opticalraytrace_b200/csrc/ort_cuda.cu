@@ -592,20 +592,36 @@ static int enqueue_ring_filter(DeviceCtx& c, Lane& L, const ort_job& job, const 
     return ORT_OK;
 }
 
+/* what the host works out per scene before anything is launched (once per call) */
+struct ScenePlan {
+    bool filter = false;              /* ring loop through the culling kernel */
+    unsigned long long aim_cut = 0;   /* ... its integer aperture cut */
+    DevFilter K;                      /* ... and error-bound constants */
+    unsigned long long ring_cut = 0;  /* the cut of the other ring kernels (their own expression) */
+};
+template <typename R>
+static void plan_scenes(const ort_job& job, const std::vector<DevScene>& ds, bool flat, std::vector<ScenePlan>& plan) {
+    plan.resize(ds.size());
+    for (size_t sc = 0; sc < ds.size(); ++sc) {
+        ScenePlan& p = plan[sc];
+        p.filter = ring_filter_applies<R>(job, ds[sc], flat, &p.aim_cut, &p.K);
+        if (!p.filter && job.phase == ORT_PHASE_RING && ds[sc].ring_shortcut &&
+            !ort_ring_aim_cut(ds[sc], &p.ring_cut, sizeof(R) == 4))
+            p.ring_cut = ~0ull; /* no draw fails L2's aperture: every word is below the cut, the all-ones word is re-tested */
+    }
+}
+
 /* one pass over the scenes of a call: the launches, or (dry) only what has to exist before them */
 template <typename R>
-static int enqueue_scenes(DeviceCtx& c, const ort_job& job, const std::vector<DevScene>& ds, int64_t first, int64_t n,
-                          bool flat, size_t smem_trace, int nlanes, unsigned long long* d_img, unsigned long long* d_cnt,
-                          int64_t* launches, bool dry) {
+static int enqueue_scenes(DeviceCtx& c, const ort_job& job, const std::vector<DevScene>& ds, const std::vector<ScenePlan>& plan,
+                          int64_t first, int64_t n, bool flat, size_t smem_trace, int nlanes, unsigned long long* d_img,
+                          unsigned long long* d_cnt, int64_t* launches, bool dry) {
     const int nscenes = (int)ds.size();
     for (int sc = 0; sc < nscenes; ++sc) {
         Lane& L = c.lanes[sc % nlanes];
-        DevSceneT<R> dsr;
-        scene_as(ds[sc], dsr);
-        unsigned long long aim_cut = 0;
-        DevFilter K;
-        if (ring_filter_applies<R>(job, ds[sc], flat, &aim_cut, &K)) {
-            int rc = enqueue_ring_filter(c, L, job, ds[sc], K, aim_cut, nscenes, first, n, d_img + (size_t)sc * ORT_IMG_BINS,
+        const ScenePlan& P = plan[sc];
+        if (P.filter) {
+            int rc = enqueue_ring_filter(c, L, job, ds[sc], P.K, P.aim_cut, nscenes, first, n, d_img + (size_t)sc * ORT_IMG_BINS,
                                          d_cnt + (size_t)sc * ORT_NSTATUS, launches, dry);
             if (rc != ORT_OK) return rc;
             continue;
@@ -615,9 +631,6 @@ static int enqueue_scenes(DeviceCtx& c, const ort_job& job, const std::vector<De
          * depend on what it is batched with */
         const int bottle_mode = (job.phase == ORT_PHASE_POINT && job.use_bottle)
                                     ? ((ds[sc].scatter_b || ds[sc].scatter_c) ? 2 : 1) : 0;
-        unsigned long long ring_cut = 0; /* the ring loop's stage A decides on the high word of the aim draw */
-        if (job.phase == ORT_PHASE_RING && ds[sc].ring_shortcut && !ort_ring_aim_cut(ds[sc], &ring_cut, sizeof(R) == 4))
-            ring_cut = ~0ull; /* no draw fails L2's aperture: every word is below the cut, the all-ones word is re-tested */
         const bool scatter_kernel = bottle_mode == 2 && !flat;
         typename Kernels<R>::trace_t k = scatter_kernel ? Kernels<R>::pick_scatter(job.source_kind)
                                                         : Kernels<R>::pick(job.phase, bottle_mode, job.source_kind, flat);
@@ -626,13 +639,15 @@ static int enqueue_scenes(DeviceCtx& c, const ort_job& job, const std::vector<De
         int orc = ctx_occupancy(c, (const void*)k, smem, &occ);
         if (orc != ORT_OK) return orc;
         if (dry) continue;
+        DevSceneT<R> dsr;
+        scene_as(ds[sc], dsr);
         const int grid = c.num_sms * occ;
         for (int64_t off = 0; off < n; off += ORT_CHUNK) {
             int64_t m = n - off < ORT_CHUNK ? n - off : ORT_CHUNK;
             DevJob dj;
             ort_make_dev_job(job, nscenes, first + off, m, dj);
             dj.image_cdf = c.d_image_cdf;
-            dj.aim_cut = ring_cut;
+            dj.aim_cut = P.ring_cut; /* the ring loop's stage A decides on the high word of the aim draw */
             int64_t batches = (m + 31) / 32;
             int64_t want = (batches + ORT_WPB - 1) / ORT_WPB;
             int gsz = (int)(want < grid ? (want > 0 ? want : 1) : grid);
@@ -668,9 +683,11 @@ static int enqueue_trace_t(DeviceCtx& c, const ort_job& job, const std::vector<D
      * occupancy query is answered from a cache afterwards) */
     unsigned long long* d_img = c.d_buf;
     unsigned long long* d_cnt = c.d_buf + (size_t)nscenes * ORT_IMG_BINS;
+    std::vector<ScenePlan> plan;
+    plan_scenes<R>(job, ds, flat, plan);
     {
         int64_t none = 0;
-        int rc = enqueue_scenes<R>(c, job, ds, first, n, flat, smem_trace, nlanes, d_img, d_cnt, &none, true);
+        int rc = enqueue_scenes<R>(c, job, ds, plan, first, n, flat, smem_trace, nlanes, d_img, d_cnt, &none, true);
         if (rc != ORT_OK) return rc;
     }
 
@@ -688,7 +705,7 @@ static int enqueue_trace_t(DeviceCtx& c, const ort_job& job, const std::vector<D
         for (int l = 1; l < nlanes; ++l) CK(cudaStreamWaitEvent(c.lanes[l].stream, c.ev_zeroed, 0));
     }
     {
-        int rc = enqueue_scenes<R>(c, job, ds, first, n, flat, smem_trace, nlanes, d_img, d_cnt, launches, false);
+        int rc = enqueue_scenes<R>(c, job, ds, plan, first, n, flat, smem_trace, nlanes, d_img, d_cnt, launches, false);
         if (rc != ORT_OK) return rc;
     }
     for (int l = 1; l < nlanes; ++l) { /* the main stream continues when every lane is done */
