@@ -661,9 +661,10 @@ static int enqueue_scenes(DeviceCtx& c, const ort_job& job, const std::vector<De
 }
 
 /* enqueue the trace of rays [first, first+n) of every scene on device ctx; returns launches */
+/* what: 1 = only the preparation (memory, kernels loaded), 2 = only the launches, 3 = both */
 template <typename R>
 static int enqueue_trace_t(DeviceCtx& c, const ort_job& job, const std::vector<DevScene>& ds, int64_t first,
-                           int64_t n, int64_t* launches) {
+                           int64_t n, int64_t* launches, int what) {
     const int nscenes = (int)ds.size();
     CK(cudaSetDevice(c.dev));
     size_t elems = (size_t)nscenes * (ORT_IMG_BINS + ORT_NSTATUS);
@@ -685,11 +686,12 @@ static int enqueue_trace_t(DeviceCtx& c, const ort_job& job, const std::vector<D
     unsigned long long* d_cnt = c.d_buf + (size_t)nscenes * ORT_IMG_BINS;
     std::vector<ScenePlan> plan;
     plan_scenes<R>(job, ds, flat, plan);
-    {
+    if (what & 1) {
         int64_t none = 0;
         int rc = enqueue_scenes<R>(c, job, ds, plan, first, n, flat, smem_trace, nlanes, d_img, d_cnt, &none, true);
         if (rc != ORT_OK) return rc;
     }
+    if (!(what & 2)) return ORT_OK;
 
     CK(cudaEventRecord(c.ev_start, c.stream));
     CK(cudaMemsetAsync(c.d_buf, 0, elems * sizeof(unsigned long long), c.stream));
@@ -716,9 +718,9 @@ static int enqueue_trace_t(DeviceCtx& c, const ort_job& job, const std::vector<D
     return ORT_OK;
 }
 static int enqueue_trace(DeviceCtx& c, const ort_job& job, const std::vector<DevScene>& ds, int64_t first,
-                         int64_t n, int64_t* launches) {
-    return job.precision == 32 ? enqueue_trace_t<float>(c, job, ds, first, n, launches)
-                               : enqueue_trace_t<double>(c, job, ds, first, n, launches);
+                         int64_t n, int64_t* launches, int what = 3) {
+    return job.precision == 32 ? enqueue_trace_t<float>(c, job, ds, first, n, launches, what)
+                               : enqueue_trace_t<double>(c, job, ds, first, n, launches, what);
 }
 
 /* pinned staging buffer -> the caller's (pageable, often untouched) buffer.  A batched call returns
@@ -775,10 +777,14 @@ extern "C" int ort_trace(const ort_job* job, const ort_scene* scenes, int nscene
     int64_t launches = 0;
     /* contiguous ray-index ranges per device; uniforms depend only on the ray
      * index, so the summed image is identical for any G */
-    for (int d = 0; d < G; ++d) {
-        int64_t lo = job->nrays * d / G, hi = job->nrays * (d + 1) / G;
-        rc = enqueue_trace(g.devs[d], *job, ds, job->first_ray + lo, hi - lo, &launches);
-        if (rc) return rc;
+    /* every device is prepared before the first one is started: a device's timed region then holds its own
+     * launches only, not the host work for the devices after it */
+    for (int pass = G > 1 ? 1 : 3; pass <= 3; pass += (pass == 1 ? 1 : 2)) {
+        for (int d = 0; d < G; ++d) {
+            int64_t lo = job->nrays * d / G, hi = job->nrays * (d + 1) / G;
+            rc = enqueue_trace(g.devs[d], *job, ds, job->first_ray + lo, hi - lo, &launches, pass);
+            if (rc) return rc;
+        }
     }
     /* one reduce of [images | counters] to device 0 / rank 0 */
     bool reduced = false;
