@@ -492,6 +492,7 @@ static bool ring_filter_applies(const ort_job& job, const DevScene& s, bool flat
 /* Slice of the ray range per cull/survivors launch pair: long enough that the tail of a launch
  * is < 1 % of it, short enough that the list of ray indices stays a few hundred MB. */
 static const int64_t ORT_RING_SLICE = (int64_t)1 << 29;
+static_assert(ORT_RING_SLICE <= ((int64_t)1 << ORT_LIST_ID_BITS), "a list entry keeps its ray index in ORT_LIST_ID_BITS bits");
 
 /* The survivors list of one lane: at most the rays that pass stage A land on it -- Binomial(slice, p),
  * p = aim_cut / 2^64, standard deviation <= sqrt(slice) / 2; capacity = expectation + 8 sqrt(slice) >= 16
@@ -556,6 +557,8 @@ static int enqueue_ring_filter(DeviceCtx& c, Lane& L, const ort_job& job, const 
 
     DevSceneT<float> sf;
     ort_scene_to_float(s, sf);
+    OrtfParamsT<OrtfV2> fp; /* every constant of the filter, twice: one 64-bit operand for two rays */
+    ortf_make_params<OrtfV2>(sf, K, job.iris_before, fp);
     /* cull(k) runs on the lane's stream, survivors(k) on its second one behind it, so that the small
      * fp64 kernel fills the tail of cull(k+1) instead of standing between two cull kernels; the
      * two list buffers alternate, and cull(k+2) waits until survivors(k) has read its buffer */
@@ -572,7 +575,7 @@ static int enqueue_ring_filter(DeviceCtx& c, Lane& L, const ort_job& job, const 
         int grid = c.num_sms * occ_cull;
         int gsz = (int)(want < grid ? (want > 0 ? want : 1) : grid);
         if (k >= 2) CK(cudaStreamWaitEvent(L.stream, L.ev_surv[buf], 0));
-        cull<<<gsz, ORT_TPB, smem_cull, L.stream>>>(sf, K, dj, list, L.d_nlist + k, (unsigned)capacity, d_cnt);
+        cull<<<gsz, ORT_TPB, smem_cull, L.stream>>>(fp, dj, list, L.d_nlist + k, (unsigned)capacity, d_cnt);
         CK(cudaGetLastError());
         CK(cudaEventRecord(L.ev_cull[buf], L.stream));
         /* the list length is only known on the device: size the grid for the longest list there can
@@ -582,7 +585,7 @@ static int enqueue_ring_filter(DeviceCtx& c, Lane& L, const ort_job& job, const 
         int sgrid = c.num_sms * occ_surv;
         int sgsz = (int)(sb < sgrid ? (sb > 0 ? sb : 1) : sgrid);
         CK(cudaStreamWaitEvent(L.stream2, L.ev_cull[buf], 0));
-        surv<<<sgsz, ORT_TPB, smem_surv, L.stream2>>>(s, sf, K, dj, list, L.d_nlist + k, (unsigned)capacity, d_img, d_cnt);
+        surv<<<sgsz, ORT_TPB, smem_surv, L.stream2>>>(s, dj, list, L.d_nlist + k, (unsigned)capacity, d_img, d_cnt);
         CK(cudaGetLastError());
         CK(cudaEventRecord(L.ev_surv[buf], L.stream2));
         *launches += 2;

@@ -239,7 +239,7 @@ __device__ __forceinline__ OrtQuadRange ort_quad_range(const DevJob& J) {
     q.cut_hi = (uint32_t)(J.aim_cut >> 32);
     return q;
 }
-template <typename EdgeFn>
+template <int CAP = ORT_QUAD_QCAP, typename EdgeFn>
 __device__ __forceinline__ unsigned ort_ring_quads_pass(const DevJob& J, const OrtQuadRange& Q, uint32_t b, uint2* q, int& n0,
                                                         unsigned lane, EdgeFn on_edge) {
     unsigned below;
@@ -265,7 +265,7 @@ __device__ __forceinline__ unsigned ort_ring_quads_pass(const DevJob& J, const O
             const unsigned m = __ballot_sync(ORT_FULL, pass);
             if (pass) {
                 int p = n0 + __popc(m & below);
-                ORT_ASSERT(p >= 0 && p < ORT_QUAD_QCAP);
+                ORT_ASSERT(p >= 0 && p < CAP);
                 q[p] = make_uint2(w[k], quad * 4u + (uint32_t)k - Q.mis);
             }
             n0 += __popc(m);
@@ -282,7 +282,7 @@ __device__ __forceinline__ unsigned ort_ring_quads_pass(const DevJob& J, const O
             nvalid += __popc(__ballot_sync(ORT_FULL, valid));
             if (pass) {
                 int p = n0 + __popc(m & below);
-                ORT_ASSERT(p >= 0 && p < ORT_QUAD_QCAP);
+                ORT_ASSERT(p >= 0 && p < CAP);
                 q[p] = make_uint2(w[k], id);
             }
             n0 += __popc(m);
@@ -673,10 +673,14 @@ ort_trace_scatter_kernel(const __grid_constant__ DevSceneT<R> S, const __grid_co
  * and the survivors kernel compares the filter's verdict with what fp64 finds:
  * counters[ORT_FILTER_SLOT_CALLED] = rays the filter called, counters[ORT_FILTER_SLOT_WRONG] =
  * calls that disagree with fp64 (must stay 0). */
+#define ORT_CULL_QCAP (64 + 32 * ORT_QUAD) /* < 64 leftovers + the survivors of one stage-A pass */
 struct SlimQueue {
-    uint2 e[ORT_QUAD_QCAP]; /* x: high word of the aim-disc r^2 draw (what stage A tested), y: ray index */
-    uint32_t hb[64];        /* ray indices on their way to the survivors list */
+    uint2 e[ORT_CULL_QCAP]; /* x: high word of the aim-disc r^2 draw (what stage A tested), y: ray index */
+    uint32_t hb[128];       /* list entries on their way to global memory */
 };
+/* VERIFY: a list entry carries the filter's verdict above the ray index (a slice has <= 2^29 rays) */
+#define ORT_LIST_ID_BITS 29
+#define ORT_LIST_ID_MASK ((1u << ORT_LIST_ID_BITS) - 1u)
 
 /* `count` (<= 32, warp-uniform) entries, one per lane, to the end of the global list */
 __device__ __forceinline__ void ort_list_append(uint32_t* __restrict__ list, unsigned* __restrict__ nlist,
@@ -697,16 +701,17 @@ __device__ __forceinline__ void ort_tally(unsigned& c, int st) {
 }
 
 #ifndef ORT_CULL_MIN_BLOCKS
-#define ORT_CULL_MIN_BLOCKS 6
+#define ORT_CULL_MIN_BLOCKS 3 /* 80 registers: two rays per lane; 4 blocks (64 registers) spill and are slower */
 #endif
 /* list[0 .. *nlist) receives the ray indices (relative to J.first_ray) handed to fp64; entries that
  * would not fit in `capacity` are counted in counters[ORT_FILTER_SLOT_OVERFLOW] instead, which
- * ort_trace reports as an error (the launcher sizes the list 16 sigma above its expectation). */
+ * ort_trace reports as an error (the launcher sizes the list 16 sigma above its expectation).
+ * A filter pass takes 64 rays, TWO per lane (ortf_filter<OrtfTwo>: packed f32x2 arithmetic). */
 template <bool VERIFY>
 __global__ void __launch_bounds__(ORT_TPB, ORT_CULL_MIN_BLOCKS)
-ort_ring_cull_kernel(const __grid_constant__ DevSceneT<float> F, const __grid_constant__ DevFilter K,
-                     const __grid_constant__ DevJob J, uint32_t* __restrict__ list, unsigned* __restrict__ nlist,
-                     const unsigned capacity, unsigned long long* __restrict__ counters) {
+ort_ring_cull_kernel(const __grid_constant__ OrtfParamsT<OrtfV2> K, const __grid_constant__ DevJob J,
+                     uint32_t* __restrict__ list, unsigned* __restrict__ nlist, const unsigned capacity,
+                     unsigned long long* __restrict__ counters) {
     extern __shared__ __align__(16) unsigned char ort_smem[];
     SlimQueue& q0 = reinterpret_cast<SlimQueue*>(ort_smem)[threadIdx.x >> 5];
     const unsigned lane = threadIdx.x & 31u;
@@ -720,40 +725,71 @@ ort_ring_cull_kernel(const __grid_constant__ DevSceneT<float> F, const __grid_co
     int n0 = 0;
     uint32_t b = gwarp;
     for (;;) {
-        const bool emit = n0 < 32 && b < Q.npasses;
+        const bool emit = n0 < 64 && b < Q.npasses;
         if (!emit && n0 == 0) break;
         if (emit) {
             /* a draw whose high word EQUALS the cut's goes on: it sits on the aperture edge, where the
              * filter hands it to fp64, and ort_l2_enter there makes the exact call */
-            c9 += ort_ring_quads_pass(J, Q, b, q0.e, n0, lane, [](uint32_t, uint32_t) { return true; });
+            c9 += ort_ring_quads_pass<ORT_CULL_QCAP>(J, Q, b, q0.e, n0, lane, [](uint32_t, uint32_t) { return true; });
             b += nwarps;
         } else {
-            uint2 e = make_uint2(0u, 0u);
-            bool act = ort_quads_pop(q0.e, n0, e, lane);
-            const uint32_t id = e.y;
-            int st = -1;
-            if (act) {
-                OrtRng g = ort_make_rng_prod(J, id);
-                st = VERIFY ? 0 : ort_ring_filter(F, K, J, g, e.x);
+            const int cnt = n0 < 64 ? n0 : 64;
+            const int base = n0 - cnt;
+            const bool act0 = (int)lane < cnt, act1 = (int)lane + 32 < cnt;
+            uint2 e0 = make_uint2(65536u, 0u), e1 = make_uint2(65536u, 0u);
+            ORT_ASSERT(base >= 0 && base + cnt <= ORT_CULL_QCAP);
+            if (act0) e0 = q0.e[base + lane];
+            if (act1) e1 = q0.e[base + 32 + lane];
+            n0 = base;
+            __syncwarp();
+            int sa, sb;
+            {
+                /* blocks 0 and 1 of both rays (an idle half runs on ray 0: its result is dropped) */
+                uint32_t a0[4], b0[4], a1[4], b1[4];
+                const OrtRng g0 = ort_make_rng_prod(J, e0.y), g1 = ort_make_rng_prod(J, e1.y);
+                ort_block(g0, 0u, a0);
+                ort_block(g0, 1u, b0);
+                ort_block(g1, 0u, a1);
+                ort_block(g1, 1u, b1);
+                const OrtfS2 st = ortf_filter<OrtfTwo>(K, make_uint2(a0[1], a1[1]), make_uint2(a0[2], a1[2]), make_uint2(a0[3], a1[3]),
+                                                       make_uint2(b0[2], b1[2]), make_uint2(b0[3], b1[3]), make_uint2(e0.x, e1.x));
+                sa = st.a;
+                sb = st.b;
+            }
+            sa = act0 ? sa : -1;
+            sb = act1 ? sb : -1;
+            if (!VERIFY) {
                 /* one compare + one predicated add per status (left to itself the compiler builds
                  * add / conditional move / move triples here) */
-                ort_tally<ORT_ST_L2_SPHERE_MISS>(c10, st);
-                ort_tally<ORT_ST_L2_CURVED_REFLECT>(c11, st);
-                ort_tally<ORT_ST_L3_IRIS_BEFORE>(c12, st);
-                ort_tally<ORT_ST_L3_S1_MISS>(c13, st);
-                ort_tally<ORT_ST_L3_APERTURE>(c14, st);
+                ort_tally<ORT_ST_L2_SPHERE_MISS>(c10, sa);
+                ort_tally<ORT_ST_L2_CURVED_REFLECT>(c11, sa);
+                ort_tally<ORT_ST_L3_IRIS_BEFORE>(c12, sa);
+                ort_tally<ORT_ST_L3_S1_MISS>(c13, sa);
+                ort_tally<ORT_ST_L3_APERTURE>(c14, sa);
+                ort_tally<ORT_ST_L2_SPHERE_MISS>(c10, sb);
+                ort_tally<ORT_ST_L2_CURVED_REFLECT>(c11, sb);
+                ort_tally<ORT_ST_L3_IRIS_BEFORE>(c12, sb);
+                ort_tally<ORT_ST_L3_S1_MISS>(c13, sb);
+                ort_tally<ORT_ST_L3_APERTURE>(c14, sb);
             }
-            /* rays for fp64: parked in a warp-private buffer and written to the list 32 at a time
-             * (one atomic and one coalesced store per 32 entries) */
-            const unsigned m = __ballot_sync(ORT_FULL, st == 0);
-            if (st == 0) {
-                int p = nh + __popc(m & below);
-                ORT_ASSERT(p >= 0 && p < 64);
-                q0.hb[p] = id;
+            /* rays for fp64 (VERIFY: every ray, with the verdict above its index): parked in a warp-private
+             * buffer and written to the list 32 at a time (one atomic and one coalesced store per 32 entries) */
+            const bool l0 = VERIFY ? act0 : sa == 0, l1 = VERIFY ? act1 : sb == 0;
+            const unsigned m0 = __ballot_sync(ORT_FULL, l0), m1 = __ballot_sync(ORT_FULL, l1);
+            if (l0) {
+                int p = nh + __popc(m0 & below);
+                ORT_ASSERT(p >= 0 && p < 128);
+                q0.hb[p] = VERIFY ? (e0.y | ((uint32_t)(sa > 0 ? sa - 9 : 0) << ORT_LIST_ID_BITS)) : e0.y;
             }
-            nh += __popc(m);
+            nh += __popc(m0);
+            if (l1) {
+                int p = nh + __popc(m1 & below);
+                ORT_ASSERT(p >= 0 && p < 128);
+                q0.hb[p] = VERIFY ? (e1.y | ((uint32_t)(sb > 0 ? sb - 9 : 0) << ORT_LIST_ID_BITS)) : e1.y;
+            }
+            nh += __popc(m1);
             __syncwarp();
-            if (nh >= 32) {
+            while (nh >= 32) {
                 nh -= 32;
                 ort_list_append(list, nlist, capacity, counters, q0.hb[nh + lane], 32u, lane);
                 __syncwarp();
@@ -778,8 +814,7 @@ struct SurvShared {
 };
 template <bool VERIFY>
 __global__ void __launch_bounds__(ORT_TPB, ORT_MIN_BLOCKS)
-ort_ring_survivors_kernel(const __grid_constant__ DevSceneT<double> S, const __grid_constant__ DevSceneT<float> F,
-                          const __grid_constant__ DevFilter K, const __grid_constant__ DevJob J, const uint32_t* __restrict__ list,
+ort_ring_survivors_kernel(const __grid_constant__ DevSceneT<double> S, const __grid_constant__ DevJob J, const uint32_t* __restrict__ list,
                           const unsigned* __restrict__ nlist, const unsigned capacity,
                           unsigned long long* __restrict__ img, unsigned long long* __restrict__ counters) {
     extern __shared__ __align__(16) unsigned char ort_smem[];
@@ -805,10 +840,13 @@ ort_ring_survivors_kernel(const __grid_constant__ DevSceneT<double> S, const __g
             int st = -1, verdict = 0;
             if (i < total) {
                 id = list[i];
+                if (VERIFY) { /* the verdict the cull kernel's filter reached, above the ray index */
+                    const uint32_t code = id >> ORT_LIST_ID_BITS;
+                    verdict = code ? (int)code + 9 : 0;
+                    id &= ORT_LIST_ID_MASK;
+                }
                 OrtRng g = ort_make_rng_prod(J, id);
                 const uint32_t hi = ort_aim_hi(g);
-                /* exactly the word the cull kernel hands the filter */
-                if (VERIFY) verdict = ort_ring_filter(F, K, J, g, hi);
                 r.px = r.py = r.pz = r.dx = r.dy = r.dz = 0.0;
                 st = ort_stage_b<ORT_PHASE_RING, ORT_SRC_POINT>(S, J, g, r, 0u, hi);
             }
