@@ -6,7 +6,7 @@
  * aperture test (total reflection in L2, no intersection with L3's first sphere, outside L3's
  * aperture): they add one to a status counter and nothing else.  WHICH counter is a chain of sign
  * decisions -- discriminants, aperture radii, the reflect-or-refract draw against the Fresnel
- * reflectance.  ort_ring_filter walks source -> L2 -> L3's first surface in fp32 (one issue slot per
+ * reflectance.  ortf_filter walks source -> L2 -> L3's first surface in fp32 (one issue slot per
  * FFMA instead of a multi-cycle DFMA, one MUFU per rcp / rsqrt / sin / cos) and returns
  *     s > 0 : the ray ends with status s -- PROVABLY what the fp64 path decides;
  *     0     : the ray survives to L3, or some decision could not be proved -> the caller traces it

@@ -6,7 +6,8 @@
  *                                    the live rays between surfaces, warp-aggregated 64-bit
  *                                    reductions into the detector image.
  *   ort_ring_cull_kernel             the ring loop's first kernel: integer aim-point test + the
- *                                    single-precision culling filter; no fp64, 48 warps per SM.
+ *                                    single-precision culling filter on two rays per lane (packed
+ *                                    f32x2 arithmetic); no fp64.
  *   ort_ring_survivors_kernel        fp64 stages over the ray indices the cull kernel lists.
  *   ort_trace_flat_kernel<...>       the same path without compaction (diagnostic / evidence).
  *   ort_volume_kernel                makeImage3D (opt-in volume image).
@@ -659,10 +660,11 @@ ort_trace_scatter_kernel(const __grid_constant__ DevSceneT<R> S, const __grid_co
  * Two kernels per slice of the ray range, because 99 % of the ring rays never need fp64 and a
  * kernel that contains the fp64 stages pays their 80 registers on every warp:
  *
- *   ort_ring_cull_kernel       integer + fp32 only, ~40 registers, 6 blocks (48 warps) per SM.
- *       A: Philox block 1 on the ray index; the aim-point aperture test on the raw 64-bit draw
- *          (aim_cut, see ort_ring_aim_cut) ends 69 % of the rays;
- *       F: the single-precision filter on the compacted survivors; the rays it can call are counted,
+ *   ort_ring_cull_kernel       integer + fp32 only, 80 registers, 3 blocks (24 warps) per SM.
+ *       A: one Philox block per FOUR rays (ort_ring_quads_pass): the aim-point aperture test on the high
+ *          word of the raw draw (aim_cut, see ort_ring_aim_cut) ends 69 % of the rays;
+ *       F: the single-precision filter on the compacted survivors, 64 per pass -- two per lane, in
+ *          packed f32x2 arithmetic (ortf_filter<OrtfTwo>); the rays it can call are counted,
  *          the others (they reach L3, or a decision was too close) are appended to a list of ray
  *          indices in global memory -- 4 bytes per listed ray, ~0.2 % .. 4 % of the rays.
  *   ort_ring_survivors_kernel  the ordinary fp64 stages B and C over that list (the draws are
@@ -670,7 +672,8 @@ ort_trace_scatter_kernel(const __grid_constant__ DevSceneT<R> S, const __grid_co
  *
  * Used when the scene has ring_shortcut, precision is 64 and ORT_FLAG_NO_FILTER is not set; the
  * results are identical to ort_trace_kernel's.  VERIFY (ORT_FLAG_VERIFY_FILTER): F lists every ray
- * and the survivors kernel compares the filter's verdict with what fp64 finds:
+ * (with the verdict of its filter above the ray index) and the survivors kernel compares that verdict with
+ * what fp64 finds:
  * counters[ORT_FILTER_SLOT_CALLED] = rays the filter called, counters[ORT_FILTER_SLOT_WRONG] =
  * calls that disagree with fp64 (must stay 0). */
 #define ORT_CULL_QCAP (64 + 32 * ORT_QUAD) /* < 64 leftovers + the survivors of one stage-A pass */
