@@ -270,3 +270,23 @@ def test_cuda_rays_on_the_aperture_cut(ort, orc):
             job32.precision = 32
             _, _, hist32, _ = ort.trace(job32, scene)
             assert int(hist32[..., :27].sum()) == n
+
+
+def test_every_filter_parameter_is_set_and_used():
+    """OrtfParamsT (ort_filter.cuh) is the flat list of constants both lane policies read; a field that
+    ortf_make_params forgets would be an uninitialised kernel parameter."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "opticalraytrace_b200", "csrc", "ort_filter.cuh")).read()
+    a = src.index("struct OrtfParamsT {")
+    body = src[a:src.index("};", a)]
+    fields = []
+    for line in body.split("\n"):
+        m = re.match(r"\s*C\s+(.*);", line.split("/*")[0])
+        if m:
+            fields += [f.strip() for f in m.group(1).split(",")]
+    assert len(fields) > 60
+    assigned = set(re.findall(r"ORTF_SET\((\w+),", src)) - {"field"}
+    used = set(re.findall(r"\bk\.(\w+)", src[src.index("template <typename P, bool FROM_FLAT>"):]))
+    assert set(fields) == assigned
+    assert set(fields) <= used

@@ -7,9 +7,10 @@ the assumed error, and prints per scene the largest |fp32 - exact| / bound per k
 number of bound violations and wrong verdicts (both must be 0), and how many of the rays that pass
 stage A the filter calls.
 
-GPU part (--gpu RAYS): ORT_FLAG_VERIFY_FILTER over RAYS rays per scene on the device -- the survivors
-kernel runs filter AND fp64 on every ray that passes stage A and counts verdicts that differ -- plus
-the exhaustive MUFU error measurement (ort_mufu_selftest).
+GPU part (--gpu RAYS): ORT_FLAG_VERIFY_FILTER over RAYS rays per scene on the device -- the culling
+kernel lists every ray that passes stage A together with the verdict of its own filter (two rays per
+lane, packed arithmetic), the fp64 kernel traces them all and counts verdicts that differ -- plus the
+exhaustive MUFU error measurement (ort_mufu_selftest).
 
     python tools/filter_verify.py [--rays 1000000]
     python tools/filter_verify.py --gpu 300000000000 [--first-ray N] [--only shipped]
