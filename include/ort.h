@@ -218,11 +218,14 @@ typedef struct {
 
 /* ---- lifetime ------------------------------------------------------------------------ */
 /* Single-process mode: drive devices 0..ngpus-1 from this process (ngpus<=0: all visible).
- * `./install.sh -n N` maps to this.  Returns the number of devices in use (>0) or ORT_E*. */
+ * `./install.sh -n N` maps to this.  Returns the number of devices in use (>0) or ORT_E*.
+ * With more than one device it also runs one small reduce, so that NCCL's channels exist before
+ * the first job is timed. */
 int ort_init(int ngpus);
 /* One-process-per-GPU mode (torchrun / MPI style): this process owns `device`; when
  * nranks > 1, `nccl_id` is the 128-byte ncclUniqueId rank 0 got from ort_nccl_unique_id()
- * and distributed by any side channel. */
+ * and distributed by any side channel.  Collective when nranks > 1: every rank calls it (it
+ * creates the communicator and runs one small reduce on it). */
 int ort_init_rank(int device, int rank, int nranks, const void* nccl_id);
 int ort_nccl_unique_id(void* out128);
 int ort_finalize(void);
