@@ -58,8 +58,9 @@ struct WarpQueue {
 };
 /* The queue in front of L2.  Its rays stand on L2's flat face, the plane z = l2_flat_z, so z is not
  * stored; it carries L2's two decision words instead (slots 4 and 5: words 3 of the Philox blocks
- * 0 and 1 the emitting stage generated), so that L2 costs no generator call.  (The ring loop's slim
- * entries use only px, py = the aim draws, and wc.) */
+ * 0 and 1 the emitting stage generated), so that L2 costs no generator call.  (With the aim-plane
+ * shortcut the ring loop keeps its own 8-byte entries -- tested word, ray index -- in this memory:
+ * ort_ring_quads_pass.) */
 template <typename R>
 struct WarpQueueL2 {
     R px[ORT_QCAP], py[ORT_QCAP], dx[ORT_QCAP], dy[ORT_QCAP], dz[ORT_QCAP];
