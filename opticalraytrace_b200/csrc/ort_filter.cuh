@@ -113,7 +113,9 @@ ORT_HD float ortf_word(uint32_t w) {
  *            .rn.f32x2 (FFMA2 & co. on sm_100a: one issue slot does the operation for both rays -- the
  *            culling kernel is bound by instruction issue, and a third of its instructions are these);
  *            comparisons, selects and the MUFU approximations are done per half.
- * Both perform the same IEEE operations in the same order on each ray, so the error analysis is one.
+ * Both perform the same operations in the same order on each ray, so the error analysis is one (where the
+ * compiler fuses a product into the following sum there is one rounding instead of two: (R1) charges each
+ * operation its own, which covers both).
  * Negations are written so that they cost nothing in either form (a constant stored negated, a
  * select that negates, or an explicit multiplication by -1, which is exact). */
 struct OrtfOne {
