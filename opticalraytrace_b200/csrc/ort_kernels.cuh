@@ -677,10 +677,18 @@ ort_trace_scatter_kernel(const __grid_constant__ DevSceneT<R> S, const __grid_co
  * what fp64 finds:
  * counters[ORT_FILTER_SLOT_CALLED] = rays the filter called, counters[ORT_FILTER_SLOT_WRONG] =
  * calls that disagree with fp64 (must stay 0). */
+#ifndef ORT_CULL_TALLY_SMEM
+#define ORT_CULL_TALLY_SMEM 1 /* statuses counted in the warp's shared memory (one ATOMS per ray, LSU pipe) instead of five
+                                 compare + predicated-add pairs per ray on the ALU pipe, which bounds this kernel: +1 %,
+                                 and the five counter registers end the spills at 80 registers */
+#endif
 #define ORT_CULL_QCAP (64 + 32 * ORT_QUAD) /* < 64 leftovers + the survivors of one stage-A pass */
 struct SlimQueue {
     uint2 e[ORT_CULL_QCAP]; /* x: high word of the aim-disc r^2 draw (what stage A tested), y: ray index */
     uint32_t hb[128];       /* list entries on their way to global memory */
+#if ORT_CULL_TALLY_SMEM
+    unsigned hist[ORT_NSTATUS]; /* this warp's histogram of the statuses the filter proved */
+#endif
 };
 /* VERIFY: a list entry carries the filter's verdict above the ray index (a slice has <= 2^29 rays) */
 #define ORT_LIST_ID_BITS 29
@@ -723,6 +731,9 @@ ort_ring_cull_kernel(const __grid_constant__ OrtfParamsT<OrtfV2> K, const __grid
     const uint32_t gwarp = blockIdx.x * ORT_WPB + (threadIdx.x >> 5);
     const OrtQuadRange Q = ort_quad_range(J);
     unsigned c9 = 0, c10 = 0, c11 = 0, c12 = 0, c13 = 0, c14 = 0;
+#if ORT_CULL_TALLY_SMEM
+    ort_hist_clear(q0.hist, lane);
+#endif
     int nh = 0;           /* entries parked in q0.hb */
     unsigned below;       /* lanes below this one */
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(below));
@@ -762,6 +773,12 @@ ort_ring_cull_kernel(const __grid_constant__ OrtfParamsT<OrtfV2> K, const __grid
             }
             sa = act0 ? sa : -1;
             sb = act1 ? sb : -1;
+#if ORT_CULL_TALLY_SMEM
+            if (!VERIFY) {
+                ort_tally_smem(q0.hist, sa, sa > 0);
+                ort_tally_smem(q0.hist, sb, sb > 0);
+            }
+#else
             if (!VERIFY) {
                 /* one compare + one predicated add per status (left to itself the compiler builds
                  * add / conditional move / move triples here) */
@@ -776,6 +793,7 @@ ort_ring_cull_kernel(const __grid_constant__ OrtfParamsT<OrtfV2> K, const __grid
                 ort_tally<ORT_ST_L3_S1_MISS>(c13, sb);
                 ort_tally<ORT_ST_L3_APERTURE>(c14, sb);
             }
+#endif
             /* rays for fp64 (VERIFY: every ray, with the verdict above its index): parked in a warp-private
              * buffer and written to the list 32 at a time (one atomic and one coalesced store per 32 entries) */
             const bool l0 = VERIFY ? act0 : sa == 0, l1 = VERIFY ? act1 : sb == 0;
@@ -801,6 +819,11 @@ ort_ring_cull_kernel(const __grid_constant__ OrtfParamsT<OrtfV2> K, const __grid
         }
     }
     if (nh > 0) ort_list_append(list, nlist, capacity, counters, (int)lane < nh ? q0.hb[lane] : 0u, (unsigned)nh, lane);
+#if ORT_CULL_TALLY_SMEM
+    if (lane == 0 && c9) atomicAdd(q0.hist + ORT_ST_L2_APERTURE, c9);
+    ort_hist_flush(q0.hist, lane, counters);
+    return;
+#endif
     /* per-lane tallies -> one atomic per status and warp */
     c10 = __reduce_add_sync(ORT_FULL, c10);
     c11 = __reduce_add_sync(ORT_FULL, c11);
