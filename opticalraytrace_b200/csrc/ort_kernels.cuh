@@ -661,7 +661,7 @@ ort_trace_scatter_kernel(const __grid_constant__ DevSceneT<R> S, const __grid_co
  * Two kernels per slice of the ray range, because 99 % of the ring rays never need fp64 and a
  * kernel that contains the fp64 stages pays their 80 registers on every warp:
  *
- *   ort_ring_cull_kernel       integer + fp32 only, 80 registers, 3 blocks (24 warps) per SM.
+ *   ort_ring_cull_kernel       integer + fp32 only, 79 registers, 3 blocks (24 warps) per SM.
  *       A: one Philox block per FOUR rays (ort_ring_quads_pass): the aim-point aperture test on the high
  *          word of the raw draw (aim_cut, see ort_ring_aim_cut) ends 69 % of the rays;
  *       F: the single-precision filter on the compacted survivors, 64 per pass -- two per lane, in
