@@ -657,9 +657,10 @@ ort_trace_scatter_kernel(const __grid_constant__ DevSceneT<R> S, const __grid_co
     ort_hist_flush(ws.hist, lane, counters);
 }
 
-/* ---- ring loop with the fp32 culling filter (ort_ring_filter) ------------------------------
+/* ---- ring loop with the fp32 culling filter (ortf_filter) ---------------------------------
  * Two kernels per slice of the ray range, because 99 % of the ring rays never need fp64 and a
- * kernel that contains the fp64 stages pays their 80 registers on every warp:
+ * kernel that also contained the fp64 stages would carry their registers and code next to the
+ * filter's (which fills its own 79 at two rays per lane):
  *
  *   ort_ring_cull_kernel       integer + fp32 only, 79 registers, 3 blocks (24 warps) per SM.
  *       A: one Philox block per FOUR rays (ort_ring_quads_pass): the aim-point aperture test on the high
