@@ -109,7 +109,7 @@ ORT_HD float ortf_word(uint32_t w) {
 /* ---- lanes --------------------------------------------------------------------------------------
  * The filter is written ONCE, over a policy P that says what a "value" is:
  *   OrtfOne  a float: one ray per lane -- the host harness (bound tests, double twin), documentation;
- *   OrtfTwo  two floats in one 64-bit register: TWO rays per lane, arithmetic as fma / mul / add / sub
+ *   OrtfTwo  two floats in one 64-bit register: TWO rays per lane, arithmetic (on the device) as fma / mul / add / sub
  *            .rn.f32x2 (FFMA2 & co. on sm_100a: one issue slot does the operation for both rays -- the
  *            culling kernel is bound by instruction issue, and a third of its instructions are these);
  *            comparisons, selects and the MUFU approximations are done per half.
@@ -156,93 +156,123 @@ struct OrtfOne {
     static ORT_HD bool first(M a) { return a; }
 };
 
-#ifdef __CUDACC__
+/* two floats in one 64-bit register; on the host (harness: the pair logic under test) the same bits, the
+ * operations done per half */
 struct OrtfV2 { unsigned long long v; };
 struct OrtfM2 { bool a, b; };
 struct OrtfS2 { int a, b; };
-__device__ __forceinline__ OrtfV2 ortf_pk(float a, float b) {
+struct OrtfW2 { uint32_t x, y; };
+ORT_HD OrtfV2 ortf_pk(float a, float b) {
     OrtfV2 r;
+#ifdef __CUDA_ARCH__
     asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(a), "f"(b));
+#else
+    uint32_t x, y;
+    memcpy(&x, &a, 4);
+    memcpy(&y, &b, 4);
+    r.v = ((unsigned long long)y << 32) | x;
+#endif
     return r;
 }
-__device__ __forceinline__ float ortf_lo(OrtfV2 a) {
+ORT_HD float ortf_lo(OrtfV2 a) {
     float x;
+#ifdef __CUDA_ARCH__
     asm("{\n\t.reg .f32 t;\n\tmov.b64 {%0, t}, %1;\n\t}" : "=f"(x) : "l"(a.v));
+#else
+    const uint32_t b = (uint32_t)a.v;
+    memcpy(&x, &b, 4);
+#endif
     return x;
 }
-__device__ __forceinline__ float ortf_hi(OrtfV2 a) {
+ORT_HD float ortf_hi(OrtfV2 a) {
     float y;
+#ifdef __CUDA_ARCH__
     asm("{\n\t.reg .f32 t;\n\tmov.b64 {t, %0}, %1;\n\t}" : "=f"(y) : "l"(a.v));
+#else
+    const uint32_t b = (uint32_t)(a.v >> 32);
+    memcpy(&y, &b, 4);
+#endif
     return y;
 }
 struct OrtfTwo {
     typedef OrtfV2 V;
     typedef OrtfM2 M;
     typedef OrtfS2 S;
-    typedef uint2 W;
+    typedef OrtfW2 W;
     static constexpr bool kTrace = false;
-    static __device__ __forceinline__ V lit(float k) { return ortf_pk(k, k); }
-    static __device__ __forceinline__ V fma(V a, V b, V c) {
+    static ORT_HD V lit(float k) { return ortf_pk(k, k); }
+    static ORT_HD V fma(V a, V b, V c) {
+#ifdef __CUDA_ARCH__
         V r;
         asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
         return r;
+#else
+        return ortf_pk(fmaf(ortf_lo(a), ortf_lo(b), ortf_lo(c)), fmaf(ortf_hi(a), ortf_hi(b), ortf_hi(c)));
+#endif
     }
-    static __device__ __forceinline__ V mul(V a, V b) {
+    static ORT_HD V mul(V a, V b) {
+#ifdef __CUDA_ARCH__
         V r;
         asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
         return r;
+#else
+        return ortf_pk(ortf_lo(a) * ortf_lo(b), ortf_hi(a) * ortf_hi(b));
+#endif
     }
-    static __device__ __forceinline__ V add(V a, V b) {
+    static ORT_HD V add(V a, V b) {
+#ifdef __CUDA_ARCH__
         V r;
         asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
         return r;
+#else
+        return ortf_pk(ortf_lo(a) + ortf_lo(b), ortf_hi(a) + ortf_hi(b));
+#endif
     }
-    static __device__ __forceinline__ V sub(V a, V b) {
+    static ORT_HD V sub(V a, V b) {
+#ifdef __CUDA_ARCH__
         V r;
         asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
         return r;
+#else
+        return ortf_pk(ortf_lo(a) - ortf_lo(b), ortf_hi(a) - ortf_hi(b));
+#endif
     }
-    static __device__ __forceinline__ V neg(V a) { return mul(a, lit(-1.0f)); } /* exact */
-    static __device__ __forceinline__ V abs(V a) { return ortf_pk(fabsf(ortf_lo(a)), fabsf(ortf_hi(a))); }
-    static __device__ __forceinline__ M gt(V a, V b) { return M{ortf_lo(a) > ortf_lo(b), ortf_hi(a) > ortf_hi(b)}; }
-    static __device__ __forceinline__ M lt(V a, V b) { return M{ortf_lo(a) < ortf_lo(b), ortf_hi(a) < ortf_hi(b)}; }
-    static __device__ __forceinline__ M ngt(V a, V b) { return M{!(ortf_lo(a) > ortf_lo(b)), !(ortf_hi(a) > ortf_hi(b))}; }
-    static __device__ __forceinline__ M nlt(V a, V b) { return M{!(ortf_lo(a) < ortf_lo(b)), !(ortf_hi(a) < ortf_hi(b))}; }
-    static __device__ __forceinline__ M abs_ngt(V a, V b) {
+    static ORT_HD V neg(V a) { return mul(a, lit(-1.0f)); } /* exact */
+    static ORT_HD V abs(V a) { return ortf_pk(fabsf(ortf_lo(a)), fabsf(ortf_hi(a))); }
+    static ORT_HD M gt(V a, V b) { return M{ortf_lo(a) > ortf_lo(b), ortf_hi(a) > ortf_hi(b)}; }
+    static ORT_HD M lt(V a, V b) { return M{ortf_lo(a) < ortf_lo(b), ortf_hi(a) < ortf_hi(b)}; }
+    static ORT_HD M ngt(V a, V b) { return M{!(ortf_lo(a) > ortf_lo(b)), !(ortf_hi(a) > ortf_hi(b))}; }
+    static ORT_HD M nlt(V a, V b) { return M{!(ortf_lo(a) < ortf_lo(b)), !(ortf_hi(a) < ortf_hi(b))}; }
+    static ORT_HD M abs_ngt(V a, V b) {
         return M{!(fabsf(ortf_lo(a)) > ortf_lo(b)), !(fabsf(ortf_hi(a)) > ortf_hi(b))};
     }
-    static __device__ __forceinline__ V sel(M m, V a, V b) {
-        return ortf_pk(m.a ? ortf_lo(a) : ortf_lo(b), m.b ? ortf_hi(a) : ortf_hi(b));
-    }
-    static __device__ __forceinline__ V sel_na(M m, V a, V b) {
-        return ortf_pk(m.a ? -ortf_lo(a) : ortf_lo(b), m.b ? -ortf_hi(a) : ortf_hi(b));
-    }
-    static __device__ __forceinline__ M mor(M x, M y) { return M{x.a || y.a, x.b || y.b}; }
-    static __device__ __forceinline__ M mand(M x, M y) { return M{x.a && y.a, x.b && y.b}; }
-    static __device__ __forceinline__ M mnot(M x) { return M{!x.a, !x.b}; }
-    static __device__ __forceinline__ M mfalse() { return M{false, false}; }
-    static __device__ __forceinline__ bool all(M x) { return x.a && x.b; }
-    static __device__ __forceinline__ void sset(S& st, M m, int code) {
+    static ORT_HD V sel(M m, V a, V b) { return ortf_pk(m.a ? ortf_lo(a) : ortf_lo(b), m.b ? ortf_hi(a) : ortf_hi(b)); }
+    static ORT_HD V sel_na(M m, V a, V b) { return ortf_pk(m.a ? -ortf_lo(a) : ortf_lo(b), m.b ? -ortf_hi(a) : ortf_hi(b)); }
+    static ORT_HD M mor(M x, M y) { return M{x.a || y.a, x.b || y.b}; }
+    static ORT_HD M mand(M x, M y) { return M{x.a && y.a, x.b && y.b}; }
+    static ORT_HD M mnot(M x) { return M{!x.a, !x.b}; }
+    static ORT_HD M mfalse() { return M{false, false}; }
+    static ORT_HD bool all(M x) { return x.a && x.b; }
+    static ORT_HD void sset(S& st, M m, int code) {
         st.a = m.a ? code : st.a;
         st.b = m.b ? code : st.b;
     }
-    static __device__ __forceinline__ S snone() { return S{0, 0}; }
-    static __device__ __forceinline__ V rcp(V a) { return ortf_pk(ortf_rcp(ortf_lo(a)), ortf_rcp(ortf_hi(a))); }
-    static __device__ __forceinline__ V rsqrt(V a) { return ortf_pk(ortf_rsqrt(ortf_lo(a)), ortf_rsqrt(ortf_hi(a))); }
-    static __device__ __forceinline__ V sqrt(V a) { return ortf_pk(ortf_sqrt(ortf_lo(a)), ortf_sqrt(ortf_hi(a))); }
-    static __device__ __forceinline__ V word(W w) { return ortf_pk(ortf_word(w.x), ortf_word(w.y)); }
-    static __device__ __forceinline__ void sincos_word(W w, V* s, V* c) {
+    static ORT_HD S snone() { return S{0, 0}; }
+    static ORT_HD V rcp(V a) { return ortf_pk(ortf_rcp(ortf_lo(a)), ortf_rcp(ortf_hi(a))); }
+    static ORT_HD V rsqrt(V a) { return ortf_pk(ortf_rsqrt(ortf_lo(a)), ortf_rsqrt(ortf_hi(a))); }
+    static ORT_HD V sqrt(V a) { return ortf_pk(ortf_sqrt(ortf_lo(a)), ortf_sqrt(ortf_hi(a))); }
+    static ORT_HD V word(W w) { return ortf_pk(ortf_word(w.x), ortf_word(w.y)); }
+    static ORT_HD void sincos_word(W w, V* s, V* c) {
         float s0, c0, s1, c1;
         ortf_sincos_word(w.x, &s0, &c0);
         ortf_sincos_word(w.y, &s1, &c1);
         *s = ortf_pk(s0, s1);
         *c = ortf_pk(c0, c1);
     }
-    static __device__ __forceinline__ M wlt(W w, uint32_t k) { return M{w.x < k, w.y < k}; }
-    static __device__ __forceinline__ float first(V a) { return ortf_lo(a); }
-    static __device__ __forceinline__ bool first(M a) { return a.a; }
+    static ORT_HD M wlt(W w, uint32_t k) { return M{w.x < k, w.y < k}; }
+    static ORT_HD float first(V a) { return ortf_lo(a); }
+    static ORT_HD bool first(M a) { return a.a; }
 };
-#endif
 
 /* Every scene or bound constant the filter touches, in the policy's value type (for OrtfTwo: the float
  * twice, so that it is one 64-bit constant-bank operand).  ortf_make_params fills it from the fp32 scene
@@ -269,13 +299,11 @@ template <> ORT_HD unsigned long long ortf_dup<unsigned long long>(float k) {
     memcpy(&b, &k, 4);
     return ((unsigned long long)b << 32) | b;
 }
-#ifdef __CUDACC__
 template <> ORT_HD OrtfV2 ortf_dup<OrtfV2>(float k) {
     OrtfV2 r;
     r.v = ortf_dup<unsigned long long>(k);
     return r;
 }
-#endif
 template <typename C>
 ORT_HD void ortf_make_params(const DevSceneT<float>& F, const DevFilter& K, int iris_before, OrtfParamsT<C>& q) {
 #define ORTF_SET(field, value) q.field = ortf_dup<C>(value)

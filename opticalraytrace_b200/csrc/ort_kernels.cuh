@@ -767,8 +767,8 @@ ort_ring_cull_kernel(const __grid_constant__ OrtfParamsT<OrtfV2> K, const __grid
                 ort_block(g0, 1u, b0);
                 ort_block(g1, 0u, a1);
                 ort_block(g1, 1u, b1);
-                const OrtfS2 st = ortf_filter<OrtfTwo>(K, make_uint2(a0[1], a1[1]), make_uint2(a0[2], a1[2]), make_uint2(a0[3], a1[3]),
-                                                       make_uint2(b0[2], b1[2]), make_uint2(b0[3], b1[3]), make_uint2(e0.x, e1.x));
+                const OrtfS2 st = ortf_filter<OrtfTwo>(K, OrtfW2{a0[1], a1[1]}, OrtfW2{a0[2], a1[2]}, OrtfW2{a0[3], a1[3]},
+                                                       OrtfW2{b0[2], b1[2]}, OrtfW2{b0[3], b1[3]}, OrtfW2{e0.x, e1.x});
                 sa = st.a;
                 sb = st.b;
             }

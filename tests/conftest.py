@@ -59,6 +59,14 @@ def harness():
         v = np.zeros(n, np.int32)
         shortcut = H.hh_ring_filter(C.byref(job), C.byref(scene), n, v.ctypes.data)
         return v, bool(shortcut)
+    H.hh_ring_filter_pairs.argtypes = [C.POINTER(abi.Job), C.POINTER(abi.Scene), C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
+
+    def ring_filter_pairs(job, scene, n, shift):
+        lo = np.zeros(n, dtype=np.int32)
+        hi = np.zeros(n, dtype=np.int32)
+        H.hh_ring_filter_pairs(C.byref(job), C.byref(scene), n, shift, lo.ctypes.data, hi.ctypes.data)
+        return lo, hi
+    run.ring_filter_pairs = ring_filter_pairs
     H.hh_ring_aim_cut.argtypes = [C.POINTER(abi.Job), C.POINTER(abi.Scene), C.POINTER(C.c_int)]
     H.hh_ring_aim_cut.restype = C.c_uint64
 

@@ -121,6 +121,39 @@ extern "C" int hh_ring_filter(const ort_job* job, const ort_scene* scene, int64_
     return (S.ring_shortcut && K.usable == 2) ? 1 : 0;
 }
 
+/* The filter's two-rays-per-lane instantiation (what the culling kernel runs; here with the packed
+ * operations done per half): ray i in the low half, ray (i + shift) % n in the high half of the same lane.
+ * lo[i] = verdict of ray i, hi[(i + shift) % n] = verdict of its partner; both must equal the one-ray
+ * instantiation's verdict whatever the partner does (ends earlier, ends later, trips a guard, ...). */
+extern "C" int hh_ring_filter_pairs(const ort_job* job, const ort_scene* scene, int64_t n, int64_t shift, int32_t* lo,
+                                    int32_t* hi) {
+    DevScene S;
+    DevJob J;
+    ort_flatten_scene(*scene, *job, S);
+    ort_make_dev_job(*job, 1, job->first_ray, n, J);
+    DevSceneT<float> F;
+    ort_scene_to_float(S, F);
+    DevFilter K;
+    ort_make_filter(S, job->iris_before != 0, K);
+    OrtfParamsT<OrtfV2> P;
+    ortf_make_params<OrtfV2>(F, K, J.iris_before, P);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t j = (i + shift) % n;
+        OrtRng g0 = harness_rng(J, i), g1 = harness_rng(J, j);
+        uint32_t a0[4], b0[4], a1[4], b1[4];
+        ort_block(g0, 0u, a0);
+        ort_block(g0, 1u, b0);
+        ort_block(g1, 0u, a1);
+        ort_block(g1, 1u, b1);
+        const OrtfS2 st = ortf_filter<OrtfTwo>(P, OrtfW2{a0[1], a1[1]}, OrtfW2{a0[2], a1[2]}, OrtfW2{a0[3], a1[3]},
+                                               OrtfW2{b0[2], b1[2]}, OrtfW2{b0[3], b1[3]}, OrtfW2{ort_aim_hi(g0), ort_aim_hi(g1)});
+        lo[i] = st.a;
+        hi[j] = st.b;
+    }
+    return (S.ring_shortcut && K.usable == 2) ? 1 : 0;
+}
+
 /* ---- double-precision twin of ort_ring_filter: the same quantities, from the exact draws and the
  * fp64 scene, recorded under the same tags ----------------------------------------------------- */
 struct TwinRec { double v[3]; };

@@ -290,3 +290,39 @@ def test_every_filter_parameter_is_set_and_used():
     used = set(re.findall(r"\bk\.(\w+)", src[src.index("template <typename P, bool FROM_FLAT>"):]))
     assert set(fields) == assigned
     assert set(fields) <= used
+
+
+@pytest.mark.parametrize("k", range(len(RING_SETUPS)))
+def test_two_rays_per_lane_equal_one_ray_per_lane(orc, harness, k):
+    """The culling kernel runs the filter on two rays per lane (ortf_filter<OrtfTwo>).  A ray's verdict must
+    not depend on its lane partner -- a partner that ends earlier, later, or trips a guard -- nor on which
+    half it sits in: for several pairings, both halves give the one-ray instantiation's verdict on every
+    ray that passes stage A.  (Host build: the packed operations are done per half; the masks, the exits
+    and the selects under test are the device's.)"""
+    files, kw = RING_SETUPS[k]
+    scene = cases.scene_for(orc, files, 1)
+    n = 200_000
+    job = abi.default_job(1, n, first_ray=7 * 10 ** 9 + k, **kw)
+    one, usable = harness.ring_filter(job, scene, n)
+    assert usable
+    passed = one >= 0
+    assert passed.sum() > 0.25 * n
+    for shift in (0, 1, 17, 99_991):
+        lo, hi = harness.ring_filter_pairs(job, scene, n, shift)
+        assert np.array_equal(lo[passed], one[passed]), shift
+        assert np.array_equal(hi[passed], one[passed]), shift
+
+
+@pytest.mark.parametrize("k", range(1, 40, 3))
+def test_two_rays_per_lane_on_random_scenes(orc, harness, k):
+    scene, _, kw = random_case(orc, k)
+    kw.pop("use_bottle")
+    n = 60_000
+    job = abi.default_job(1, n, first_ray=11 * 10 ** 9 + k, **kw)
+    one, usable = harness.ring_filter(job, scene, n)
+    if not usable:
+        pytest.skip("the launcher does not run the filter on this scene")
+    passed = one >= 0
+    for shift in (1, 29_989):
+        lo, hi = harness.ring_filter_pairs(job, scene, n, shift)
+        assert np.array_equal(lo[passed], one[passed]) and np.array_equal(hi[passed], one[passed]), shift
